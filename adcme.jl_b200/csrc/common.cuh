@@ -1,0 +1,284 @@
+// common.cuh — shared host/device plumbing for libadcme_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+#include "../../include/adcme_b200.h"
+
+namespace ab {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+int  fail(int code, const char* fmt, ...);
+
+#define AB_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return ab::fail(AB_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,      \
+                            cudaGetErrorString(e__));                                   \
+    } while (0)
+
+#define AB_TRY(call)                       \
+    do {                                   \
+        int rc__ = (call);                 \
+        if (rc__ != AB_OK) return rc__;    \
+    } while (0)
+
+#define AB_LAUNCH_CHECK()                                                               \
+    do {                                                                                \
+        ab::count_launch();                                                             \
+        cudaError_t e__ = cudaPeekAtLastError();                                        \
+        if (e__ != cudaSuccess)                                                         \
+            return ab::fail(AB_ECUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__,  \
+                            cudaGetErrorString(e__));                                   \
+    } while (0)
+
+// ---------------------------------------------------------------- runtime state
+cudaStream_t stream();        // stream every kernel of this library is launched on
+int          ensure_device(); // lazily binds the device; AB_ECUDA if there is no usable GPU
+int          sm_count();
+void         count_launch();
+double       opt(const char* key, double dflt);
+void         timer_add(int which, double seconds);
+
+// ---------------------------------------------------------------- device memory
+int dev_alloc(void** p, size_t bytes);
+int dev_free(void* p);
+
+template <class T>
+struct DevBuf {
+    T*     p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&)            = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    int alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) count = 1;
+        return dev_alloc((void**)&p, count * sizeof(T));
+    }
+    void release() {
+        if (p) dev_free(p);
+        p = nullptr;
+        n = 0;
+    }
+    T* take() {
+        T* q = p;
+        p    = nullptr;
+        n    = 0;
+        return q;
+    }
+};
+
+bool is_device_ptr(const void* p);
+
+// Input argument that may live on host or device: dev() is always a device pointer.
+template <class T>
+struct In {
+    const T* d = nullptr;
+    DevBuf<T> tmp;
+    int bind(const T* p, size_t count) {
+        if (count == 0 || p == nullptr) { d = p; return AB_OK; }
+        if (is_device_ptr(p)) { d = p; return AB_OK; }
+        AB_TRY(tmp.alloc(count));
+        AB_CUDA(cudaMemcpyAsync(tmp.p, p, count * sizeof(T), cudaMemcpyHostToDevice, stream()));
+        d = tmp.p;
+        return AB_OK;
+    }
+};
+
+// Output argument that may live on host or device; commit() copies back when host.
+template <class T>
+struct Out {
+    T*  d    = nullptr;
+    T*  host = nullptr;
+    size_t n = 0;
+    DevBuf<T> tmp;
+    int bind(T* p, size_t count) {
+        n = count;
+        if (count == 0 || p == nullptr) { d = p; return AB_OK; }
+        if (is_device_ptr(p)) { d = p; return AB_OK; }
+        AB_TRY(tmp.alloc(count));
+        d    = tmp.p;
+        host = p;
+        return AB_OK;
+    }
+    // asynchronous copy-back followed by a stream sync (host memory must be valid on return)
+    int commit() {
+        if (host && n) {
+            AB_CUDA(cudaMemcpyAsync(host, d, n * sizeof(T), cudaMemcpyDeviceToHost, stream()));
+            AB_CUDA(cudaStreamSynchronize(stream()));
+        }
+        return AB_OK;
+    }
+};
+
+// ---------------------------------------------------------------- CSR handle
+struct Csr {
+    int64_t m = 0, n = 0, nnz = 0, T = 0;
+    // CSR proper. colind/values are padded by 8 entries so 16-byte bulk copies may over-read.
+    int32_t* rowptr = nullptr;   // [m+1]
+    int32_t* colind = nullptr;   // [nnz+8]
+    double*  values = nullptr;   // [nnz+8]
+    // triplet bookkeeping (null when the handle was created from CSR: identity map)
+    uint32_t* perm     = nullptr; // [T]  sorted position -> input triplet
+    uint32_t* segstart = nullptr; // [nnz+1] first sorted position of each stored entry
+    int32_t*  slot     = nullptr; // [T]  input triplet -> stored entry
+    int32_t*  entry_row = nullptr; // [nnz] row of each stored entry (lazy)
+    // SpMV tiling facts (computed at finalize)
+    int32_t max_tile_nnz[3] = {0, 0, 0};   // max nnz over 256- / 128- / 64-row tiles
+    int32_t max_row_nnz  = 0;
+    // Jacobi: 1/diag (1 where the diagonal is absent or zero), lazy
+    double* dinv = nullptr;
+    bool    dinv_valid = false;
+    // cached transpose (lazy): handle id of A', and map tperm (A' entry -> A entry)
+    int64_t   th    = 0;
+    uint32_t* tperm = nullptr;
+    // solver workspace (lazy): 8 vectors of length max(m,n) + scalars
+    double* work = nullptr;
+    size_t  work_len = 0;
+    void*   scal = nullptr;       // device SolveScal block (solver.cu)
+    double* partials = nullptr;   // reduction partials
+    uint32_t* ticket = nullptr;   // last-block tickets
+    void* graph_cache = nullptr;
+    ~Csr();
+};
+
+Csr*    csr_get(int64_t h);       // nullptr + error set when unknown
+int64_t csr_put(Csr* c);
+int     csr_erase(int64_t h);
+int     csr_finalize(Csr* c);     // computes tiling facts after rowptr/colind/values are in place
+int     csr_ensure_dinv(Csr* c);
+int     csr_ensure_entry_row(Csr* c);
+int     csr_ensure_transpose(Csr* c, Csr** out);
+int     csr_ensure_work(Csr* c, size_t nvec);
+std::mutex& big_lock();
+
+// ---------------------------------------------------------------- primitives (assemble.cu)
+// exclusive prefix sum of uint32 (in -> out, may alias); total written to *d_total (device) if non-null
+int scan_exclusive_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* d_total);
+// stable LSD radix sort of 64-bit keys (bits [0,nbits)) carrying a 32-bit payload
+int radix_sort_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
+                   size_t n, int nbits, uint64_t** keys_out, uint32_t** vals_out);
+
+// ---------------------------------------------------------------- spmv.cu
+// y = A x.  When dotvec != nullptr the launch also produces dot_result[0] = <y, dotvec> and
+// dot_result[1] = <y, y> (deterministic two-stage reduction through partials/ticket).
+// done_flag (device int, may be null): the kernel is a no-op when *done_flag != 0.
+constexpr int MAX_REDUCE_GRID = 8192;   // partials buffers hold NV * MAX_REDUCE_GRID doubles
+int launch_spmv(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
+                double* partials, uint32_t* ticket, const int* done_flag);
+int launch_spmm(const Csr* c, const double* X, int64_t k, double* Y);
+
+}  // namespace ab
+
+// ---------------------------------------------------------------- device helpers
+#ifdef __CUDACC__
+namespace abd {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum; result valid in thread 0. `sh` must hold >= 32 doubles.
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (w == 0) {
+        r = (lane < THREADS / 32) ? sh[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}
+
+// Deterministic grid reduction: each block stores its partial, the last block to arrive
+// (ticket counter) sums all partials in a fixed order and calls fin(total).
+// Must be called by all threads of the block; `mine` valid in thread 0.
+template <int THREADS, int NV, class Fin>
+__device__ __forceinline__ void grid_reduce(const double (&mine)[NV], double* partials,
+                                            uint32_t* ticket, double* sh, Fin fin) {
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) partials[(size_t)k * gridDim.x + blockIdx.x] = mine[k];
+        __threadfence();
+        uint32_t t = atomicAdd(ticket, 1u);
+        s_last     = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double tot[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double a = 0.0;
+            const volatile double* pk = partials + (size_t)k * gridDim.x;
+            for (unsigned i = threadIdx.x; i < gridDim.x; i += THREADS) a += pk[i];
+            tot[k] = block_sum<THREADS>(a, sh);
+        }
+        if (threadIdx.x == 0) {
+            *ticket = 0;   // re-arm for the next launch
+            fin(tot);
+        }
+    }
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA unit, SASS: UBLKCP) -------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; dst, src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+__device__ __forceinline__ double2 ldg_stream_d2(const double2* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+
+}  // namespace abd
+#endif

@@ -1,0 +1,583 @@
+// solver.cu — the sparse `\` : Jacobi-preconditioned CG and BiCGSTAB, and the adjoint solve.
+//
+// Replaces SparseSolver / SparseSolverGrad (deps/CustomOps/SparseSolver/SparseSolver.h:13-70)
+// and Solve / SolveGrad (deps/CustomOps/SparseFactorizationSolve/Solve/Solve.h:3-33):
+//     forward  u = A^{-1} f
+//     backward x = A^{-T} grad_u ; grad_f = x ; grad_vv[k] = -x[ii_k] * u[jj_k]  (per input triplet)
+// The reference factorises with Eigen; here the same linear systems are solved iteratively
+// (the reference documents that other solvers are admissible behind the op signature,
+// docs/src/tu_customop.md:28-36,120-121).  Parity is on the solution, not on iteration counts.
+//
+// All scalars of the recurrences (rho, alpha, beta, omega, residual norms, flags) live in device
+// memory; a whole chunk of iterations is enqueued without a host round trip, the host only polls
+// the `done` flag between chunks.  Every inner product is fused into the kernel that produces
+// its operand (SpMV + <p,Ap>; axpy updates + <r,z>,<r,r>) and reduced with a fixed-order
+// two-stage reduction (no floating-point atomics), so a solve is bit-reproducible.
+//
+// CG iteration = 3 launches:   K1  Ap = A p, pAp            (spmv.cu)
+//                              K2  x += a p, r -= a Ap, rz' = <r, D^-1 r>, rr = <r,r>
+//                              K3  p = D^-1 r + b p
+// Algorithmic bytes / iteration: 12*nnz + 4*(N+1) + 13*8*N.
+#include "common.cuh"
+#include <string>
+#include <map>
+#include <list>
+#include <math.h>
+
+#include "cg_kernels.cuh"
+
+namespace ab {
+
+// ---------------------------------------------------------------- Jacobi diagonal
+__global__ void dinv_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                            const double* __restrict__ values, int64_t m, int64_t col_shift,
+                            double* __restrict__ dinv) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    double d = 0.0;
+    for (int j = rowptr[r]; j < rowptr[r + 1]; ++j)
+        if (colind[j] == r + col_shift) d += values[j];
+    dinv[r] = (d != 0.0 && isfinite(d)) ? 1.0 / d : 1.0;
+}
+
+int csr_ensure_dinv(Csr* c) {
+    if (c->dinv_valid) return AB_OK;
+    if (!c->dinv) AB_TRY(dev_alloc((void**)&c->dinv, (size_t)(c->m + 2) * sizeof(double)));
+    if (c->m) {
+        dinv_kernel<<<(unsigned)((c->m + 255) / 256), 256, 0, stream()>>>(c->rowptr, c->colind, c->values, c->m, 0, c->dinv);
+        AB_LAUNCH_CHECK();
+    }
+    c->dinv_valid = true;
+    return AB_OK;
+}
+
+static size_t work_stride(const Csr* c) {
+    size_t len = (size_t)(c->m > c->n ? c->m : c->n);
+    if (len == 0) len = 1;
+    return (len + 1) & ~(size_t)1;   // keeps every work vector 16-byte aligned
+}
+
+int csr_ensure_work(Csr* c, size_t nvec) {
+    const size_t stride = work_stride(c);
+    if (c->work_len < nvec * stride) {
+        dev_free(c->work);
+        c->work = nullptr;
+        AB_TRY(dev_alloc((void**)&c->work, nvec * stride * sizeof(double)));
+        c->work_len = nvec * stride;
+    }
+    if (!c->scal) {
+        AB_TRY(dev_alloc((void**)&c->scal, sizeof(SolveScal)));
+        AB_CUDA(cudaMemsetAsync(c->scal, 0, sizeof(SolveScal), stream()));
+        AB_TRY(dev_alloc((void**)&c->partials, (size_t)4 * MAX_REDUCE_GRID * sizeof(double)));
+        AB_TRY(dev_alloc((void**)&c->ticket, 4 * sizeof(uint32_t)));
+        AB_CUDA(cudaMemsetAsync(c->ticket, 0, 4 * sizeof(uint32_t), stream()));
+    }
+    return AB_OK;
+}
+double* work_vec(Csr* c, int i) { return c->work + (size_t)i * work_stride(c); }
+
+// ---------------------------------------------------------------- BiCGSTAB kernels (right-preconditioned)
+// r = b ; rhat = b ; p = b ; y = D^-1 p ; x = 0 ; rho = <rhat,r> = bb
+__global__ void __launch_bounds__(EW_THREADS)
+bicg_init_kernel(const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x,
+                 double* __restrict__ r, double* __restrict__ rhat, double* __restrict__ p, double* __restrict__ y,
+                 size_t n, double tol, SolveScal* s, double* partials, uint32_t* ticket) {
+    __shared__ double sh[32];
+    double a1 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        double bi = b[i];
+        x[i] = 0.0; r[i] = bi; rhat[i] = bi; p[i] = bi; y[i] = dinv[i] * bi;
+        a1 = fma(bi, bi, a1);
+    }
+    double mine[1];
+    mine[0] = abd::block_sum<EW_THREADS>(a1, sh);
+    abd::grid_reduce<EW_THREADS, 1>(mine, partials, ticket, sh, [=](const double(&t)[1]) {
+        s->rho = t[0]; s->bb = t[0]; s->rr = t[0];
+        s->alpha = 1.0; s->omega = 1.0;
+        s->thr = tol < 0 ? -1.0 : tol * tol * t[0];
+        s->iters = 0;
+        s->bad = 0;
+        s->breakdown = isfinite(t[0]) ? 0 : 1;
+        s->done = (t[0] == 0.0 || s->breakdown) ? 1 : 0;
+    });
+}
+// after v = A y with dots[0] = <v, rhat>: alpha = rho/<rhat,v> ; s = r - alpha v ; z = D^-1 s ; ss = <s,s>
+__global__ void __launch_bounds__(EW_THREADS)
+bicg_s_kernel(const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
+              double* __restrict__ sv, double* __restrict__ z, size_t n, SolveScal* s, double* partials,
+              uint32_t* ticket) {
+    __shared__ double sh[32];
+    if (s->done) return;
+    const double rv = s->dots[0];
+    const bool bad = (rv == 0.0) || !isfinite(rv) || !isfinite(s->rho);
+    const double alpha = bad ? 0.0 : s->rho / rv;
+    double a0 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        double si = fma(-alpha, v[i], r[i]);
+        sv[i] = si;
+        z[i]  = dinv[i] * si;
+        a0 = fma(si, si, a0);
+    }
+    double mine[1];
+    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
+    abd::grid_reduce<EW_THREADS, 1>(mine, partials, ticket, sh, [=](const double(&t)[1]) {
+        s->alpha = alpha;
+        s->rr = t[0];   // provisional: ||s||^2
+        s->bad = (s->thr >= 0.0 && t[0] <= s->thr) ? 1 : 0;   // s already below tolerance: take the half step
+        if (bad || !isfinite(t[0])) { s->breakdown = 1; s->done = 1; }
+    });
+}
+// after t = A z with dots = {<t,s>, <t,t>}: omega = ts/tt ; x += alpha y + omega z ; r = s - omega t ;
+// rho' = <rhat,r> ; rr = <r,r> ; then beta and the new direction need rho' -> separate kernel.
+__global__ void __launch_bounds__(EW_THREADS)
+bicg_x_kernel(const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ sv,
+              const double* __restrict__ t, const double* __restrict__ rhat, double* __restrict__ x,
+              double* __restrict__ r, size_t n, SolveScal* s, double* partials, uint32_t* ticket) {
+    __shared__ double sh[32];
+    if (s->done) return;
+    const double ts = s->dots[0], tt = s->dots[1];
+    // ||s|| already tiny (tt == 0): take the half step x += alpha y and stop
+    const bool half = (tt == 0.0) || (s->bad != 0);
+    const double omega = half ? 0.0 : ts / tt;
+    const double alpha = s->alpha;
+    double a0 = 0.0, a1 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        double xi = fma(alpha, y[i], x[i]);
+        xi = fma(omega, z[i], xi);
+        double ri = fma(-omega, t[i], sv[i]);
+        x[i] = xi;
+        r[i] = ri;
+        a0 = fma(rhat[i], ri, a0);
+        a1 = fma(ri, ri, a1);
+    }
+    double mine[2];
+    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
+    mine[1] = abd::block_sum<EW_THREADS>(a1, sh);
+    abd::grid_reduce<EW_THREADS, 2>(mine, partials, ticket, sh, [=](const double(&q)[2]) {
+        const double rho_old = s->rho;
+        s->rho = q[0];
+        s->rr  = q[1];
+        s->iters += 1;
+        // beta for the next direction, stored in dots[1] (dots[] are free until the next SpMV)
+        double beta = (q[0] / rho_old) * (alpha / omega);
+        s->dots[1] = beta;
+        s->omega = omega;
+        if (!isfinite(q[0]) || !isfinite(q[1]) || !isfinite(omega)) { s->breakdown = 1; s->done = 1; }
+        else if (s->thr >= 0.0 && q[1] <= s->thr) s->done = 1;
+        else if (half || omega == 0.0 || q[0] == 0.0 || !isfinite(beta)) { s->breakdown = 1; s->done = 1; }
+    });
+}
+// p = r + beta (p - omega v) ; y = D^-1 p
+__global__ void __launch_bounds__(EW_THREADS)
+bicg_p_kernel(const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
+              double* __restrict__ p, double* __restrict__ y, size_t n, const SolveScal* __restrict__ s) {
+    if (s->done) return;
+    const double beta = s->dots[1], omega = s->omega;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        double pi = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+        p[i] = pi;
+        y[i] = dinv[i] * pi;
+    }
+}
+
+// grad_vv[t] = -x[row_t] * u[col_t]
+__global__ void grad_vv_kernel(const int32_t* __restrict__ slot, const int32_t* __restrict__ entry_row,
+                               const int32_t* __restrict__ colind, const double* __restrict__ x,
+                               const double* __restrict__ u, size_t T, double* __restrict__ g) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    int32_t e = slot ? slot[t] : (int32_t)t;
+    g[t] = -x[entry_row[e]] * u[colind[e]];
+}
+
+// ---------------------------------------------------------------- host drivers
+enum Method { M_CG = 0, M_BICGSTAB = 1 };
+
+static int parse_method(const char* method, Method* out) {
+    std::string s = method ? method : "auto";
+    if (s == "CG" || s == "cg" || s == "SimplicialLLT" || s == "SimplicialLDLT") { *out = M_CG; return AB_OK; }
+    if (s == "BiCGSTAB" || s == "bicgstab" || s == "auto" || s == "SparseLU" || s == "SparseQR") { *out = M_BICGSTAB; return AB_OK; }
+    return fail(AB_EINVAL, "unknown sparse solver method '%s'", s.c_str());
+}
+
+static SolveScal* g_hscal = nullptr;   // pinned host mirror
+
+int read_scal(Csr* c, SolveScal* out) {
+    if (!g_hscal) AB_CUDA(cudaMallocHost((void**)&g_hscal, sizeof(SolveScal)));
+    AB_CUDA(cudaMemcpyAsync(g_hscal, c->scal, sizeof(SolveScal), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    *out = *g_hscal;
+    return AB_OK;
+}
+
+// Runs CG on device pointers b -> x (both length n, device).  tol < 0: fixed iteration count.
+static int run_cg(Csr* c, const double* b, double* x, double tol, int maxit, SolveScal* fin) {
+    const size_t n = (size_t)c->m;
+    AB_TRY(csr_ensure_dinv(c));
+    AB_TRY(csr_ensure_work(c, 8));
+    double *r = work_vec(c, 0), *p = work_vec(c, 1), *Ap = work_vec(c, 2);
+    SolveScal* s = (SolveScal*)c->scal;
+    const unsigned g = ew_grid(n);
+    cg_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->dinv, x, r, p, n, tol, s, c->partials, c->ticket, 0);
+    AB_LAUNCH_CHECK();
+    int check = (int)opt("check_every", 0);
+    if (check <= 0) check = n > (size_t)4000000 ? 16 : 64;
+    int it = 0;
+    SolveScal h;
+    while (it < maxit) {
+        int chunk = maxit - it < check ? maxit - it : check;
+        for (int k = 0; k < chunk; ++k, ++it) {
+            const int parity = it & 1;
+            AB_TRY(launch_spmv(c, p, Ap, p, s->dots, c->partials, c->ticket, &s->done));
+            cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, 0);
+            AB_LAUNCH_CHECK();
+            cg_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, c->dinv, p, n, parity, s);
+            AB_LAUNCH_CHECK();
+        }
+        if (tol < 0 && it < maxit) continue;   // fixed-count run: no polling
+        AB_TRY(read_scal(c, &h));
+        if (h.done) break;
+    }
+    AB_TRY(read_scal(c, fin));
+    return AB_OK;
+}
+
+static int run_bicgstab(Csr* c, const double* b, double* x, double tol, int maxit, SolveScal* fin) {
+    const size_t n = (size_t)c->m;
+    AB_TRY(csr_ensure_dinv(c));
+    AB_TRY(csr_ensure_work(c, 8));
+    double *r = work_vec(c, 0), *rhat = work_vec(c, 1), *p = work_vec(c, 2), *v = work_vec(c, 3),
+           *sv = work_vec(c, 4), *t = work_vec(c, 5), *y = work_vec(c, 6), *z = work_vec(c, 7);
+    SolveScal* s = (SolveScal*)c->scal;
+    const unsigned g = ew_grid(n);
+    bicg_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->dinv, x, r, rhat, p, y, n, tol, s, c->partials, c->ticket);
+    AB_LAUNCH_CHECK();
+    int check = (int)opt("check_every", 0);
+    if (check <= 0) check = n > (size_t)4000000 ? 8 : 32;
+    int it = 0;
+    SolveScal h;
+    while (it < maxit) {
+        int chunk = maxit - it < check ? maxit - it : check;
+        for (int k = 0; k < chunk; ++k, ++it) {
+            AB_TRY(launch_spmv(c, y, v, rhat, s->dots, c->partials, c->ticket, &s->done));
+            bicg_s_kernel<<<g, EW_THREADS, 0, stream()>>>(r, v, c->dinv, sv, z, n, s, c->partials, c->ticket);
+            AB_LAUNCH_CHECK();
+            AB_TRY(launch_spmv(c, z, t, sv, s->dots, c->partials, c->ticket, &s->done));
+            bicg_x_kernel<<<g, EW_THREADS, 0, stream()>>>(y, z, sv, t, rhat, x, r, n, s, c->partials, c->ticket);
+            AB_LAUNCH_CHECK();
+            bicg_p_kernel<<<g, EW_THREADS, 0, stream()>>>(r, v, c->dinv, p, y, n, s);
+            AB_LAUNCH_CHECK();
+        }
+        AB_TRY(read_scal(c, &h));
+        if (h.done) break;
+    }
+    AB_TRY(read_scal(c, fin));
+    return AB_OK;
+}
+
+// The vector kernels use 16-byte accesses: a caller buffer that is only 8-byte aligned is bounced.
+static int run_method(Csr* c, Method meth, const double* b, double* x, double tol, int maxit, SolveScal* fin) {
+    DevBuf<double> xal;
+    double* xuser = nullptr;
+    if (((uintptr_t)x & 15) != 0) {
+        AB_TRY(xal.alloc((size_t)c->m + 2));
+        xuser = x;
+        x = xal.p;
+    }
+    AB_TRY((meth == M_CG) ? run_cg(c, b, x, tol, maxit, fin) : run_bicgstab(c, b, x, tol, maxit, fin));
+    if (xuser) AB_CUDA(cudaMemcpyAsync(xuser, x, (size_t)c->m * sizeof(double), cudaMemcpyDeviceToDevice, stream()));
+    return AB_OK;
+}
+
+// true residual ||b - A x|| / ||b|| computed with one extra SpMV (used to vet a BiCGSTAB "breakdown" exit)
+__global__ void __launch_bounds__(EW_THREADS)
+resid_kernel(const double* __restrict__ b, const double* __restrict__ Ax, size_t n, double* out2, double* partials,
+             uint32_t* ticket) {
+    __shared__ double sh[32];
+    double a0 = 0.0, a1 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        double d = b[i] - Ax[i];
+        a0 = fma(d, d, a0);
+        a1 = fma(b[i], b[i], a1);
+    }
+    double mine[2];
+    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
+    mine[1] = abd::block_sum<EW_THREADS>(a1, sh);
+    abd::grid_reduce<EW_THREADS, 2>(mine, partials, ticket, sh, [=](const double(&t)[2]) { out2[0] = t[0]; out2[1] = t[1]; });
+}
+
+static int true_relres(Csr* c, const double* b, const double* x, double* relres) {
+    AB_TRY(csr_ensure_work(c, 8));
+    double* Ax = work_vec(c, 5);
+    SolveScal* s = (SolveScal*)c->scal;
+    AB_TRY(launch_spmv(c, x, Ax, nullptr, nullptr, nullptr, nullptr, nullptr));
+    resid_kernel<<<ew_grid((size_t)c->m), EW_THREADS, 0, stream()>>>(b, Ax, (size_t)c->m, s->dots, c->partials, c->ticket);
+    AB_LAUNCH_CHECK();
+    SolveScal h;
+    AB_TRY(read_scal(c, &h));
+    *relres = h.dots[1] > 0 ? sqrt(h.dots[0] / h.dots[1]) : sqrt(h.dots[0]);
+    return AB_OK;
+}
+
+// Solve A x = b with device pointers.  Shared by forward and adjoint.
+static int solve_dev(Csr* c, Method meth, const double* b, double* x, double tol, int maxit, int* iters,
+                     double* relres) {
+    if (c->m != c->n) return fail(AB_EINVAL, "sparse solve needs a square matrix (got %lld x %lld)", (long long)c->m, (long long)c->n);
+    if (tol <= 0) tol = opt("tol", 1e-12);
+    if (maxit <= 0) maxit = (int)opt("maxit", 0);
+    if (maxit <= 0) { long long mm = 10 * (long long)c->m + 100; maxit = (int)(mm < 200000 ? mm : 200000); }
+    if (c->m == 0) { if (iters) *iters = 0; if (relres) *relres = 0; return AB_OK; }
+    cudaEvent_t e0, e1;
+    AB_CUDA(cudaEventCreate(&e0)); AB_CUDA(cudaEventCreate(&e1));
+    AB_CUDA(cudaEventRecord(e0, stream()));
+    SolveScal fin;
+    int rc = run_method(c, meth, b, x, tol, maxit, &fin);
+    cudaEventRecord(e1, stream());
+    cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    timer_add(AB_TIMER_SOLVE, ms * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != AB_OK) return rc;
+    double rel = fin.bb > 0 ? sqrt(fin.rr / fin.bb) : 0.0;
+    if (iters) *iters = fin.iters;
+    if (relres) *relres = rel;
+    const bool converged = fin.done && !fin.breakdown;
+    if (converged) return AB_OK;
+    // breakdown or maxit: vet with the true residual (BiCGSTAB can "break down" at the solution)
+    double tr = rel;
+    if (isfinite(fin.rr)) {
+        int rc2 = true_relres(c, b, x, &tr);
+        if (rc2 != AB_OK) return rc2;
+        if (relres) *relres = tr;
+        if (isfinite(tr) && tr <= tol * 10) return AB_OK;
+    }
+    if (fin.breakdown)
+        return fail(AB_EBREAKDOWN, "Sparse solver failed: %s breakdown after %d iterations (relres %.3e); matrix singular%s",
+                    meth == M_CG ? "CG" : "BiCGSTAB", fin.iters, tr, meth == M_CG ? " or not SPD" : "");
+    return fail(AB_ENOCONV, "Sparse solver did not converge: %s relres %.3e > tol %.3e after %d iterations",
+                meth == M_CG ? "CG" : "BiCGSTAB", tr, tol, fin.iters);
+}
+
+// ---------------------------------------------------------------- factorize cache (LRU keyed by id)
+struct FactCache {
+    std::list<int64_t> order;                 // most recent first
+    std::map<int64_t, int64_t> id2h;          // id -> CSR handle
+    int64_t next_id = 1;
+    size_t  max_size = 999999;
+};
+static FactCache g_fact;
+static std::mutex g_fact_mu;
+
+}  // namespace ab
+
+using namespace ab;
+
+extern "C" {
+
+int ab_solve(int64_t h, const char* method, const double* f_, double* u_, double tol, int maxit, int* iters,
+             double* relres) {
+    AB_TRY(ensure_device());
+    Csr* c = csr_get(h);
+    if (!c) return AB_EHANDLE;
+    Method meth;
+    AB_TRY(parse_method(method, &meth));
+    if (c->m > 0 && (!f_ || !u_)) return fail(AB_EINVAL, "null vector");
+    std::lock_guard<std::mutex> lk(big_lock());
+    In<double> f; Out<double> u;
+    AB_TRY(f.bind(f_, c->m)); AB_TRY(u.bind(u_, c->m));
+    int rc = solve_dev(c, meth, f.d, u.d, tol, maxit, iters, relres);
+    if (rc == AB_OK || rc == AB_ENOCONV) { int rc2 = u.commit(); if (rc2 != AB_OK) return rc2; }
+    return rc;
+}
+
+int ab_cg_fixed(int64_t h, const double* f_, double* u_, int iters, double* relres) {
+    AB_TRY(ensure_device());
+    Csr* c = csr_get(h);
+    if (!c) return AB_EHANDLE;
+    if (iters < 0 || (c->m > 0 && (!f_ || !u_))) return fail(AB_EINVAL, "bad argument");
+    if (c->m != c->n) return fail(AB_EINVAL, "square matrix required");
+    std::lock_guard<std::mutex> lk(big_lock());
+    In<double> f; Out<double> u;
+    AB_TRY(f.bind(f_, c->m)); AB_TRY(u.bind(u_, c->m));
+    SolveScal fin;
+    AB_TRY(run_method(c, M_CG, f.d, u.d, -1.0, iters, &fin));
+    AB_TRY(u.commit());
+    if (relres) *relres = fin.bb > 0 ? sqrt(fin.rr / fin.bb) : 0.0;
+    if (fin.breakdown) return fail(AB_EBREAKDOWN, "CG breakdown after %d iterations (matrix not SPD?)", fin.iters);
+    return AB_OK;
+}
+
+int ab_solve_grad(int64_t h, const char* method, const double* grad_u_, const double* u_, double* grad_vv_,
+                  double* grad_f_, double tol, int maxit, int* iters, double* relres) {
+    AB_TRY(ensure_device());
+    Csr* c = csr_get(h);
+    if (!c) return AB_EHANDLE;
+    Method meth;
+    AB_TRY(parse_method(method, &meth));
+    if (c->m > 0 && (!grad_u_ || (grad_vv_ && !u_))) return fail(AB_EINVAL, "null vector");
+    std::lock_guard<std::mutex> lk(big_lock());
+    In<double> g, u;
+    AB_TRY(g.bind(grad_u_, c->m));
+    if (grad_vv_) AB_TRY(u.bind(u_, c->m));
+    // x = A^{-T} g.  CG asserts symmetry, so A itself is used; BiCGSTAB goes through the cached A'.
+    Csr* ct = c;
+    if (meth != M_CG) AB_TRY(csr_ensure_transpose(c, &ct));
+    Out<double> gf;
+    DevBuf<double> xtmp;
+    double* x = nullptr;
+    if (grad_f_) { AB_TRY(gf.bind(grad_f_, c->m)); x = gf.d; }
+    else { AB_TRY(xtmp.alloc(c->m)); x = xtmp.p; }
+    AB_TRY(solve_dev(ct, meth, g.d, x, tol, maxit, iters, relres));
+    if (grad_vv_ && c->T > 0) {
+        AB_TRY(csr_ensure_entry_row(c));
+        Out<double> gv;
+        AB_TRY(gv.bind(grad_vv_, c->T));
+        grad_vv_kernel<<<(unsigned)((c->T + 255) / 256), 256, 0, stream()>>>(c->slot, c->entry_row, c->colind, x, u.d, (size_t)c->T, gv.d);
+        AB_LAUNCH_CHECK();
+        AB_TRY(gv.commit());
+    }
+    if (grad_f_) AB_TRY(gf.commit());
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    return AB_OK;
+}
+
+int ab_sparse_solver(const int64_t* ii, const int64_t* jj, const double* vv, int64_t nv, const double* f,
+                     int64_t d, const char* method, double* u) {
+    int64_t h = 0;
+    AB_TRY(ab_csr_from_coo(nv, ii, jj, vv, d, d, 1, &h));
+    int rc = ab_solve(h, method, f, u, 0.0, 0, nullptr, nullptr);
+    ab_csr_destroy(h);
+    return rc;
+}
+
+int ab_sparse_solver_grad(const double* grad_u, const double* u, const int64_t* ii, const int64_t* jj,
+                          const double* vv, int64_t nv, const double* f, int64_t d, const char* method,
+                          double* grad_vv, double* grad_f) {
+    (void)f;
+    int64_t h = 0;
+    AB_TRY(ab_csr_from_coo(nv, ii, jj, vv, d, d, 1, &h));
+    int rc = ab_solve_grad(h, method, grad_u, u, grad_vv, grad_f, 0.0, 0, nullptr, nullptr);
+    ab_csr_destroy(h);
+    return rc;
+}
+
+int ab_factorize(const int64_t* ii, const int64_t* jj, const double* vv, int64_t nv, int64_t d,
+                 int64_t max_cache_size, int64_t* id) {
+    if (!id) return fail(AB_EINVAL, "id is null");
+    int64_t h = 0;
+    AB_TRY(ab_csr_from_coo(nv, ii, jj, vv, d, d, 1, &h));
+    {   // build A', Jacobi diagonals and workspace now: "factorization" cost is paid once
+        std::lock_guard<std::mutex> lk(big_lock());
+        Csr* c = csr_get(h);
+        Csr* t = nullptr;
+        int rc = csr_ensure_transpose(c, &t);
+        if (rc == AB_OK) rc = csr_ensure_dinv(c);
+        if (rc == AB_OK) rc = csr_ensure_dinv(t);
+        if (rc != AB_OK) { csr_erase(h); return rc; }
+    }
+    std::vector<int64_t> evict;
+    {
+        std::lock_guard<std::mutex> lk(g_fact_mu);
+        if (max_cache_size > 0 && (size_t)max_cache_size > 0) g_fact.max_size = (size_t)max_cache_size;
+        int64_t nid = g_fact.next_id++;
+        g_fact.id2h[nid] = h;
+        g_fact.order.push_front(nid);
+        while (g_fact.order.size() > g_fact.max_size) {
+            int64_t old = g_fact.order.back();
+            g_fact.order.pop_back();
+            evict.push_back(g_fact.id2h[old]);
+            g_fact.id2h.erase(old);
+        }
+        *id = nid;
+    }
+    for (int64_t eh : evict) ab_csr_destroy(eh);
+    return AB_OK;
+}
+
+static int fact_lookup(int64_t id, int64_t* h) {
+    std::lock_guard<std::mutex> lk(g_fact_mu);
+    auto it = g_fact.id2h.find(id);
+    if (it == g_fact.id2h.end())
+        return fail(AB_EHANDLE, "factorization id %lld is not cached (increase max_cache_size)", (long long)id);
+    g_fact.order.remove(id);
+    g_fact.order.push_front(id);
+    *h = it->second;
+    return AB_OK;
+}
+
+int ab_factorized_solve(int64_t id, const double* rhs, int64_t d, double* out) {
+    int64_t h;
+    AB_TRY(fact_lookup(id, &h));
+    Csr* c = csr_get(h);
+    if (!c) return AB_EHANDLE;
+    if (c->m != d) return fail(AB_EINVAL, "rhs length %lld != matrix size %lld", (long long)d, (long long)c->m);
+    return ab_solve(h, "auto", rhs, out, 0.0, 0, nullptr, nullptr);
+}
+
+int ab_factorized_solve_grad(int64_t id, const double* grad_out, const double* out, const int64_t* ii,
+                             const int64_t* jj, int64_t nv, int64_t d, double* grad_rhs, double* grad_vv) {
+    (void)ii; (void)jj;   // the handle already holds the triplet -> entry map
+    int64_t h;
+    AB_TRY(fact_lookup(id, &h));
+    Csr* c = csr_get(h);
+    if (!c) return AB_EHANDLE;
+    if (c->m != d || c->T != nv) return fail(AB_EINVAL, "size mismatch with the factorized matrix");
+    return ab_solve_grad(h, "auto", grad_out, out, grad_vv, grad_rhs, 0.0, 0, nullptr, nullptr);
+}
+
+}  // extern "C"
+
+// ---- measurement hook: per-kernel durations of the CG iteration (bench.py roofline) ----------
+namespace ab {
+__global__ void fill_kernel(double* p, size_t n, double v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+}  // namespace ab
+
+extern "C" int ab_bench_cg_kernels(int64_t h, int reps, double* ms_spmv_dot, double* ms_update, double* ms_direction) {
+    AB_TRY(ensure_device());
+    Csr* c = csr_get(h);
+    if (!c) return AB_EHANDLE;
+    if (reps < 1 || reps > 1000 || c->m != c->n || c->m == 0) return fail(AB_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(big_lock());
+    AB_TRY(csr_ensure_dinv(c));
+    AB_TRY(csr_ensure_work(c, 8));
+    const size_t n = (size_t)c->m;
+    double *r = work_vec(c, 0), *p = work_vec(c, 1), *Ap = work_vec(c, 2), *b = work_vec(c, 3), *x = work_vec(c, 4);
+    SolveScal* s = (SolveScal*)c->scal;
+    const unsigned g = ew_grid(n);
+    fill_kernel<<<g, 256, 0, stream()>>>(b, n, 1.0);
+    AB_LAUNCH_CHECK();
+    cg_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->dinv, x, r, p, n, -1.0, s, c->partials, c->ticket, 0);
+    AB_LAUNCH_CHECK();
+    std::vector<cudaEvent_t> ev(4 * (size_t)reps);
+    for (auto& e : ev) AB_CUDA(cudaEventCreate(&e));
+    for (int it = 0; it < reps; ++it) {
+        const int parity = it & 1;
+        AB_CUDA(cudaEventRecord(ev[4 * it + 0], stream()));
+        AB_TRY(launch_spmv(c, p, Ap, p, s->dots, c->partials, c->ticket, &s->done));
+        AB_CUDA(cudaEventRecord(ev[4 * it + 1], stream()));
+        cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, 0);
+        AB_LAUNCH_CHECK();
+        AB_CUDA(cudaEventRecord(ev[4 * it + 2], stream()));
+        cg_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, c->dinv, p, n, parity, s);
+        AB_LAUNCH_CHECK();
+        AB_CUDA(cudaEventRecord(ev[4 * it + 3], stream()));
+    }
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    double t[3] = {0, 0, 0};
+    for (int it = 0; it < reps; ++it)
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[4 * it + k], ev[4 * it + k + 1]);
+            t[k] += ms;
+        }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (ms_spmv_dot) *ms_spmv_dot = t[0] / reps;
+    if (ms_update) *ms_update = t[1] / reps;
+    if (ms_direction) *ms_direction = t[2] / reps;
+    SolveScal fin;
+    AB_TRY(read_scal(c, &fin));
+    if (fin.breakdown) return fail(AB_EBREAKDOWN, "CG breakdown during the kernel timing run");
+    return AB_OK;
+}

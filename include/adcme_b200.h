@@ -1,0 +1,220 @@
+/*
+ * adcme_b200.h — flat C-ABI of libadcme_b200.so
+ *
+ * B200-native (sm_100a) replacement for ADCME.jl's sparse linear-algebra
+ * custom-op hot path.  Every entry point takes plain pointers and sizes; no
+ * torch / TensorFlow types cross this boundary.  Host code (Julia `ccall`,
+ * Python `ctypes`, C) binds exactly these symbols.
+ *
+ * Conventions (mirroring the reference's own native-op conventions,
+ * /root/reference/src/extra.jl:160-235 and deps/CustomOpsTemplate):
+ *   - every function returns 0 on success and a negative AB_E* code otherwise;
+ *     ab_last_error() returns the thread-local message for the last failure
+ *     (the reference surfaces a TF `Status` string as PyCall.PyError,
+ *     test/sparse.jl:335-339);
+ *   - all array arguments are CALLER-OWNED.  Each pointer may be a device
+ *     pointer or a host pointer (detected with cudaPointerGetAttributes);
+ *     host buffers are staged over PCIe inside the call;
+ *   - outputs are caller-allocated after an explicit size query
+ *     (the reference pattern: SparseCompressor.nout, SAMAP[h]->get_n(),
+ *     deps/CustomOps/SparseAccumulate/SparseAccumulator.cpp:202);
+ *   - cross-call state lives in a process-global table keyed by an integer
+ *     handle (reference: SAMAP, deps/CustomOps/SparseAccumulate/SparseAccumulator.cpp:8;
+ *     cache1/cache2, deps/CustomOps/SparseFactorizationSolve/lru_cache.cpp:215-216);
+ *   - values are fp64; there is no fp32 path (reference: src/variable.jl:742-764).
+ *   - There is NO CPU fallback: every compute entry point fails with
+ *     AB_ECUDA when no sm_100 device is usable.
+ */
+#ifndef ADCME_B200_H
+#define ADCME_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes --------------------------------------------------- */
+#define AB_OK            0
+#define AB_EINVAL       -1  /* bad argument (null pointer, negative size, unknown method …)     */
+#define AB_EHANDLE      -2  /* unknown / destroyed handle                                       */
+#define AB_ECUDA        -3  /* CUDA runtime failure (message has the cudaError string)          */
+#define AB_ERANGE       -4  /* a row/column index outside [base, base+dim)                      */
+#define AB_ENOCONV      -5  /* iterative solve hit maxit without reaching tol                   */
+#define AB_EBREAKDOWN   -6  /* solver breakdown: singular / non-SPD / NaN (reference: "Sparse
+                               solver factorization failed.", SparseSolver.cpp:119-138)         */
+#define AB_EUNSUPPORTED -7  /* size beyond 32-bit local index space, unknown option …           */
+#define AB_ENCCL        -8  /* NCCL failure on the multi-GPU path                                */
+
+/* ---- lifecycle, errors, stream -------------------------------------- */
+/* Replaces mpi_init/mpi_finalize/mpi_size (deps/CustomOps/MPI/MPI_Utils.cpp:9-69). */
+int         ab_init(int device);            /* bind this process to one GPU; idempotent           */
+int         ab_finalize(void);              /* drop every handle and cached workspace             */
+int         ab_device_count(void);          /* number of visible CUDA devices (0 if none)         */
+const char* ab_last_error(void);
+const char* ab_version(void);
+int         ab_set_stream(void* cuda_stream); /* launches go to this cudaStream_t (default: 0)   */
+int         ab_synchronize(void);
+/* tunables: "tol" (default solve tolerance), "maxit", "spmv_variant", "check_every", "verbose" */
+int         ab_set_option(const char* key, double value);
+int         ab_get_option(const char* key, double* value);
+
+/* ---- SparseAssembler (reference a3) ---------------------------------
+ * src/sparse.jl:480-534; deps/CustomOps/SparseAccumulate/Impl.cpp:11-118.
+ * handle/nrow/row/cols are int32 and rows/cols 1-based exactly as in the
+ * reference; a contribution is kept iff abs(v) > tol (strict, applied per
+ * contribution BEFORE accumulation, Impl.cpp:16); duplicates are NOT summed;
+ * ab_asm_copy dumps row by row in insertion order and destroys the handle. */
+int     ab_asm_create(int32_t h, int32_t nrow, double tol);
+int     ab_asm_add(int32_t h, int32_t row, const int32_t* cols, const double* vals, int32_t k);
+int     ab_asm_add_coo(int32_t h, const int32_t* rows, const int32_t* cols,
+                       const double* vals, int64_t k);          /* bulk form of ab_asm_add     */
+int64_t ab_asm_nnz(int32_t h);                                   /* <0: error code              */
+int     ab_asm_copy(int32_t h, int32_t* rows, int32_t* cols, double* vals);
+int     ab_asm_destroy(int32_t h);
+
+/* ---- COO -> CSR assembly with duplicate summation (a1 + a4 + a5) ----
+ * SparseTensor(ii,jj,vv,m,n) (src/sparse.jl:62-76) followed by what every
+ * consumer does to it: Eigen setFromTriplets (SparseSolver.h:16-22) — sum
+ * duplicates in input order, sorted column indices within each row.
+ * `base` is 1 for the op boundary (find(), SparseSolver.h:19) and 0 for
+ * tf.SparseTensor indices.  The handle keeps rowptr/colind/values AND the
+ * triplet -> stored-entry map, so gradients can be delivered per INPUT triplet
+ * in the caller's original order (SparseCompress.h:45-54).
+ * Errors: AB_ERANGE if an index is out of range (the reference is UB there). */
+int ab_csr_from_coo(int64_t T, const int64_t* ii, const int64_t* jj, const double* vv,
+                    int64_t m, int64_t n, int base, int64_t* out_h);
+int ab_csr_from_coo32(int64_t T, const int32_t* ii, const int32_t* jj, const double* vv,
+                      int64_t m, int64_t n, int base, int64_t* out_h);
+/* adopt an existing 0-based CSR (copied); T == nnz and the triplet map is the identity */
+int ab_csr_create(int64_t m, int64_t n, int64_t nnz, const int32_t* rowptr,
+                  const int32_t* colind, const double* values, int64_t* out_h);
+int ab_csr_query(int64_t h, int64_t* m, int64_t* n, int64_t* nnz, int64_t* T);
+int ab_csr_export(int64_t h, int32_t* rowptr /*[m+1]*/, int32_t* colind /*[nnz]*/,
+                  double* values /*[nnz]*/);              /* any output may be NULL              */
+int ab_csr_export_map(int64_t h, int32_t* slot /*[T]*/); /* slot[t] = stored entry of triplet t */
+/* re-reduce new triplet values through the cached map: no re-sort (a11-style reuse) */
+int ab_csr_update_values(int64_t h, const double* vv /*[T]*/);
+int ab_csr_transpose(int64_t h, int64_t* out_h);          /* explicit A' (src/sparse.jl:220-225) */
+int ab_csr_destroy(int64_t h);
+
+/* ---- compress (a4) ----------------------------------------------------
+ * deps/CustomOps/SparseCompress/SparseCompress.h:21-54.  idx2 is the 0-based
+ * row-major [N,2] int64 index matrix of a tf.SparseTensor, SORTED (precondition
+ * inherited from the reference); equal neighbours are merged, values summed
+ * left to right. */
+int ab_compress_count(int64_t N, const int64_t* idx2, int64_t* nout);
+int ab_compress(int64_t N, const int64_t* idx2, const double* v,
+                int64_t* out_idx2 /*[nout,2]*/, double* out_v /*[nout]*/);
+int ab_compress_grad(int64_t N, const int64_t* idx2, const double* grad_nv /*[nout]*/,
+                     double* grad_v /*[N]*/);
+
+/* ---- mpi_create_matrix (a6): sorted COO -> (rows, ncols, cols) --------
+ * deps/Plugin/MPITensor/MPITensor.h:1-36. */
+int ab_coo_to_rows_count(int64_t n, const int64_t* idx2, int64_t* nrow);
+int ab_coo_to_rows(int64_t n, const int64_t* idx2, int64_t ilower,
+                   int32_t* rows /*[nrow]*/, int32_t* ncols /*[nrow]*/, int32_t* cols /*[n]*/);
+
+/* ---- SpMV / SpMM and gradients (a7, a8) -------------------------------
+ * src/sparse.jl:227-264 -> tf.sparse.sparse_dense_matmul.  X, Y are ROW-MAJOR
+ * [ncols,k] / [nrows,k] fp64 (k == 1 is SpMV).  transA != 0 multiplies by A'
+ * (the `o*s` path, sparse.jl:251).
+ * grad_values is per INPUT triplet: dvv[t] = <dY[i_t,:], X[j_t,:]>.
+ * grad_dense is dX = A' dY. */
+int ab_spmm(int64_t h, int transA, const double* X, int64_t k, double* Y);
+int ab_spmm_grad_values(int64_t h, const double* dY, const double* X, int64_t k,
+                        double* dvv /*[T]*/);
+int ab_spmm_grad_dense(int64_t h, const double* dY, int64_t k, double* dX);
+
+/* ---- sparse `\` and its adjoint (a9, a10, a11) ------------------------
+ * src/sparse.jl:413-445; SparseSolver.h:13-70; Solve.h:3-33.
+ * method: "CG" | "BiCGSTAB" | "auto", plus the reference's strings mapped as
+ *   "SimplicialLLT","SimplicialLDLT" -> CG ; "SparseLU","SparseQR" -> BiCGSTAB.
+ * Both solvers are Jacobi-preconditioned.  tol <= 0 / maxit <= 0 pick the
+ * options "tol" / "maxit".  Convergence test: ||f - A u||_2 <= tol*||f||_2 on
+ * the recurrence residual.  iters / relres may be NULL.
+ * Non-convergence returns AB_ENOCONV (u still holds the last iterate),
+ * breakdown AB_EBREAKDOWN — never a silent NaN.
+ * ab_solve_grad: x = A^{-T} grad_u ; grad_f = x ; grad_vv[t] = -x[i_t]*u[j_t]
+ * for every input triplet t (duplicates each get the same formula). */
+int ab_solve(int64_t h, const char* method, const double* f, double* u,
+             double tol, int maxit, int* iters, double* relres);
+int ab_solve_grad(int64_t h, const char* method, const double* grad_u, const double* u,
+                  double* grad_vv /*[T] or NULL*/, double* grad_f /*[n] or NULL*/,
+                  double tol, int maxit, int* iters, double* relres);
+/* run exactly `iters` CG iterations with the convergence test disabled
+ * (benchmark entry: BASELINE.json "CG iters/s"); returns relres at the end */
+int ab_cg_fixed(int64_t h, const double* f, double* u, int iters, double* relres);
+
+/* One-shot forms with the reference op signatures (1-based int64 ii/jj):
+ * SparseSolver / SparseSolverGrad, deps/CustomOps/SparseSolver/SparseSolver.cpp:21-60 */
+int ab_sparse_solver(const int64_t* ii, const int64_t* jj, const double* vv, int64_t nv,
+                     const double* f, int64_t d, const char* method, double* u);
+int ab_sparse_solver_grad(const double* grad_u, const double* u,
+                          const int64_t* ii, const int64_t* jj, const double* vv, int64_t nv,
+                          const double* f, int64_t d, const char* method,
+                          double* grad_vv /*[nv]*/, double* grad_f /*[d]*/);
+
+/* factorize / solve with an id-keyed cache (a11):
+ * SparseFactorization.h:4-34, Solve.h:3-33.  "Factorizing" here assembles and
+ * caches CSR(A), CSR(A'), the Jacobi diagonals and the solver workspace. */
+int ab_factorize(const int64_t* ii, const int64_t* jj, const double* vv, int64_t nv,
+                 int64_t d, int64_t max_cache_size, int64_t* id);
+int ab_factorized_solve(int64_t id, const double* rhs, int64_t d, double* out);
+int ab_factorized_solve_grad(int64_t id, const double* grad_out, const double* out,
+                             const int64_t* ii, const int64_t* jj, int64_t nv, int64_t d,
+                             double* grad_rhs, double* grad_vv);
+
+/* ---- stencil matrix generators (N1) -----------------------------------
+ * 3-D 7-point Dirichlet Laplacian (diag 6, off -1) on an nx*ny*nz grid, rows
+ * [row_lo,row_hi) only (a z-slab when row_lo/row_hi are multiples of nx*ny),
+ * built direct-to-CSR on the device.  Column ids are GLOBAL. */
+int ab_poisson3d_csr(int64_t nx, int64_t ny, int64_t nz, int64_t row_lo, int64_t row_hi,
+                     int64_t* out_h);
+/* 2-D 5-point variable-coefficient operator from a halo-extended kext[(n+2)*(n+2)]:
+ * docs/src/assets/Codes/MPI/ccode/GetPoissonMatrix.h:15-51, with sign so that
+ * sign=+1 reproduces the reference values and sign=-1 the SPD matrix (-A).
+ * Dirichlet: neighbours outside the n*n grid are dropped.                      */
+int ab_poisson2d_csr(int64_t n, const double* kext, int sign, int64_t* out_h);
+int ab_poisson2d_update(int64_t h, int64_t n, const double* kext, int sign);
+/* adjoint of the generator: GetPoissonMatrix.h:55-72 (xgrad = A^{-T}g, uext = halo-extended u) */
+int ab_poisson2d_grad(int64_t n, const double* xgrad, const double* uext, int sign,
+                      double* grad_kext /*[(n+2)*(n+2)]*/);
+
+/* ---- row-block distributed CSR + solve (a12) --------------------------
+ * Replaces mpi_SparseTensor `\` (src/mpi.jl:420-508; MPITensor.h:103-152):
+ * one process per GPU, rank r owns rows [ilower, iupper] (Hypre IJ layout,
+ * inclusive), local CSR with GLOBAL column ids.  NCCL carries the CG inner
+ * products; halo planes move over NVLink.  The host bootstraps NCCL by passing
+ * the 128-byte ncclUniqueId made by ab_dist_unique_id on rank 0.           */
+int ab_dist_unique_id(void* id128);
+int ab_dist_init(int rank, int world, const void* id128);
+int ab_dist_finalize(void);
+int ab_dist_csr_create(int64_t h_local, int64_t ilower, int64_t iupper, int64_t N,
+                       int64_t* out_dh);
+int ab_dist_spmv(int64_t dh, const double* x_local, double* y_local);
+int ab_dist_solve(int64_t dh, const char* method, const double* f_local, double* u_local,
+                  double tol, int maxit, int* iters, double* relres);
+int ab_dist_cg_fixed(int64_t dh, const double* f_local, double* u_local, int iters,
+                     double* relres);
+int ab_dist_destroy(int64_t dh);
+
+/* ---- timers (reference: MPITensor_Solve_Timer_*, MPITensor.cpp:15-21) -- */
+#define AB_TIMER_SOLVE    0
+#define AB_TIMER_SPMM     1
+#define AB_TIMER_ASSEMBLY 2
+int    ab_timer_reset(void);
+double ab_timer_get(int which);   /* accumulated device seconds */
+
+/* ---- measurement hooks (bench.py only) --------------------------------
+ * Launch the named kernel `reps` times back to back on the current stream and
+ * return the average launch duration in ms from CUDA events on that stream. */
+int ab_bench_spmv(int64_t h, const double* x, double* y, int reps, int with_dot, double* ms);
+int ab_bench_cg_kernels(int64_t h, int reps, double* ms_spmv_dot, double* ms_update,
+                        double* ms_direction);
+int64_t ab_launch_count(void);   /* kernels launched by this library since ab_init */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADCME_B200_H */

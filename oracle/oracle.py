@@ -1,0 +1,296 @@
+"""Python face of the CPU oracle (TEST INFRASTRUCTURE — see the header of adcme_oracle.c).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  It wraps oracle/liboracle.so (the C restatement of the reference's algorithms) with
+ctypes and adds a SuperLU-based direct solve for mid-size systems: Eigen::SparseLU, which the
+reference calls at deps/CustomOps/SparseSolver/SparseSolver.h:13-44, is the same supernodal LU
+family as SuperLU, and parity is on the solution (<= 1e-10 relative residual), not on pivots.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "adcme_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True, stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_accum_create.restype = C.c_void_p
+        _lib.orc_accum_create.argtypes = [C.c_int, C.c_double]
+        _lib.orc_accum_add.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.orc_accum_nnz.restype = C.c_int64
+        _lib.orc_accum_nnz.argtypes = [C.c_void_p]
+        _lib.orc_accum_copy.argtypes = [C.c_void_p] * 4
+        _lib.orc_compress.restype = C.c_int64
+        _lib.orc_coo_to_rows_count.restype = C.c_int64
+        _lib.orc_coo_to_csr.restype = C.c_int64
+        _lib.orc_poisson2d_matrix.restype = C.c_int64
+        _lib.orc_pcg_jacobi.restype = C.c_int
+        _lib.orc_pcg_jacobi.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+# ---------------------------------------------------------------- SparseAssembler
+class Accumulator:
+    """SparseAccum (deps/CustomOps/SparseAccumulate/Impl.cpp:11-48)."""
+
+    def __init__(self, nrow: int, tol: float = 0.0):
+        self._h = lib().orc_accum_create(int(nrow), float(tol))
+
+    def add(self, row: int, cols, vals) -> int:
+        cols, vals = _i32(cols), _f64(vals)
+        return lib().orc_accum_add(self._h, int(row), _p(cols), _p(vals), len(vals))
+
+    def nnz(self) -> int:
+        return int(lib().orc_accum_nnz(self._h))
+
+    def copy(self):
+        k = self.nnz()
+        rows, cols, vals = np.zeros(k, np.int32), np.zeros(k, np.int32), np.zeros(k, np.float64)
+        lib().orc_accum_copy(self._h, _p(rows), _p(cols), _p(vals))
+        self._h = None
+        return rows, cols, vals
+
+
+# ---------------------------------------------------------------- compress / coo_to_rows
+def compress(idx2, v):
+    idx2, v = _i64(idx2).reshape(-1, 2), _f64(v)
+    N = len(v)
+    oi, ov = np.zeros((max(N, 1), 2), np.int64), np.zeros(max(N, 1), np.float64)
+    k = lib().orc_compress(C.c_int64(N), _p(idx2), _p(v), _p(oi), _p(ov))
+    return oi[:k].copy(), ov[:k].copy()
+
+
+def compress_grad(idx2, grad_nv):
+    idx2, g = _i64(idx2).reshape(-1, 2), _f64(grad_nv)
+    N = idx2.shape[0]
+    out = np.zeros(N, np.float64)
+    lib().orc_compress_grad(C.c_int64(N), _p(idx2), _p(g), _p(out))
+    return out
+
+
+def coo_to_rows(idx2, ilower: int):
+    idx2 = _i64(idx2).reshape(-1, 2)
+    n = idx2.shape[0]
+    nrow = lib().orc_coo_to_rows_count(C.c_int64(n), _p(idx2))
+    rows, ncols, cols = np.zeros(nrow, np.int32), np.zeros(nrow, np.int32), np.zeros(n, np.int32)
+    lib().orc_coo_to_rows(C.c_int64(n), _p(idx2), C.c_int64(ilower), _p(rows), _p(ncols), _p(cols))
+    return rows, ncols, cols
+
+
+# ---------------------------------------------------------------- COO -> CSR (setFromTriplets)
+def coo_to_csr(ii, jj, vv, m: int, n: int, base: int = 1):
+    ii, jj, vv = _i64(ii), _i64(jj), _f64(vv)
+    T = len(vv)
+    rowptr = np.zeros(m + 1, np.int32)
+    colind = np.zeros(max(T, 1), np.int32)
+    values = np.zeros(max(T, 1), np.float64)
+    slot = np.zeros(max(T, 1), np.int32)
+    nnz = lib().orc_coo_to_csr(C.c_int64(T), _p(ii), _p(jj), _p(vv), C.c_int(base), C.c_int64(m), C.c_int64(n),
+                               _p(rowptr), _p(colind), _p(values), _p(slot))
+    if nnz < 0:
+        raise IndexError("triplet index out of range")
+    return rowptr, colind[:nnz].copy(), values[:nnz].copy(), slot[:T].copy()
+
+
+# ---------------------------------------------------------------- SpMM + grads (TF semantics)
+def spmm_coo(idx2, val, m: int, B, adjoint_a: bool = False):
+    idx2, val = _i64(idx2).reshape(-1, 2), _f64(val)
+    B = _f64(B)
+    vec = B.ndim == 1
+    B2 = B.reshape(len(B), -1)
+    k = B2.shape[1]
+    out = np.zeros((m, k), np.float64)
+    lib().orc_spmm_coo(C.c_int64(len(val)), _p(idx2), _p(val), C.c_int64(m), C.c_int64(k), _p(B2), _p(out),
+                       C.c_int(1 if adjoint_a else 0))
+    return out[:, 0].copy() if vec else out
+
+
+def spmm_grad_values(idx2, grad, B):
+    idx2 = _i64(idx2).reshape(-1, 2)
+    grad, B = _f64(grad), _f64(B)
+    g2, B2 = grad.reshape(len(grad), -1), B.reshape(len(B), -1)
+    out = np.zeros(idx2.shape[0], np.float64)
+    lib().orc_spmm_grad_values(C.c_int64(idx2.shape[0]), _p(idx2), C.c_int64(g2.shape[1]), _p(g2), _p(B2), _p(out))
+    return out
+
+
+def csr_spmm(rowptr, colind, values, X):
+    rowptr, colind, values = _i32(rowptr), _i32(colind), _f64(values)
+    X = _f64(X)
+    vec = X.ndim == 1
+    X2 = X.reshape(len(X), -1)
+    m, k = len(rowptr) - 1, X2.shape[1]
+    Y = np.zeros((m, k), np.float64)
+    lib().orc_csr_spmm(C.c_int64(m), _p(rowptr), _p(colind), _p(values), C.c_int64(k), _p(X2), _p(Y))
+    return Y[:, 0].copy() if vec else Y
+
+
+# ---------------------------------------------------------------- SparseSolver fwd / bwd
+class SolverError(RuntimeError):
+    """Mirrors Status(INTERNAL, "Sparse solver factorization failed.") (SparseSolver.cpp:119-138)."""
+
+
+def sparse_solver(ii, jj, vv, f, d: int | None = None, dense_limit: int = 600):
+    ii, jj, vv, f = _i64(ii), _i64(jj), _f64(vv), _f64(f)
+    d = len(f) if d is None else d
+    if d <= dense_limit:
+        u = np.zeros(d, np.float64)
+        rc = lib().orc_sparse_solver(_p(ii), _p(jj), _p(vv), C.c_int64(len(vv)), _p(f), C.c_int64(d), C.c_int(0), _p(u))
+        if rc != 0:
+            raise SolverError("Sparse solver factorization failed.")
+        return u
+    return _splu_solve(ii, jj, vv, f, d, transpose=False)
+
+
+def sparse_solver_grad(grad_u, u, ii, jj, vv, d: int | None = None, dense_limit: int = 600):
+    ii, jj, vv, grad_u, u = _i64(ii), _i64(jj), _f64(vv), _f64(grad_u), _f64(u)
+    d = len(u) if d is None else d
+    if d <= dense_limit:
+        gv, gf = np.zeros(len(vv), np.float64), np.zeros(d, np.float64)
+        rc = lib().orc_sparse_solver_grad(_p(grad_u), _p(u), _p(ii), _p(jj), _p(vv), C.c_int64(len(vv)), C.c_int64(d),
+                                          _p(gv), _p(gf))
+        if rc != 0:
+            raise SolverError("Sparse solver factorization failed.")
+        return gv, gf
+    x = _splu_solve(ii, jj, vv, grad_u, d, transpose=True)
+    gv = np.zeros(len(vv), np.float64)
+    lib().orc_solver_grad_vv(_p(x), _p(u), _p(ii), _p(jj), C.c_int64(len(vv)), _p(gv))
+    return gv, x
+
+
+def _splu_solve(ii, jj, vv, f, d, transpose):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    r, c = (jj - 1, ii - 1) if transpose else (ii - 1, jj - 1)
+    A = sp.coo_matrix((vv, (r, c)), shape=(d, d)).tocsc()   # duplicates summed, like setFromTriplets
+    try:
+        lu = spla.splu(A)
+    except RuntimeError as e:   # exactly singular
+        raise SolverError("Sparse solver factorization failed.") from e
+    x = lu.solve(f)
+    # one step of iterative refinement keeps the oracle itself well below the 1e-10 gate
+    x = x + lu.solve(f - A @ x)
+    return x
+
+
+# ---------------------------------------------------------------- Poisson generators
+def poisson2d_matrix(n: int, kext):
+    """GetPoissonMatrixForward (GetPoissonMatrix.h:15-51), single-rank colext."""
+    kext = _f64(kext).reshape(n + 2, n + 2)
+    cols, val, ncols = np.zeros(5 * n * n, np.int64), np.zeros(5 * n * n, np.float64), np.zeros(n * n, np.int32)
+    p = lib().orc_poisson2d_matrix(C.c_int64(n), _p(kext), _p(cols), _p(val), _p(ncols))
+    return cols[:p].copy(), val[:p].copy(), ncols
+
+
+def poisson2d_grad(n: int, xgrad, uext):
+    xgrad, uext = _f64(xgrad), _f64(uext)
+    out = np.zeros((n + 2) * (n + 2), np.float64)
+    lib().orc_poisson2d_grad(C.c_int64(n), _p(xgrad), _p(uext), _p(out))
+    return out
+
+
+def poisson3d_csr(nx: int, ny: int, nz: int):
+    N = nx * ny * nz
+    nnz = C.c_int64(0)
+    lib().orc_poisson3d_csr_count(C.c_int64(nx), C.c_int64(ny), C.c_int64(nz), C.byref(nnz))
+    rowptr, colind, values = np.zeros(N + 1, np.int32), np.zeros(nnz.value, np.int32), np.zeros(nnz.value, np.float64)
+    lib().orc_poisson3d_csr(C.c_int64(nx), C.c_int64(ny), C.c_int64(nz), _p(rowptr), _p(colind), _p(values))
+    return rowptr, colind, values
+
+
+# ---------------------------------------------------------------- CPU Jacobi-PCG (baseline port)
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+def pcg_jacobi(rowptr, colind, values, b, tol: float = 1e-12, maxit: int = 10000):
+    rowptr, colind, values, b = _i32(rowptr), _i32(colind), _f64(values), _f64(b)
+    n = len(b)
+    x, work = np.zeros(n, np.float64), np.empty(4 * n, np.float64)
+    relres = C.c_double(0)
+    it = lib().orc_pcg_jacobi(C.c_int64(n), _p(rowptr), _p(colind), _p(values), _p(b), _p(x), float(tol), int(maxit),
+                              C.byref(relres), _p(work))
+    return x, it, relres.value
+
+
+# ---------------------------------------------------------------- synthetic inputs shared by tests and bench
+def facewise_triplets_2d(n: int, seed: int = 233, shuffle: bool = True):
+    """FEM-style face-wise assembly stream of the 2-D 5-point Dirichlet Laplacian on n x n
+    (the reference idiom is docs/src/tu_fem.md:41-54): every interior face emits
+    (i,i,+1),(j,j,+1),(i,j,-1),(j,i,-1), every boundary face emits (i,i,+1).  1-based int64."""
+    idx = np.arange(n * n, dtype=np.int64).reshape(n, n)
+    I, J, V = [], [], []
+
+    def faces(a, b):
+        a, b = a.ravel(), b.ravel()
+        I.extend([a, b, a, b]); J.extend([a, b, b, a])
+        V.extend([np.ones(len(a)), np.ones(len(a)), -np.ones(len(a)), -np.ones(len(a))])
+
+    faces(idx[:, :-1], idx[:, 1:])
+    faces(idx[:-1, :], idx[1:, :])
+    for edge in (idx[0, :], idx[-1, :], idx[:, 0], idx[:, -1]):
+        I.append(edge.ravel()); J.append(edge.ravel()); V.append(np.ones(edge.size))
+    ii, jj, vv = np.concatenate(I) + 1, np.concatenate(J) + 1, np.concatenate(V)
+    if shuffle:
+        p = np.random.default_rng(seed).permutation(len(vv))
+        ii, jj, vv = ii[p], jj[p], vv[p]
+    return ii, jj, vv
+
+
+def facewise_triplets_3d(n: int, seed: int = 233, shuffle: bool = True):
+    """Same scheme for the 3-D 7-point Laplacian on n^3: diag 6, off -1."""
+    idx = np.arange(n ** 3, dtype=np.int64).reshape(n, n, n)
+    I, J, V = [], [], []
+
+    def faces(a, b):
+        a, b = a.ravel(), b.ravel()
+        I.extend([a, b, a, b]); J.extend([a, b, b, a])
+        V.extend([np.ones(len(a)), np.ones(len(a)), -np.ones(len(a)), -np.ones(len(a))])
+
+    faces(idx[:, :, :-1], idx[:, :, 1:])
+    faces(idx[:, :-1, :], idx[:, 1:, :])
+    faces(idx[:-1, :, :], idx[1:, :, :])
+    for face in (idx[0], idx[-1], idx[:, 0], idx[:, -1], idx[:, :, 0], idx[:, :, -1]):
+        I.append(face.ravel()); J.append(face.ravel()); V.append(np.ones(face.size))
+    ii, jj, vv = np.concatenate(I) + 1, np.concatenate(J) + 1, np.concatenate(V)
+    if shuffle:
+        p = np.random.default_rng(seed).permutation(len(vv))
+        ii, jj, vv = ii[p], jj[p], vv[p]
+    return ii, jj, vv
