@@ -191,12 +191,15 @@ __global__ void grad_vv_kernel(const int32_t* __restrict__ slot, const int32_t* 
 }
 
 // ---------------------------------------------------------------- host drivers
-enum Method { M_CG = 0, M_BICGSTAB = 1 };
+// M_GENERAL = BiCGSTAB first, dense partial-pivot LU on the device when it fails and n is small:
+// what the reference strings SparseLU / SparseQR / auto map to (they never fail on a regular matrix).
+enum Method { M_CG = 0, M_BICGSTAB = 1, M_GENERAL = 2 };
 
 static int parse_method(const char* method, Method* out) {
     std::string s = method ? method : "auto";
     if (s == "CG" || s == "cg" || s == "SimplicialLLT" || s == "SimplicialLDLT") { *out = M_CG; return AB_OK; }
-    if (s == "BiCGSTAB" || s == "bicgstab" || s == "auto" || s == "SparseLU" || s == "SparseQR") { *out = M_BICGSTAB; return AB_OK; }
+    if (s == "BiCGSTAB" || s == "bicgstab") { *out = M_BICGSTAB; return AB_OK; }
+    if (s == "auto" || s == "SparseLU" || s == "SparseQR") { *out = M_GENERAL; return AB_OK; }
     return fail(AB_EINVAL, "unknown sparse solver method '%s'", s.c_str());
 }
 
@@ -319,6 +322,101 @@ static int true_relres(Csr* c, const double* b, const double* x, double* relres)
     return AB_OK;
 }
 
+// ---------------------------------------------------------------- small dense fallback
+// Partial-pivot Gaussian elimination of the (tiny) matrix scattered to dense storage, one CTA.
+// Gives the legacy direct-solver strings the behaviour the reference has on matrices no Krylov
+// method likes (test/sparse.jl:323-333 factorises sprand(10,10,0.7)); a zero pivot is the
+// reference's "Sparse solver factorization failed." (SparseSolver.cpp:119-138).
+constexpr int DENSE_LU_MAX = 2048;
+
+__global__ void csr_to_dense_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                    const double* __restrict__ values, int d, double* __restrict__ A) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= d) return;
+    for (int j = rowptr[r]; j < rowptr[r + 1]; ++j) A[(size_t)r * d + colind[j]] += values[j];
+}
+
+__global__ void __launch_bounds__(1024)
+dense_lu_kernel(double* __restrict__ A, double* __restrict__ x, int d, int* __restrict__ info) {
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_piv;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for (int k = 0; k < d; ++k) {
+        // pivot search in column k
+        double best = -1.0; int bi = k;
+        for (int r = k + t; r < d; r += 1024) { double v = fabs(A[(size_t)r * d + k]); if (v > best) { best = v; bi = r; } }
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { s_val[w] = best; s_idx[w] = bi; }
+        __syncthreads();
+        if (w == 0) {
+            best = s_val[lane]; bi = s_idx[lane];
+            for (int o = 16; o > 0; o >>= 1) {
+                double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) { s_piv = (best > 0.0 && isfinite(best)) ? bi : -1; }
+        }
+        __syncthreads();
+        const int piv = s_piv;
+        if (piv < 0) { if (t == 0) *info = k + 1; return; }
+        if (piv != k) {
+            for (int cc = t; cc < d; cc += 1024) { double a = A[(size_t)k * d + cc]; A[(size_t)k * d + cc] = A[(size_t)piv * d + cc]; A[(size_t)piv * d + cc] = a; }
+            if (t == 0) { double a = x[k]; x[k] = x[piv]; x[piv] = a; }
+        }
+        __syncthreads();
+        const double pk = A[(size_t)k * d + k];
+        const int rem = d - k - 1;
+        // rows below k: one warp per row, lanes over columns
+        for (int r = k + 1 + w; r < d; r += 32) {
+            const double f = A[(size_t)r * d + k] / pk;
+            if (f != 0.0) {
+                for (int cc = k + 1 + lane; cc < d; cc += 32) A[(size_t)r * d + cc] -= f * A[(size_t)k * d + cc];
+                if (lane == 0) x[r] -= f * x[k];
+            }
+            __syncwarp();
+            if (lane == 0) A[(size_t)r * d + k] = 0.0;
+        }
+        (void)rem;
+        __syncthreads();
+    }
+    // back substitution
+    for (int k = d - 1; k >= 0; --k) {
+        double acc = 0.0;
+        for (int cc = k + 1 + t; cc < d; cc += 1024) acc += A[(size_t)k * d + cc] * x[cc];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_val[w] = acc;
+        __syncthreads();
+        if (t == 0) {
+            double sum = 0.0;
+            for (int i = 0; i < 32; ++i) sum += s_val[i];
+            x[k] = (x[k] - sum) / A[(size_t)k * d + k];
+        }
+        __syncthreads();
+    }
+}
+
+static int dense_lu_solve(Csr* c, const double* b, double* x) {
+    const int d = (int)c->m;
+    DevBuf<double> A; DevBuf<int> info;
+    AB_TRY(A.alloc((size_t)d * d)); AB_TRY(info.alloc(1));
+    AB_CUDA(cudaMemsetAsync(A.p, 0, (size_t)d * d * sizeof(double), stream()));
+    AB_CUDA(cudaMemsetAsync(info.p, 0, sizeof(int), stream()));
+    csr_to_dense_kernel<<<(d + 255) / 256, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, d, A.p);
+    AB_LAUNCH_CHECK();
+    if (x != b) AB_CUDA(cudaMemcpyAsync(x, b, (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, stream()));
+    dense_lu_kernel<<<1, 1024, 0, stream()>>>(A.p, x, d, info.p);
+    AB_LAUNCH_CHECK();
+    int h = 0;
+    AB_CUDA(cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    if (h) return fail(AB_EBREAKDOWN, "Sparse solver factorization failed. (zero pivot in column %d)", h - 1);
+    return AB_OK;
+}
+
 // Solve A x = b with device pointers.  Shared by forward and adjoint.
 static int solve_dev(Csr* c, Method meth, const double* b, double* x, double tol, int maxit, int* iters,
                      double* relres) {
@@ -350,6 +448,13 @@ static int solve_dev(Csr* c, Method meth, const double* b, double* x, double tol
         if (rc2 != AB_OK) return rc2;
         if (relres) *relres = tr;
         if (isfinite(tr) && tr <= tol * 10) return AB_OK;
+    }
+    if (meth == M_GENERAL && c->m <= DENSE_LU_MAX) {
+        double tr2 = 0;
+        AB_TRY(dense_lu_solve(c, b, x));
+        AB_TRY(true_relres(c, b, x, &tr2));
+        if (relres) *relres = tr2;
+        return AB_OK;
     }
     if (fin.breakdown)
         return fail(AB_EBREAKDOWN, "Sparse solver failed: %s breakdown after %d iterations (relres %.3e); matrix singular%s",

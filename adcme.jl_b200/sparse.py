@@ -41,6 +41,9 @@ def _shape(x):
 class SparseTensor:
     """COO triplets (1-based, duplicates allowed) + a lazily assembled device CSR handle."""
 
+    __array_ufunc__ = None      # numpy defers `ndarray @ SparseTensor` to __rmatmul__
+    __array_priority__ = 1000
+
     def __init__(self, I, J=None, V=None, m=None, n=None, is_diag: bool = False):
         if J is None and hasattr(I, "tocoo"):          # SparseTensor(A::SparseMatrixCSC), sparse.jl:144-157
             coo = I.tocoo()
