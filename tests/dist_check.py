@@ -1,0 +1,66 @@
+"""Multi-GPU parity check, launched under torchrun on a real multi-GPU box (not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29533 tests/dist_check.py [grid=96]
+
+Each rank owns a z-slab of the n^3 7-point Poisson matrix.  Checks, against quantities every rank can
+compute alone: (1) distributed SpMV == matrix-free stencil on the same seeded global vector,
+(2) distributed Jacobi-PCG solve of A u = A*1 returns ones with relres <= 1e-10, and (3) the iterate
+after a fixed number of iterations equals the single-GPU solver's iterate to 1e-12."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import __graft_entry__ as ge  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 96
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    dist.init_process_group("nccl", device_id=dev)
+    pkg = ge.load_package()
+    pkg.mpi_init(rank, world, lr)
+    N = n ** 3
+    A = pkg.mpi_SparseTensor.poisson3d(n, n, n, rank, world)
+    lo, hi = A.ilower, A.iupper
+    g = torch.Generator(device=dev).manual_seed(233)
+    x = torch.rand(N, dtype=torch.float64, device=dev, generator=g) * 2 - 1      # same on every rank
+    X = x.view(n, n, n)
+    S = 6.0 * X
+    S[1:] -= X[:-1]; S[:-1] -= X[1:]
+    S[:, 1:] -= X[:, :-1]; S[:, :-1] -= X[:, 1:]
+    S[:, :, 1:] -= X[:, :, :-1]; S[:, :, :-1] -= X[:, :, 1:]
+    y = A @ x[lo:hi + 1].contiguous()
+    e1 = float((y - S.reshape(-1)[lo:hi + 1]).abs().max() / S.abs().max())
+    b = A @ torch.ones(A.nloc, dtype=torch.float64, device=dev)
+    u, it, rr = A.solve(b, tol=1e-11)
+    e2 = float((u - 1).abs().max())
+    # single-GPU reference iterate on the full system (every rank can afford it at test sizes)
+    h = C.c_int64(0)
+    pkg.check(pkg.lib.ab_poisson3d_csr(n, n, n, 0, N, C.byref(h)))
+    Af = pkg.SparseTensor.from_handle(h.value)      # keep the wrapper alive: its finaliser frees the handle
+    bf = Af @ torch.ones(N, dtype=torch.float64, device=dev)
+    uf = torch.empty_like(bf)
+    r = C.c_double(0)
+    pkg.check(pkg.lib.ab_cg_fixed(h.value, bf.data_ptr(), uf.data_ptr(), 40, C.byref(r)))
+    ud, rd = A.cg_fixed(b, 40)
+    e3 = float((ud - uf[lo:hi + 1]).abs().max() / uf.abs().max())
+    ok = e1 <= 1e-12 and rr <= 1e-11 and e2 <= 1e-7 and e3 <= 1e-12 and abs(rd - r.value) <= 1e-10 * r.value
+    print(f"rank {rank}/{world}: rows [{lo},{hi}] spmv_err {e1:.2e} solve iters {it} relres {rr:.2e} err {e2:.2e} "
+          f"fixed-iterate err {e3:.2e} {'OK' if ok else 'FAIL'}", flush=True)
+    t = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(t)
+    A.close()
+    pkg.mpi_finalize()
+    dist.destroy_process_group()
+    sys.exit(0 if int(t.item()) == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
