@@ -148,6 +148,13 @@ struct Csr {
     double* partials = nullptr;   // reduction partials
     uint32_t* ticket = nullptr;   // last-block tickets
     void* graph_cache = nullptr;
+    // long-row work list for SpMM / SDDMM (lazy): rows longer than LONG_ROW are split into
+    // CHUNK-entry pieces so one power-law row cannot serialise a whole warp
+    int32_t* long_rows = nullptr;         // [long_nrows]
+    int32_t* long_row_chunk0 = nullptr;   // [long_nrows+1] first chunk of each long row
+    int32_t* long_chunk_row = nullptr;    // [long_nchunks]
+    int32_t* long_chunk_start = nullptr;  // [long_nchunks] first entry of the chunk
+    int64_t  long_nrows = -1, long_nchunks = 0;   // -1: not built yet
     ~Csr();
 };
 
@@ -175,6 +182,12 @@ int radix_sort_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t*
 constexpr int MAX_REDUCE_GRID = 8192;   // partials buffers hold NV * MAX_REDUCE_GRID doubles
 int launch_spmv(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
                 double* partials, uint32_t* ticket, const int* done_flag);
+// restricted to a list of tiles (distributed SpMV: interior first, boundary after the halo);
+// accumulate != 0 adds the fused dots onto dot_result.  spmv_tile_rows: rows per tile, 0 = n/a.
+int launch_spmv_part(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
+                     double* partials, uint32_t* ticket, const int* done_flag, const int32_t* tile_list,
+                     int64_t nlist, int accumulate);
+int spmv_tile_rows(const Csr* c);
 int launch_spmm(const Csr* c, const double* X, int64_t k, double* Y);
 
 }  // namespace ab

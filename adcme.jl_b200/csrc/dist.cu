@@ -8,14 +8,27 @@
 // Setup (once per pattern): the off-rank columns a rank touches are found on the device
 // (flag -> compact -> radix sort -> unique), the local CSR is re-indexed to
 // [0,nloc) = owned columns, [nloc, nloc+next) = halo columns, and the owners learn which of
-// their rows to ship (index lists swapped with ncclSend/ncclRecv).
-// SpMV: pack owned boundary values -> grouped ncclSend/ncclRecv straight into the halo tail of
-// the extended vector (NVLink P2P under NCCL) -> the same TMA-staged SpMV kernel as one GPU.
-// CG: the two inner products per iteration are 2-element fp64 ncclAllReduce calls on the same
-// stream; the scalar recurrences stay on the device (cg_fin_kernel), no host round trip.
+// their rows to ship (index lists swapped with ncclSend/ncclRecv).  Tiles of the SpMV kernel are
+// split into "interior" (no halo column) and "boundary" lists.
 //
-// NCCL is dlopen()ed (libnccl.so.2 — the copy PyTorch already loaded when the host is Python),
-// so single-GPU users never need it.
+// Data path (default, "dist_p2p" = 1): peer memory over NVLink, no NCCL call inside the iteration.
+//   * the direction vector (owned part + halo tail) and a small flag block live in cudaMalloc
+//     memory that every peer maps with CUDA IPC;
+//   * halo_push_kernel gathers the boundary values and STORES them straight into the consumers'
+//     halo tails (st.global on peer-mapped pointers), then the last CTA releases a sequence flag
+//     in each consumer's flag block;
+//   * interior tiles are multiplied while those stores fly; halo_wait_kernel acquires the flags;
+//     boundary tiles follow and add their share of the fused dot products;
+//   * the two inner products per iteration are all-reduced by p2p_allreduce2_kernel: every rank
+//     stores its two partial sums into all peers' slots, spins on the eight sequence flags, and
+//     adds the slots in rank order — bit-identical on every rank, ~one NVLink round trip.
+//   Ordering: a rank cannot push halo k+1 before it has passed the <p,Ap> reduction of iteration
+//   k, which needs every peer's contribution, which a peer issues only after its SpMV k finished
+//   reading its halo — so one halo buffer suffices; reduction slots are double-buffered by parity.
+// Fallback ("dist_p2p" = 0 or IPC unavailable): pack -> grouped ncclSend/ncclRecv, ncclAllReduce.
+//
+// NCCL is dlopen()ed (libnccl.so.2 — the copy PyTorch already loaded when the host is Python);
+// it bootstraps (ids, index lists, IPC handles) and serves the fallback path.
 #include "common.cuh"
 #include "cg_kernels.cuh"
 #include <dlfcn.h>
@@ -75,16 +88,52 @@ static int nccl_load() {
                             g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error"); \
     } while (0)
 
+constexpr int MAXW = 16;   // ranks on one NVSwitch box
+
+// Lives in cudaMalloc memory on each rank and is IPC-mapped by every peer.
+struct P2PBlock {
+    double   red[2][MAXW][2];     // all-reduce slots [parity][source rank][2 values]
+    uint32_t red_flag[2][MAXW];   // sequence number whose values sit in red[parity][source]
+    uint32_t halo_flag[MAXW];     // halo_flag[source] = sequence number of its last finished push
+    uint32_t err;                 // a spin loop timed out
+    uint32_t ticket;              // last-CTA ticket of halo_push_kernel
+};
+
 struct DistCsr {
     Csr* loc = nullptr;            // re-indexed local block: m = nloc, n = nloc + next
     int64_t ilower = 0, iupper = -1, N = 0;
     int64_t nloc = 0, next = 0;
     std::vector<int> send_cnt, send_off, recv_cnt, recv_off;   // per peer, in vector entries
+    std::vector<int64_t> dst_off;  // where my values land in peer p's extended vector
     int64_t nsend = 0;
     int32_t* send_idx = nullptr;   // [nsend] local row ids to ship, grouped by destination
-    double*  sendbuf  = nullptr;   // [nsend]
+    double*  sendbuf  = nullptr;   // [nsend]                                 (NCCL fallback)
     double*  xext     = nullptr;   // [nloc + next (+pad)]  SpMV operand / CG direction vector
-    ~DistCsr() { delete loc; dev_free(send_idx); dev_free(sendbuf); dev_free(xext); }
+    bool     xext_cuda_malloc = false;
+    // interior / boundary tile lists of the SpMV tile kernel (null when the matrix is not tiled)
+    int32_t* tiles_int = nullptr; int32_t* tiles_bnd = nullptr;
+    int64_t  n_int = 0, n_bnd = 0;
+    // peer-memory path
+    bool p2p = false;
+    P2PBlock* blk = nullptr;                 // mine
+    P2PBlock* peer_blk_h[MAXW] = {};         // opened mappings (host copy), [me] = blk
+    double*   peer_x_h[MAXW] = {};           // peers' xext + dst_off (host copy)
+    void*     opened[2 * MAXW] = {};         // raw pointers to close
+    int       nopened = 0;
+    P2PBlock** d_peer_blk = nullptr;         // device copies of the tables
+    double**   d_peer_x = nullptr;
+    int*       d_send_off = nullptr;         // [world+1]
+    int*       d_send_cnt = nullptr;         // [world]
+    int*       d_recv_cnt = nullptr;         // [world]
+    uint32_t halo_seq = 0, red_seq = 0;
+    ~DistCsr() {
+        delete loc;
+        dev_free(send_idx); dev_free(sendbuf); dev_free(tiles_int); dev_free(tiles_bnd);
+        dev_free(d_peer_blk); dev_free(d_peer_x); dev_free(d_send_off); dev_free(d_send_cnt); dev_free(d_recv_cnt);
+        for (int i = 0; i < nopened; ++i) cudaIpcCloseMemHandle(opened[i]);
+        if (xext) { if (xext_cuda_malloc) cudaFree(xext); else dev_free(xext); }
+        if (blk) cudaFree(blk);
+    }
 };
 static std::map<int64_t, DistCsr*> g_dist;
 static int64_t g_next_dh = 1;
@@ -135,13 +184,118 @@ __global__ void to_local_idx_kernel(const int64_t* __restrict__ gidx, size_t n, 
     if (g < lo || g > hi) { atomicExch(err, 1); g = lo; }
     lidx[k] = (int32_t)(g - lo);
 }
+// flags[t] = 1 when tile t (R rows) has an entry in the halo columns
+__global__ void tile_halo_flag_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, int64_t m,
+                                      int R, int64_t nloc, uint32_t* __restrict__ flags) {
+    const int64_t tile = blockIdx.x;
+    const int64_t r0 = tile * R, r1 = min(r0 + R, m);
+    __shared__ int any;
+    if (threadIdx.x == 0) any = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int j = rowptr[r0] + threadIdx.x; j < rowptr[r1]; j += blockDim.x) mine |= (colind[j] >= nloc);
+    if (mine) any = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) flags[tile] = any ? 1u : 0u;
+}
+__global__ void tile_split_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ excl, int64_t ntiles,
+                                  int32_t* __restrict__ t_int, int32_t* __restrict__ t_bnd) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    if (flags[t]) t_bnd[excl[t]] = (int32_t)t; else t_int[t - excl[t]] = (int32_t)t;
+}
+
+// ---------------------------------------------------------------- data-path kernels
 __global__ void pack_kernel(const int32_t* __restrict__ idx, const double* __restrict__ x, size_t n, double* __restrict__ buf) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) buf[k] = x[idx[k]];
 }
 
-static int halo_exchange(DistCsr* d) {
-    if (g_world == 1 || (d->nsend == 0 && d->next == 0)) return AB_OK;
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spins until *p has reached seq; gives up after ~2^31 clocks and reports through *err
+__device__ __forceinline__ void wait_seq(const uint32_t* p, uint32_t seq, uint32_t* err) {
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(p) - seq) < 0) {
+        if (clock64() - t0 > (1ll << 32)) { atomicExch(err, 1u); break; }
+        __nanosleep(20);
+    }
+}
+
+// Gathers this rank's boundary values and stores them into the consumers' halo tails over NVLink
+// (peer_x[p] is peer p's extended vector at the offset reserved for this rank); the last CTA then
+// publishes `seq` in every consumer's flag block.
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const int32_t* __restrict__ send_idx, const double* __restrict__ x, int64_t nsend,
+                 const int* __restrict__ send_off, const int* __restrict__ send_cnt, double* const* __restrict__ peer_x,
+                 P2PBlock* const* __restrict__ peer_blk, P2PBlock* my_blk, int world, int me, uint32_t seq) {
+    __shared__ bool s_last;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nsend; k += (int64_t)gridDim.x * blockDim.x) {
+        int p = 0;
+        while (p + 1 < world && k >= send_off[p + 1]) ++p;
+        peer_x[p][k - send_off[p]] = x[send_idx[k]];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(&my_blk->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x == 0) my_blk->ticket = 0;
+        if ((int)threadIdx.x < world && send_cnt[threadIdx.x] > 0)
+            st_release_sys(&peer_blk[threadIdx.x]->halo_flag[me], seq);
+    }
+}
+
+__global__ void halo_wait_kernel(P2PBlock* blk, const int* __restrict__ recv_cnt, int world, uint32_t seq) {
+    const int p = threadIdx.x;
+    if (p < world && recv_cnt[p] > 0) wait_seq(&blk->halo_flag[p], seq, &blk->err);
+}
+
+// All-reduce (sum) of two doubles over the box, one 32-thread CTA per rank.
+__global__ void p2p_allreduce2_kernel(double* vals, P2PBlock* blk, P2PBlock* const* __restrict__ peer_blk, int world,
+                                      int me, uint32_t seq) {
+    const int t = threadIdx.x, par = seq & 1u;
+    if (t < world) {
+        P2PBlock* dst = peer_blk[t];
+        dst->red[par][me][0] = vals[0];
+        dst->red[par][me][1] = vals[1];
+        __threadfence_system();
+        st_release_sys(&dst->red_flag[par][me], seq);
+        wait_seq(&blk->red_flag[par][t], seq, &blk->err);
+    }
+    __syncwarp();
+    if (t == 0) {
+        double s0 = 0.0, s1 = 0.0;
+        const volatile double* r = &blk->red[par][0][0];
+        for (int p = 0; p < world; ++p) { s0 += r[2 * p]; s1 += r[2 * p + 1]; }   // rank order: same bits everywhere
+        vals[0] = s0;
+        vals[1] = s1;
+    }
+}
+
+static int halo_begin(DistCsr* d) {
+    if (g_world == 1) return AB_OK;
+    if (d->p2p) {
+        ++d->halo_seq;
+        if (d->nsend) {
+            unsigned grid = (unsigned)std::min<int64_t>((d->nsend + 255) / 256, (int64_t)sm_count() * 4);
+            halo_push_kernel<<<grid, 256, 0, stream()>>>(d->send_idx, d->xext, d->nsend, d->d_send_off, d->d_send_cnt,
+                                                         d->d_peer_x, d->d_peer_blk, d->blk, g_world, g_rank, d->halo_seq);
+            AB_LAUNCH_CHECK();
+        }
+        return AB_OK;
+    }
+    if (d->nsend == 0 && d->next == 0) return AB_OK;
     if (d->nsend) {
         pack_kernel<<<(unsigned)((d->nsend + 255) / 256), 256, 0, stream()>>>(d->send_idx, d->xext, (size_t)d->nsend, d->sendbuf);
         AB_LAUNCH_CHECK();
@@ -155,10 +309,47 @@ static int halo_exchange(DistCsr* d) {
     AB_NCCL(g_nccl.GroupEnd());
     return AB_OK;
 }
+static int halo_end(DistCsr* d) {
+    if (g_world == 1 || !d->p2p || d->next == 0) return AB_OK;
+    halo_wait_kernel<<<1, 32, 0, stream()>>>(d->blk, d->d_recv_cnt, g_world, d->halo_seq);
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
 
-static int allreduce2(double* p) {
+static int allreduce2(DistCsr* d, double* p) {
     if (g_world == 1) return AB_OK;
+    if (d->p2p) {
+        ++d->red_seq;
+        p2p_allreduce2_kernel<<<1, 32, 0, stream()>>>(p, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq);
+        AB_LAUNCH_CHECK();
+        return AB_OK;
+    }
     AB_NCCL(g_nccl.AllReduce(p, p, 2, ncclDouble, ncclSum, g_comm, stream()));
+    return AB_OK;
+}
+
+// y = A_local [x_owned ; halo], halo exchange overlapped with the interior tiles when possible
+static int dist_spmv_dev(DistCsr* d, double* y, const double* dotvec, double* dots, const int* done) {
+    Csr* c = d->loc;
+    AB_TRY(halo_begin(d));
+    const bool split = g_world > 1 && d->p2p && d->tiles_int && d->n_bnd > 0;
+    if (!split) {
+        AB_TRY(halo_end(d));
+        return launch_spmv(c, d->xext, y, dotvec, dots, c->partials, c->ticket, done);
+    }
+    if (d->n_int > 0)
+        AB_TRY(launch_spmv_part(c, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_int, d->n_int, 0));
+    AB_TRY(halo_end(d));
+    return launch_spmv_part(c, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_bnd, d->n_bnd,
+                            d->n_int > 0 ? 1 : 0);
+}
+
+static int check_p2p_err(DistCsr* d) {
+    if (!d->p2p) return AB_OK;
+    uint32_t e = 0;
+    AB_CUDA(cudaMemcpyAsync(&e, &d->blk->err, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    if (e) return fail(AB_ENCCL, "peer-memory wait timed out (a rank stopped participating)");
     return AB_OK;
 }
 
@@ -175,7 +366,7 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
     cg_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->dinv, x, r, p, n, tol, s, c->partials, c->ticket, raw);
     AB_LAUNCH_CHECK();
     if (raw) {
-        AB_TRY(allreduce2(s->red));
+        AB_TRY(allreduce2(d, s->red));
         cg_fin_kernel<<<1, 1, 0, stream()>>>(s, 0, 0, tol);
         AB_LAUNCH_CHECK();
     }
@@ -187,13 +378,12 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
         int chunk = maxit - it < check ? maxit - it : check;
         for (int k = 0; k < chunk; ++k, ++it) {
             const int parity = it & 1;
-            AB_TRY(halo_exchange(d));
-            AB_TRY(launch_spmv(c, p, Ap, p, s->dots, c->partials, c->ticket, &s->done));
-            if (raw) AB_TRY(allreduce2(s->dots));
+            AB_TRY(dist_spmv_dev(d, Ap, p, s->dots, &s->done));
+            if (raw) AB_TRY(allreduce2(d, s->dots));
             cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, raw);
             AB_LAUNCH_CHECK();
             if (raw) {
-                AB_TRY(allreduce2(s->red));
+                AB_TRY(allreduce2(d, s->red));
                 cg_fin_kernel<<<1, 1, 0, stream()>>>(s, 1, parity, tol);
                 AB_LAUNCH_CHECK();
             }
@@ -205,6 +395,70 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
         if (h.done) break;   // identical on every rank: the flags derive from all-reduced values
     }
     AB_TRY(read_scal(c, fin));
+    AB_TRY(check_p2p_err(d));
+    return AB_OK;
+}
+
+// ---------------------------------------------------------------- peer-memory setup
+struct IpcPair { cudaIpcMemHandle_t x, blk; };
+
+static int setup_p2p(DistCsr* d, const std::vector<int64_t>& dst_off_from_peer) {
+    // every rank must take the same path: local success is min-reduced over the box
+    int ok = 1;
+    IpcPair mine;
+    memset(&mine, 0, sizeof(mine));
+    if (cudaMalloc((void**)&d->blk, sizeof(P2PBlock)) != cudaSuccess) { cudaGetLastError(); ok = 0; d->blk = nullptr; }
+    if (ok) {
+        cudaMemset(d->blk, 0, sizeof(P2PBlock));
+        if (cudaIpcGetMemHandle(&mine.x, d->xext) != cudaSuccess || cudaIpcGetMemHandle(&mine.blk, d->blk) != cudaSuccess) {
+            cudaGetLastError(); ok = 0;
+        }
+    }
+    DevBuf<char> all;
+    AB_TRY(all.alloc(sizeof(IpcPair) * (size_t)g_world));
+    AB_CUDA(cudaMemcpyAsync(all.p + sizeof(IpcPair) * g_rank, &mine, sizeof(IpcPair), cudaMemcpyHostToDevice, stream()));
+    AB_NCCL(g_nccl.AllGather(all.p + sizeof(IpcPair) * g_rank, all.p, sizeof(IpcPair), ncclChar, g_comm, stream()));
+    std::vector<IpcPair> hall(g_world);
+    AB_CUDA(cudaMemcpyAsync(hall.data(), all.p, sizeof(IpcPair) * (size_t)g_world, cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    if (ok) {
+        for (int p = 0; p < g_world && ok; ++p) {
+            if (p == g_rank) { d->peer_blk_h[p] = d->blk; d->peer_x_h[p] = nullptr; continue; }
+            void* pb = nullptr; void* px = nullptr;
+            if (cudaIpcOpenMemHandle(&pb, hall[p].blk, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            d->opened[d->nopened++] = pb;
+            d->peer_blk_h[p] = (P2PBlock*)pb;
+            if (d->send_cnt[p] > 0) {
+                if (cudaIpcOpenMemHandle(&px, hall[p].x, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+                d->opened[d->nopened++] = px;
+                d->peer_x_h[p] = (double*)px + dst_off_from_peer[p];
+            }
+        }
+    }
+    // agree
+    DevBuf<double> flag;
+    AB_TRY(flag.alloc(2));
+    double hv[2] = {(double)ok, 0.0};
+    AB_CUDA(cudaMemcpyAsync(flag.p, hv, sizeof(hv), cudaMemcpyHostToDevice, stream()));
+    AB_NCCL(g_nccl.AllReduce(flag.p, flag.p, 2, ncclDouble, ncclMin, g_comm, stream()));
+    AB_CUDA(cudaMemcpyAsync(hv, flag.p, sizeof(hv), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    if (hv[0] < 0.5) { d->p2p = false; return AB_OK; }
+    AB_TRY(dev_alloc((void**)&d->d_peer_blk, sizeof(P2PBlock*) * MAXW));
+    AB_TRY(dev_alloc((void**)&d->d_peer_x, sizeof(double*) * MAXW));
+    AB_TRY(dev_alloc((void**)&d->d_send_off, sizeof(int) * (MAXW + 1)));
+    AB_TRY(dev_alloc((void**)&d->d_send_cnt, sizeof(int) * MAXW));
+    AB_TRY(dev_alloc((void**)&d->d_recv_cnt, sizeof(int) * MAXW));
+    int so[MAXW + 1] = {}, sc[MAXW] = {}, rc[MAXW] = {};
+    for (int p = 0; p < g_world; ++p) { so[p] = d->send_off[p]; sc[p] = d->send_cnt[p]; rc[p] = d->recv_cnt[p]; }
+    for (int p = g_world; p <= MAXW; ++p) so[p] = (int)d->nsend;
+    AB_CUDA(cudaMemcpyAsync(d->d_peer_blk, d->peer_blk_h, sizeof(P2PBlock*) * MAXW, cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemcpyAsync(d->d_peer_x, d->peer_x_h, sizeof(double*) * MAXW, cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemcpyAsync(d->d_send_off, so, sizeof(so), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemcpyAsync(d->d_send_cnt, sc, sizeof(sc), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemcpyAsync(d->d_recv_cnt, rc, sizeof(rc), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    d->p2p = true;
     return AB_OK;
 }
 
@@ -226,7 +480,7 @@ int ab_dist_unique_id(void* id128) {
 
 int ab_dist_init(int rank, int world, const void* id128) {
     AB_TRY(ensure_device());
-    if (world < 1 || rank < 0 || rank >= world) return fail(AB_EINVAL, "bad rank/world");
+    if (world < 1 || world > MAXW || rank < 0 || rank >= world) return fail(AB_EINVAL, "bad rank/world (at most %d ranks)", MAXW);
     g_rank = rank; g_world = world;
     if (world == 1) return AB_OK;
     if (!id128) return fail(AB_EINVAL, "null id buffer");
@@ -245,6 +499,7 @@ int ab_dist_finalize(void) {
         for (auto& kv : g_dist) all.push_back(kv.second);
         g_dist.clear();
     }
+    if (!all.empty()) cudaStreamSynchronize(stream());
     for (auto* d : all) delete d;
     if (g_comm && g_nccl.CommDestroy) { g_nccl.CommDestroy(g_comm); g_comm = nullptr; }
     g_rank = 0; g_world = 1;
@@ -327,11 +582,20 @@ int ab_dist_csr_create(int64_t h_local, int64_t ilower, int64_t iupper, int64_t 
             AB_LAUNCH_CHECK();
         }
         AB_TRY(csr_finalize(c));
-        AB_TRY(dev_alloc((void**)&d->xext, (size_t)(nloc + next + 2) * sizeof(double)));
-        AB_CUDA(cudaMemsetAsync(d->xext, 0, (size_t)(nloc + next + 2) * sizeof(double), stream()));
+        const bool want_p2p = g_world > 1 && opt("dist_p2p", 1.0) != 0.0;
+        const size_t xbytes = (size_t)(nloc + next + 2) * sizeof(double);
+        if (want_p2p) {
+            // IPC needs a cudaMalloc allocation (not the stream-ordered pool)
+            if (cudaMalloc((void**)&d->xext, xbytes) != cudaSuccess) { cudaGetLastError(); return fail(AB_ECUDA, "cudaMalloc(%zu) failed", xbytes); }
+            d->xext_cuda_malloc = true;
+        } else {
+            AB_TRY(dev_alloc((void**)&d->xext, xbytes));
+        }
+        AB_CUDA(cudaMemsetAsync(d->xext, 0, xbytes, stream()));
         // ---- 4. who owns my halo columns (ext is sorted, owners are contiguous runs)
         d->send_cnt.assign(g_world, 0); d->send_off.assign(g_world, 0);
         d->recv_cnt.assign(g_world, 0); d->recv_off.assign(g_world, 0);
+        d->dst_off.assign(g_world, 0);
         if (g_world == 1) return AB_OK;
         std::vector<int64_t> hext(next);
         if (next) {
@@ -349,22 +613,29 @@ int ab_dist_csr_create(int64_t h_local, int64_t ilower, int64_t iupper, int64_t 
             }
             if (k != hext.size()) return fail(AB_EINVAL, "a halo column is owned by no rank (row ranges must tile [0,N))");
         }
-        // ---- 5. tell each owner how many / which rows I need
-        DevBuf<int32_t> dcnt_out, dcnt_in;
-        AB_TRY(dcnt_out.alloc(g_world)); AB_TRY(dcnt_in.alloc(g_world));
-        AB_CUDA(cudaMemcpyAsync(dcnt_out.p, d->recv_cnt.data(), (size_t)g_world * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
-        AB_CUDA(cudaMemsetAsync(dcnt_in.p, 0, (size_t)g_world * sizeof(int32_t), stream()));
+        // ---- 5. tell each owner how many rows I need and where its values land in my vector
+        std::vector<int64_t> out2(2 * (size_t)g_world, 0), in2(2 * (size_t)g_world, 0);
+        for (int p = 0; p < g_world; ++p) { out2[2 * p] = d->recv_cnt[p]; out2[2 * p + 1] = nloc + d->recv_off[p]; }
+        DevBuf<int64_t> dout, din;
+        AB_TRY(dout.alloc(2 * (size_t)g_world)); AB_TRY(din.alloc(2 * (size_t)g_world));
+        AB_CUDA(cudaMemcpyAsync(dout.p, out2.data(), out2.size() * sizeof(int64_t), cudaMemcpyHostToDevice, stream()));
+        AB_CUDA(cudaMemsetAsync(din.p, 0, in2.size() * sizeof(int64_t), stream()));
         AB_NCCL(g_nccl.GroupStart());
         for (int p = 0; p < g_world; ++p) {
             if (p == g_rank) continue;
-            AB_NCCL(g_nccl.Send(dcnt_out.p + p, 1, ncclInt32, p, g_comm, stream()));
-            AB_NCCL(g_nccl.Recv(dcnt_in.p + p, 1, ncclInt32, p, g_comm, stream()));
+            AB_NCCL(g_nccl.Send(dout.p + 2 * p, 2, ncclInt64, p, g_comm, stream()));
+            AB_NCCL(g_nccl.Recv(din.p + 2 * p, 2, ncclInt64, p, g_comm, stream()));
         }
         AB_NCCL(g_nccl.GroupEnd());
-        AB_CUDA(cudaMemcpyAsync(d->send_cnt.data(), dcnt_in.p, (size_t)g_world * sizeof(int32_t), cudaMemcpyDeviceToHost, stream()));
+        AB_CUDA(cudaMemcpyAsync(in2.data(), din.p, in2.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, stream()));
         AB_CUDA(cudaStreamSynchronize(stream()));
         int64_t ns = 0;
-        for (int p = 0; p < g_world; ++p) { d->send_off[p] = (int)ns; ns += d->send_cnt[p]; }
+        for (int p = 0; p < g_world; ++p) {
+            d->send_cnt[p] = (int)in2[2 * p];
+            d->dst_off[p]  = in2[2 * p + 1];
+            d->send_off[p] = (int)ns;
+            ns += d->send_cnt[p];
+        }
         d->nsend = ns;
         DevBuf<int64_t> gsend;
         AB_TRY(gsend.alloc((size_t)ns));
@@ -388,6 +659,26 @@ int ab_dist_csr_create(int64_t h_local, int64_t ilower, int64_t iupper, int64_t 
             AB_CUDA(cudaStreamSynchronize(stream()));
             if (herr) return fail(AB_EINVAL, "a peer asked for a row this rank does not own");
         }
+        // ---- 6. interior / boundary tiles (overlap of the halo with the interior SpMV)
+        const int R = spmv_tile_rows(c);
+        if (R && next && nloc) {
+            const int64_t ntiles = (nloc + R - 1) / R;
+            DevBuf<uint32_t> tf, te, tot;
+            AB_TRY(tf.alloc(ntiles)); AB_TRY(te.alloc(ntiles)); AB_TRY(tot.alloc(1));
+            tile_halo_flag_kernel<<<(unsigned)ntiles, 128, 0, stream()>>>(c->rowptr, c->colind, nloc, R, nloc, tf.p);
+            AB_LAUNCH_CHECK();
+            AB_TRY(scan_exclusive_u32(tf.p, te.p, (size_t)ntiles, tot.p));
+            uint32_t nb_ = 0;
+            AB_CUDA(cudaMemcpyAsync(&nb_, tot.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream()));
+            AB_CUDA(cudaStreamSynchronize(stream()));
+            d->n_bnd = nb_; d->n_int = ntiles - nb_;
+            AB_TRY(dev_alloc((void**)&d->tiles_int, (size_t)(d->n_int + 1) * sizeof(int32_t)));
+            AB_TRY(dev_alloc((void**)&d->tiles_bnd, (size_t)(d->n_bnd + 1) * sizeof(int32_t)));
+            tile_split_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream()>>>(tf.p, te.p, ntiles, d->tiles_int, d->tiles_bnd);
+            AB_LAUNCH_CHECK();
+        }
+        // ---- 7. peer mappings
+        if (want_p2p) AB_TRY(setup_p2p(d, d->dst_off));
         AB_CUDA(cudaStreamSynchronize(stream()));
         return AB_OK;
     };
@@ -411,6 +702,7 @@ int ab_dist_destroy(int64_t dh) {
         d = it->second;
         g_dist.erase(it);
     }
+    cudaStreamSynchronize(stream());
     delete d;
     return AB_OK;
 }
@@ -423,9 +715,15 @@ int ab_dist_spmv(int64_t dh, const double* x_, double* y_) {
     std::lock_guard<std::mutex> lk(big_lock());
     Out<double> y;
     AB_TRY(y.bind(y_, (size_t)d->nloc));
+    AB_TRY(csr_ensure_work(d->loc, 4));
     if (d->nloc) AB_CUDA(cudaMemcpyAsync(d->xext, x_, (size_t)d->nloc * sizeof(double), cudaMemcpyDefault, stream()));
-    AB_TRY(halo_exchange(d));
-    AB_TRY(launch_spmv(d->loc, d->xext, y.d, nullptr, nullptr, nullptr, nullptr, nullptr));
+    AB_TRY(dist_spmv_dev(d, y.d, nullptr, nullptr, nullptr));
+    if (g_world > 1 && d->p2p) {
+        // box-wide rendezvous: nobody may overwrite a halo tail that a slower rank is still reading
+        SolveScal* s = (SolveScal*)d->loc->scal;
+        AB_TRY(allreduce2(d, s->red));
+        AB_TRY(check_p2p_err(d));
+    }
     AB_TRY(y.commit());
     return AB_OK;
 }

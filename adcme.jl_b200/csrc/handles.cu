@@ -120,6 +120,7 @@ Csr::~Csr() {
     dev_free(perm); dev_free(segstart); dev_free(slot); dev_free(entry_row);
     dev_free(dinv); dev_free(tperm); dev_free(work); dev_free(scal);
     dev_free(partials); dev_free(ticket);
+    dev_free(long_rows); dev_free(long_row_chunk0); dev_free(long_chunk_row); dev_free(long_chunk_start);
 }
 
 Csr* csr_get(int64_t h) {

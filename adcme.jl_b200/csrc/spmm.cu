@@ -6,73 +6,150 @@
 //     Y[i,:]  = sum_k v_k X[j_k,:]
 //     dX      = A' dY
 //     dv[k]   = <dY[i_k,:], X[j_k,:]>      one value per INPUT triplet
+//
+// k >= 32: one warp per row; the row's entries are fetched 32 at a time (coalesced) and broadcast
+// by shuffle; lane c owns columns c, c+32, … so every X-row gather is one or more full 256-byte
+// requests, UB of them in flight per warp.  Rows longer than LONG_ROW (power-law tails) are cut into
+// CHUNK-entry pieces handled by separate warps, with a fixed-order combine — no atomics, so the
+// result is deterministic.  Algorithmic bytes: 12*nnz + 4*(m+1) + 8*k*(n+m) compulsory;
+// 12*nnz + 8*k*(nnz+m) under the no-reuse gather model (DESIGN.md reports both).
 #include "common.cuh"
 
 namespace ab {
 
-// One group of CL lanes per row; lane c of the group owns columns c, c+CL, ...  (NC of them).
-template <int CL, int NC>
+constexpr int LONG_ROW = 4096;
+constexpr int CHUNK    = 1024;
+
+// ---------------------------------------------------------------- long-row work list
+__global__ void long_flag_kernel(const int32_t* __restrict__ rowptr, int64_t m, uint32_t* __restrict__ flags) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < m) flags[r] = (rowptr[r + 1] - rowptr[r] > LONG_ROW) ? 1u : 0u;
+}
+__global__ void long_compact_kernel(const int32_t* __restrict__ rowptr, int64_t m, const uint32_t* __restrict__ excl,
+                                    int32_t* __restrict__ rows, uint32_t* __restrict__ nchunk) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    int len = rowptr[r + 1] - rowptr[r];
+    if (len > LONG_ROW) { rows[excl[r]] = (int32_t)r; nchunk[excl[r]] = (uint32_t)((len + CHUNK - 1) / CHUNK); }
+}
+__global__ void long_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ rows,
+                                 const int32_t* __restrict__ chunk0, int64_t nlong, int32_t* __restrict__ crow,
+                                 int32_t* __restrict__ cstart) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlong) return;
+    const int r = rows[i], a = rowptr[r], b = rowptr[r + 1];
+    int cidx = chunk0[i];
+    for (int s = a; s < b; s += CHUNK, ++cidx) { crow[cidx] = r; cstart[cidx] = s; }
+}
+
+static int csr_ensure_long(Csr* c) {
+    if (c->long_nrows >= 0) return AB_OK;
+    if (c->max_row_nnz <= LONG_ROW || c->m == 0) { c->long_nrows = 0; c->long_nchunks = 0; return AB_OK; }
+    DevBuf<uint32_t> flags, total, nchunk;
+    AB_TRY(flags.alloc(c->m)); AB_TRY(total.alloc(1));
+    unsigned nb = (unsigned)((c->m + 255) / 256);
+    long_flag_kernel<<<nb, 256, 0, stream()>>>(c->rowptr, c->m, flags.p);
+    AB_LAUNCH_CHECK();
+    AB_TRY(scan_exclusive_u32(flags.p, flags.p, (size_t)c->m, total.p));
+    uint32_t nlong = 0;
+    AB_CUDA(cudaMemcpyAsync(&nlong, total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    AB_TRY(dev_alloc((void**)&c->long_rows, (size_t)(nlong + 1) * sizeof(int32_t)));
+    AB_TRY(dev_alloc((void**)&c->long_row_chunk0, (size_t)(nlong + 1) * sizeof(int32_t)));
+    AB_TRY(nchunk.alloc(nlong + 1));
+    AB_CUDA(cudaMemsetAsync(nchunk.p, 0, (size_t)(nlong + 1) * sizeof(uint32_t), stream()));
+    long_compact_kernel<<<nb, 256, 0, stream()>>>(c->rowptr, c->m, flags.p, c->long_rows, nchunk.p);
+    AB_LAUNCH_CHECK();
+    AB_TRY(scan_exclusive_u32(nchunk.p, (uint32_t*)c->long_row_chunk0, (size_t)nlong + 1, total.p));
+    uint32_t nch = 0;
+    AB_CUDA(cudaMemcpyAsync(&nch, total.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    AB_TRY(dev_alloc((void**)&c->long_chunk_row, (size_t)(nch + 1) * sizeof(int32_t)));
+    AB_TRY(dev_alloc((void**)&c->long_chunk_start, (size_t)(nch + 1) * sizeof(int32_t)));
+    long_fill_kernel<<<(nlong + 255) / 256, 256, 0, stream()>>>(c->rowptr, c->long_rows, c->long_row_chunk0, nlong,
+                                                               c->long_chunk_row, c->long_chunk_start);
+    AB_LAUNCH_CHECK();
+    c->long_nrows = nlong; c->long_nchunks = nch;
+    return AB_OK;
+}
+
+// ---------------------------------------------------------------- SpMM
+// One group of CL lanes per row; lane c of the group owns column c (k <= 32 here).
+template <int CL>
 __global__ void __launch_bounds__(256)
 spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
             const double* __restrict__ values, const double* __restrict__ X, double* __restrict__ Y,
-            int64_t m, int k, int c0) {
+            int64_t m, int k) {
     constexpr int RPB = 256 / CL;
     const int sub = threadIdx.x % CL;
     for (int64_t rb = (int64_t)blockIdx.x * RPB; rb < m; rb += (int64_t)gridDim.x * RPB) {
         const int64_t row = rb + threadIdx.x / CL;
-        if (row >= m) continue;
-        double acc[NC];
-#pragma unroll
-        for (int q = 0; q < NC; ++q) acc[q] = 0.0;
+        if (row >= m || sub >= k) continue;
+        double acc = 0.0;
         const int a = rowptr[row], b = rowptr[row + 1];
-        for (int j = a; j < b; ++j) {
-            const double v = values[j];
-            const double* xr = X + (size_t)colind[j] * k + c0;
+        int j = a;
+        for (; j + 4 <= b; j += 4) {
+            double v[4], xv[4];
 #pragma unroll
-            for (int q = 0; q < NC; ++q) {
-                const int cc = sub + q * CL;
-                if (c0 + cc < k) acc[q] = fma(v, __ldg(xr + cc), acc[q]);
-            }
-        }
-        double* yr = Y + (size_t)row * k + c0;
+            for (int u = 0; u < 4; ++u) { v[u] = values[j + u]; xv[u] = __ldg(X + (size_t)colind[j + u] * k + sub); }
 #pragma unroll
-        for (int q = 0; q < NC; ++q) {
-            const int cc = sub + q * CL;
-            if (c0 + cc < k) yr[cc] = acc[q];
+            for (int u = 0; u < 4; ++u) acc = fma(v[u], xv[u], acc);
         }
+        for (; j < b; ++j) acc = fma(values[j], __ldg(X + (size_t)colind[j] * k + sub), acc);
+        Y[(size_t)row * k + sub] = acc;
     }
 }
 
-// k >= 32: one warp per row, entries fetched 32 at a time (coalesced) and broadcast by shuffle.
+// accumulates entries [a,b) of one row into acc[] (lane owns columns c0+lane+32u)
 template <int NC>
-__global__ void __launch_bounds__(256)
-spmm_warp_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
-                 const double* __restrict__ values, const double* __restrict__ X, double* __restrict__ Y,
-                 int64_t m, int k, int c0) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
-    const int64_t nwarp = ((int64_t)gridDim.x * 256) >> 5;
-    for (int64_t row = warp0; row < m; row += nwarp) {
-        double acc[NC];
+__device__ __forceinline__ void spmm_range(const int32_t* __restrict__ colind, const double* __restrict__ values,
+                                           const double* __restrict__ X, int k, int c0, int a, int b, int lane,
+                                           double (&acc)[NC]) {
+    constexpr int UB = NC == 1 ? 8 : 4;
+    for (int base = a; base < b; base += 32) {
+        const int cnt = min(32, b - base);
+        int cj = 0;
+        double vj = 0.0;
+        if (lane < cnt) { cj = colind[base + lane]; vj = values[base + lane]; }
+        // UB entries at a time: all their X-row gathers are issued before the first FMA needs one
+        for (int q0 = 0; q0 < cnt; q0 += UB) {
+            double xv[UB][NC], vq[UB];
 #pragma unroll
-        for (int q = 0; q < NC; ++q) acc[q] = 0.0;
-        const int a = rowptr[row], b = rowptr[row + 1];
-        for (int base = a; base < b; base += 32) {
-            const int cnt = min(32, b - base);
-            int cj = 0;
-            double vj = 0.0;
-            if (lane < cnt) { cj = colind[base + lane]; vj = values[base + lane]; }
-            for (int q = 0; q < cnt; ++q) {
-                const int cq = __shfl_sync(0xffffffffu, cj, q);
-                const double vq = __shfl_sync(0xffffffffu, vj, q);
+            for (int b8 = 0; b8 < UB; ++b8) {
+                const int q = q0 + b8;
+                const int cq = __shfl_sync(0xffffffffu, cj, q & 31);
+                vq[b8] = __shfl_sync(0xffffffffu, vj, q & 31);
                 const double* xr = X + (size_t)cq * k + c0;
 #pragma unroll
                 for (int u = 0; u < NC; ++u) {
                     const int cc = lane + 32 * u;
-                    if (c0 + cc < k) acc[u] = fma(vq, __ldg(xr + cc), acc[u]);
+                    xv[b8][u] = (q < cnt && c0 + cc < k) ? __ldg(xr + cc) : 0.0;
                 }
             }
+#pragma unroll
+            for (int b8 = 0; b8 < UB; ++b8)
+#pragma unroll
+                for (int u = 0; u < NC; ++u) acc[u] = fma(vq[b8], xv[b8][u], acc[u]);
         }
+    }
+}
+
+// k >= 32: one warp per row (rows longer than long_thresh are left to the chunk kernels)
+template <int NC>
+__global__ void __launch_bounds__(256)
+spmm_warp_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                 const double* __restrict__ values, const double* __restrict__ X, double* __restrict__ Y,
+                 int64_t m, int k, int c0, int long_thresh) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * 256) >> 5;
+    for (int64_t row = warp0; row < m; row += nwarp) {
+        const int a = rowptr[row], b = rowptr[row + 1];
+        if (b - a > long_thresh) continue;
+        double acc[NC];
+#pragma unroll
+        for (int q = 0; q < NC; ++q) acc[q] = 0.0;
+        spmm_range<NC>(colind, values, X, k, c0, a, b, lane, acc);
         double* yr = Y + (size_t)row * k + c0;
 #pragma unroll
         for (int u = 0; u < NC; ++u) {
@@ -81,22 +158,80 @@ spmm_warp_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
         }
     }
 }
+// one warp per CHUNK of a long row -> partial[chunk, :]
+template <int NC>
+__global__ void __launch_bounds__(256)
+spmm_chunk_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                  const double* __restrict__ values, const double* __restrict__ X,
+                  const int32_t* __restrict__ chunk_row, const int32_t* __restrict__ chunk_start, int64_t nchunks,
+                  int k, int c0, double* __restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * 256) >> 5;
+    for (int64_t ch = warp0; ch < nchunks; ch += nwarp) {
+        const int a = chunk_start[ch], b = min(a + CHUNK, rowptr[chunk_row[ch] + 1]);
+        double acc[NC];
+#pragma unroll
+        for (int q = 0; q < NC; ++q) acc[q] = 0.0;
+        spmm_range<NC>(colind, values, X, k, c0, a, b, lane, acc);
+#pragma unroll
+        for (int u = 0; u < NC; ++u) {
+            const int cc = lane + 32 * u;
+            if (c0 + cc < k) partial[(size_t)ch * k + c0 + cc] = acc[u];
+        }
+    }
+}
+// one warp per long row: chunk partials added in chunk order (deterministic)
+__global__ void __launch_bounds__(256)
+spmm_combine_kernel(const int32_t* __restrict__ long_rows, const int32_t* __restrict__ chunk0, int64_t nlong, int k,
+                    const double* __restrict__ partial, double* __restrict__ Y) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (w >= nlong) return;
+    const int c_a = chunk0[w], c_b = chunk0[w + 1];
+    for (int cc = lane; cc < k; cc += 32) {
+        double s = 0.0;
+        for (int ch = c_a; ch < c_b; ++ch) s += partial[(size_t)ch * k + cc];
+        Y[(size_t)long_rows[w] * k + cc] = s;
+    }
+}
 
-int launch_spmm(const Csr* c, const double* X, int64_t k, double* Y) {
+int launch_spmm(const Csr* c_, const double* X, int64_t k, double* Y) {
+    Csr* c = const_cast<Csr*>(c_);
     if (c->m == 0 || k == 0) return AB_OK;
     if (k == 1) return launch_spmv(c, X, Y, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (k > INT32_MAX / 2) return fail(AB_EUNSUPPORTED, "k too large");
     const int kk = (int)k;
     if (kk >= 32) {
+        AB_TRY(csr_ensure_long(c));
+        const int thresh = c->long_nrows > 0 ? LONG_ROW : INT32_MAX;
         int64_t nblk = (c->m + 7) / 8;
         int64_t cap  = (int64_t)sm_count() * 8 * 8;
         unsigned grid = (unsigned)(nblk < cap ? nblk : cap);
+        DevBuf<double> partial;
+        if (c->long_nrows > 0) AB_TRY(partial.alloc((size_t)c->long_nchunks * kk));
+        unsigned gridc = (unsigned)((c->long_nchunks + 7) / 8);
         for (int c0 = 0; c0 < kk; c0 += 128) {
-            int rem = kk - c0;
-            if (rem > 96) spmm_warp_kernel<4><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, Y, c->m, kk, c0);
-            else if (rem > 64) spmm_warp_kernel<3><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, Y, c->m, kk, c0);
-            else if (rem > 32) spmm_warp_kernel<2><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, Y, c->m, kk, c0);
-            else spmm_warp_kernel<1><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, Y, c->m, kk, c0);
+            const int rem = kk - c0;
+#define AB_W(NCC)                                                                                                   \
+    do {                                                                                                            \
+        spmm_warp_kernel<NCC><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, Y, c->m, kk, c0, thresh); \
+        AB_LAUNCH_CHECK();                                                                                          \
+        if (c->long_nrows > 0) {                                                                                    \
+            spmm_chunk_kernel<NCC><<<gridc, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, c->long_chunk_row, \
+                                                                c->long_chunk_start, c->long_nchunks, kk, c0, partial.p); \
+            AB_LAUNCH_CHECK();                                                                                      \
+        }                                                                                                           \
+    } while (0)
+            if (rem > 96) AB_W(4);
+            else if (rem > 64) AB_W(3);
+            else if (rem > 32) AB_W(2);
+            else AB_W(1);
+#undef AB_W
+        }
+        if (c->long_nrows > 0) {
+            spmm_combine_kernel<<<(unsigned)((c->long_nrows + 7) / 8), 256, 0, stream()>>>(c->long_rows, c->long_row_chunk0,
+                                                                                         c->long_nrows, kk, partial.p, Y);
             AB_LAUNCH_CHECK();
         }
         return AB_OK;
@@ -107,7 +242,7 @@ int launch_spmm(const Csr* c, const double* X, int64_t k, double* Y) {
     int64_t nblk = (c->m + rpb - 1) / rpb;
     int64_t cap  = (int64_t)sm_count() * 8 * 8;
     unsigned grid = (unsigned)(nblk < cap ? nblk : cap);
-#define AB_SPMM(CLL) spmm_kernel<CLL, 1><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, Y, c->m, kk, 0)
+#define AB_SPMM(CLL) spmm_kernel<CLL><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, Y, c->m, kk)
     switch (CL) {
         case 2: AB_SPMM(2); break;
         case 4: AB_SPMM(4); break;
@@ -120,7 +255,8 @@ int launch_spmm(const Csr* c, const double* X, int64_t k, double* Y) {
     return AB_OK;
 }
 
-// SDDMM sampled at the stored pattern: dv[e] = <dY[row_e,:], X[col_e,:]>, CL lanes per entry
+// ---------------------------------------------------------------- SDDMM (value gradient)
+// small k: CL lanes per stored entry, dv[e] = <dY[row_e,:], X[col_e,:]>
 template <int CL>
 __global__ void __launch_bounds__(256)
 sddmm_kernel(const int32_t* __restrict__ entry_row, const int32_t* __restrict__ colind,
@@ -142,6 +278,79 @@ sddmm_kernel(const int32_t* __restrict__ entry_row, const int32_t* __restrict__ 
     }
 }
 
+// 32 <= k <= 128: a warp handles entries [a,b) of one row.  The dY row stays in registers; 32 entries
+// at once: lane c accumulates its columns' products for each entry (32 independent X-row gathers in
+// flight), then a butterfly transpose-reduce (31 shuffles per 32 entries instead of 160) leaves
+// entry l's dot product in lane l, stored coalesced.
+template <int NC>
+__device__ __forceinline__ void sddmm_range(const int32_t* __restrict__ colind, const double* __restrict__ X, int k,
+                                            const double (&dy)[NC], int a, int b, int lane, double* __restrict__ dv) {
+    constexpr int EB = 16;   // entries per batch
+    for (int base = a; base < b; base += EB) {
+        const int cnt = min(EB, b - base);
+        // lanes beyond the batch keep column 0: their gathers hit row 0 of X (cached) and their
+        // products are never stored, so every load below is unconditional and all EB of them are
+        // in flight together (a predicated load inside a branch would serialise the warp)
+        const int cj = lane < cnt ? colind[base + lane] : 0;
+        double prod[EB];
+#pragma unroll
+        for (int q = 0; q < EB; ++q) {
+            const int cq = __shfl_sync(0xffffffffu, cj, q);
+            const double* xr = X + (size_t)cq * k;
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < NC; ++u) {
+                const int cc = lane + 32 * u;
+                const double xv = __ldg(xr + (cc < k ? cc : 0));
+                s = cc < k ? fma(dy[u], xv, s) : s;
+            }
+            prod[q] = s;
+        }
+#pragma unroll
+        for (int s = EB / 2; s >= 1; s >>= 1) {
+            const bool up = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+                const double send = up ? prod[i] : prod[i + s];
+                const double keep = up ? prod[i + s] : prod[i];
+                prod[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            }
+        }
+        // lanes l and l^16 each hold half of entry (l & 15)'s sum
+        const double tot = prod[0] + __shfl_xor_sync(0xffffffffu, prod[0], 16);
+        if (lane < cnt) dv[base + lane] = tot;
+    }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(256)
+sddmm_warp_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                  const double* __restrict__ dY, const double* __restrict__ X, int64_t m, int k,
+                  const int32_t* __restrict__ chunk_row, const int32_t* __restrict__ chunk_start, int64_t nchunks,
+                  int long_thresh, double* __restrict__ dv) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * 256) >> 5;
+    // work items: the m rows (long ones skipped) followed by the chunks of the long rows
+    for (int64_t w = warp0; w < m + nchunks; w += nwarp) {
+        int64_t row; int a, b;
+        if (w < m) {
+            row = w; a = rowptr[row]; b = rowptr[row + 1];
+            if (a == b || b - a > long_thresh) continue;
+        } else {
+            const int64_t ch = w - m;
+            row = chunk_row[ch]; a = chunk_start[ch]; b = min(a + CHUNK, rowptr[row + 1]);
+        }
+        double dy[NC];
+#pragma unroll
+        for (int u = 0; u < NC; ++u) {
+            const int cc = lane + 32 * u;
+            dy[u] = cc < k ? __ldg(dY + (size_t)row * k + cc) : 0.0;
+        }
+        sddmm_range<NC>(colind, X, k, dy, a, b, lane, dv);
+    }
+}
+
 __global__ void gather_slot_kernel(const int32_t* __restrict__ slot, const double* __restrict__ dv, size_t T,
                                    double* __restrict__ out) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -150,6 +359,23 @@ __global__ void gather_slot_kernel(const int32_t* __restrict__ slot, const doubl
 
 static int launch_sddmm(Csr* c, const double* dY, const double* X, int k, double* dv) {
     if (c->nnz == 0) return AB_OK;
+    if (k >= 32 && k <= 128) {
+        AB_TRY(csr_ensure_long(c));
+        const int thresh = c->long_nrows > 0 ? LONG_ROW : INT32_MAX;
+        int64_t nblk = (c->m + c->long_nchunks + 7) / 8;
+        int64_t cap  = (int64_t)sm_count() * 8 * 8;
+        unsigned grid = (unsigned)(nblk < cap ? nblk : cap);
+#define AB_SDW(NCC)                                                                                                \
+    sddmm_warp_kernel<NCC><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, dY, X, c->m, k, c->long_chunk_row,    \
+                                                       c->long_chunk_start, c->long_nchunks, thresh, dv)
+        if (k <= 32) AB_SDW(1);
+        else if (k <= 64) AB_SDW(2);
+        else if (k <= 96) AB_SDW(3);
+        else AB_SDW(4);
+#undef AB_SDW
+        AB_LAUNCH_CHECK();
+        return AB_OK;
+    }
     AB_TRY(csr_ensure_entry_row(c));
     int CL = 1;
     while (CL < k && CL < 32) CL <<= 1;
@@ -183,6 +409,9 @@ int ab_spmm(int64_t h, int transA, const double* X_, int64_t k, double* Y_) {
     if (!c) return AB_EHANDLE;
     if (k < 0) return fail(AB_EINVAL, "k < 0");
     std::lock_guard<std::mutex> lk(big_lock());
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool timing = opt("timers", 0.0) != 0.0;
+    if (timing) { AB_CUDA(cudaEventCreate(&e0)); AB_CUDA(cudaEventCreate(&e1)); AB_CUDA(cudaEventRecord(e0, stream())); }
     Csr* a = c;
     if (transA) AB_TRY(csr_ensure_transpose(c, &a));
     if ((a->n * k > 0 && !X_) || (a->m * k > 0 && !Y_)) return fail(AB_EINVAL, "null operand");
@@ -191,6 +420,12 @@ int ab_spmm(int64_t h, int transA, const double* X_, int64_t k, double* Y_) {
     AB_TRY(launch_spmm(a, X.d, k, Y.d));
     AB_TRY(Y.commit());
     if (X.tmp.p) AB_CUDA(cudaStreamSynchronize(stream()));
+    if (timing) {
+        AB_CUDA(cudaEventRecord(e1, stream())); AB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        timer_add(AB_TIMER_SPMM, ms * 1e-3);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
     return AB_OK;
 }
 
@@ -233,7 +468,7 @@ int ab_bench_spmv(int64_t h, const double* x, double* y, int reps, int with_dot,
     if (!x || !y || !ms || reps < 1) return fail(AB_EINVAL, "bad argument");
     if (!is_device_ptr(x) || !is_device_ptr(y)) return fail(AB_EINVAL, "ab_bench_spmv needs device vectors");
     std::lock_guard<std::mutex> lk(big_lock());
-    AB_TRY(csr_ensure_work(c, 8));
+    AB_TRY(csr_ensure_work(c, 10));
     double* dots = (double*)c->scal + 2;   // SolveScal::dots
     cudaEvent_t e0, e1;
     AB_CUDA(cudaEventCreate(&e0)); AB_CUDA(cudaEventCreate(&e1));

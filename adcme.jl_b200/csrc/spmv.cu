@@ -15,6 +15,8 @@
 //    consecutive addresses (2 x 128-byte lines per request) instead of the 7-8 scattered lines an
 //    entry-per-lane mapping produces.  Summation inside a row is sequential in stored (column)
 //    order, like the reference loop.
+//    An optional tile list restricts a launch to a subset of tiles (distributed SpMV: interior
+//    tiles run while the halo is in flight, boundary tiles afterwards, dots accumulated in order).
 //
 //  * spmv_vector_kernel<L> — general fallback (long / irregular rows): L lanes per row straight
 //    from global memory, shuffle reduction.
@@ -30,8 +32,9 @@ template <int R, int U>
 __global__ void __launch_bounds__(R)
 spmv_tile_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                  const double* __restrict__ values, const double* __restrict__ x, double* __restrict__ y,
-                 int64_t m, unsigned ntiles, const double* __restrict__ dotvec, double* partials,
-                 uint32_t* ticket, double* dot_result, const int* __restrict__ done) {
+                 int64_t m, unsigned ntiles, const int32_t* __restrict__ tile_list, int accumulate,
+                 const double* __restrict__ dotvec, double* partials, uint32_t* ticket, double* dot_result,
+                 const int* __restrict__ done) {
     __shared__ alignas(16) double  s_val[TILE_NNZ];
     __shared__ alignas(16) int32_t s_col[TILE_NNZ];
     __shared__ int32_t s_rp[R + 1];
@@ -45,7 +48,8 @@ spmv_tile_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     }
     double dot = 0.0, dot2 = 0.0;
     unsigned phase = 0;
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (unsigned ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const unsigned tile = tile_list ? (unsigned)tile_list[ti] : ti;
         const int64_t r0 = (int64_t)tile * R;
         const int nr = (int)min((int64_t)R, m - r0);
         if (t < nr) s_rp[t] = rowptr[r0 + t];
@@ -94,8 +98,8 @@ spmv_tile_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
         mine[0] = abd::block_sum<R>(dot, s_red);
         mine[1] = abd::block_sum<R>(dot2, s_red);
         abd::grid_reduce<R, 2>(mine, partials, ticket, s_red, [=](const double(&tot)[2]) {
-            dot_result[0] = tot[0];
-            dot_result[1] = tot[1];
+            dot_result[0] = accumulate ? dot_result[0] + tot[0] : tot[0];
+            dot_result[1] = accumulate ? dot_result[1] + tot[1] : tot[1];
         });
     }
 }
@@ -148,37 +152,47 @@ static int pick_vector_lanes(const Csr* c) {
     return 32;
 }
 
+// rows per tile the tile kernel would use for this matrix (0: not eligible)
+int spmv_tile_rows(const Csr* c) {
+    for (int l = 0; l < 3; ++l)
+        if (c->max_tile_nnz[l] <= TILE_NNZ - 8) return 256 >> l;
+    return 0;
+}
+
 template <int R, int U>
 static int launch_tile(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
-                       double* partials, uint32_t* ticket, const int* done_flag, int ctas_per_sm) {
-    unsigned ntiles = (unsigned)((c->m + R - 1) / R);
-    unsigned cap    = (unsigned)(sm_count() * ctas_per_sm);
+                       double* partials, uint32_t* ticket, const int* done_flag, int ctas_per_sm,
+                       const int32_t* tile_list, int64_t nlist, int accumulate) {
+    unsigned ntiles = tile_list ? (unsigned)nlist : (unsigned)((c->m + R - 1) / R);
+    if (ntiles == 0) return AB_OK;
+    unsigned cap = (unsigned)(sm_count() * ctas_per_sm);
     if (cap > (unsigned)MAX_REDUCE_GRID) cap = MAX_REDUCE_GRID;
     unsigned grid = ntiles < cap ? ntiles : cap;
-    spmv_tile_kernel<R, U><<<grid, R, 0, stream()>>>(c->rowptr, c->colind, c->values, x, y, c->m, ntiles, dotvec,
-                                                     partials, ticket, dot_result, done_flag);
+    spmv_tile_kernel<R, U><<<grid, R, 0, stream()>>>(c->rowptr, c->colind, c->values, x, y, c->m, ntiles, tile_list,
+                                                     accumulate, dotvec, partials, ticket, dot_result, done_flag);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
 
-int launch_spmv(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
-                double* partials, uint32_t* ticket, const int* done_flag) {
+// tile_list != nullptr: only those tiles (requires spmv_tile_rows(c) != 0); accumulate: add the
+// fused dots onto dot_result instead of overwriting.
+int launch_spmv_part(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
+                     double* partials, uint32_t* ticket, const int* done_flag, const int32_t* tile_list,
+                     int64_t nlist, int accumulate) {
     if (c->m == 0) return AB_OK;
     // spmv_variant: -1 auto, 0 vector kernel, 1 tile kernel U=8, 2 tile kernel U=4
     int variant = (int)opt("spmv_variant", -1);
-    int lvl = -1;   // 0: R=256, 1: R=128, 2: R=64
-    for (int l = 0; l < 3; ++l)
-        if (c->max_tile_nnz[l] <= TILE_NNZ - 8) { lvl = l; break; }
-    if (variant < 0) variant = lvl >= 0 ? 1 : 0;
-    if (variant >= 1 && lvl < 0) variant = 0;
+    const int R = spmv_tile_rows(c);
+    if (tile_list && R == 0) return fail(AB_EUNSUPPORTED, "tile lists need a tile-kernel matrix");
+    if (variant < 0 || tile_list) variant = R ? (variant == 2 ? 2 : 1) : 0;
+    if (variant >= 1 && R == 0) variant = 0;
     if (variant >= 1) {
         const int cps = (int)opt("spmv_ctas_per_sm", 8);
-        if (lvl == 0) {
-            if (variant == 2) return launch_tile<256, 4>(c, x, y, dotvec, dot_result, partials, ticket, done_flag, cps);
-            return launch_tile<256, 8>(c, x, y, dotvec, dot_result, partials, ticket, done_flag, cps);
-        }
-        if (lvl == 1) return launch_tile<128, 8>(c, x, y, dotvec, dot_result, partials, ticket, done_flag, cps);
-        return launch_tile<64, 8>(c, x, y, dotvec, dot_result, partials, ticket, done_flag, cps);
+#define AB_T(RR, UU) launch_tile<RR, UU>(c, x, y, dotvec, dot_result, partials, ticket, done_flag, cps, tile_list, nlist, accumulate)
+        if (R == 256) return variant == 2 ? AB_T(256, 4) : AB_T(256, 8);
+        if (R == 128) return AB_T(128, 8);
+        return AB_T(64, 8);
+#undef AB_T
     }
     const int L = pick_vector_lanes(c);
     const int64_t rpb = 256 / L;
@@ -199,6 +213,11 @@ int launch_spmv(const Csr* c, const double* x, double* y, const double* dotvec, 
 #undef AB_VEC
     AB_LAUNCH_CHECK();
     return AB_OK;
+}
+
+int launch_spmv(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
+                double* partials, uint32_t* ticket, const int* done_flag) {
+    return launch_spmv_part(c, x, y, dotvec, dot_result, partials, ticket, done_flag, nullptr, 0, 0);
 }
 
 }  // namespace ab

@@ -32,7 +32,7 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 ITERS_PER_STEP = 200      # "time >= 200 CG iterations"
-REF_ITERS_PER_STEP = 2
+REF_ITERS_PER_STEP = 10
 METRIC = "cg_iters_per_s_poisson3d_512_fp64"
 UNIT = "CG iterations/s"
 

@@ -221,6 +221,50 @@ def test_spmm_parity(pkg, orc, m, n, T, k):
     assert rel_err(gx, orc.spmm_coo(idx2, vv, n, G, adjoint_a=True)) <= TOL_VAL
 
 
+@pytest.mark.parametrize("k", [32, 40, 128, 150])
+def test_spmm_power_law_long_rows(pkg, orc, k):
+    """C5-shaped: a few rows far longer than LONG_ROW (4096) are cut into chunks and recombined."""
+    rng = np.random.default_rng(233)
+    m = n = 3000
+    deg = np.minimum(np.floor(rng.uniform(1e-9, 1, m) ** (-1 / 1.1)), 20000).astype(np.int64)
+    deg[5], deg[6], deg[2999] = 20000, 4097, 9000
+    ii = np.repeat(np.arange(1, m + 1), deg)
+    jj = rng.integers(1, n + 1, ii.size)
+    vv = rng.standard_normal(ii.size)
+    A = pkg.SparseTensor(ii, jj, vv, m, n)
+    idx2 = np.stack([ii - 1, jj - 1], 1)
+    X = rng.uniform(-1, 1, (n, k))
+    assert rel_err(A @ X, orc.spmm_coo(idx2, vv, m, X)) <= TOL_VAL
+    G = rng.uniform(-1, 1, (m, k))
+    gv = np.empty(ii.size)
+    pkg.check(pkg.lib.ab_spmm_grad_values(A.handle(), G.ctypes.data, X.ctypes.data, k, gv.ctypes.data))
+    assert rel_err(gv, orc.spmm_grad_values(idx2, G, X)) <= TOL_VAL
+    gx = np.empty_like(X)
+    pkg.check(pkg.lib.ab_spmm_grad_dense(A.handle(), G.ctypes.data, k, gx.ctypes.data))
+    assert rel_err(gx, orc.spmm_coo(idx2, vv, n, G, adjoint_a=True)) <= TOL_VAL
+
+
+def test_refinement_reaches_true_residual(pkg):
+    """Ill-conditioned SPD system (2-D variable-coefficient operator, 700^2): the recurrence residual
+    alone stalls above 1e-10; the refinement step must deliver the TRUE residual (north_star bar)."""
+    import torch
+
+    n = 700
+    xs = torch.arange(0, n + 2, dtype=torch.float64, device="cuda") / (n + 1)
+    X, Y = torch.meshgrid(xs, xs, indexing="ij")
+    kext = (1 + 50 * X ** 2 + Y ** 2).contiguous()
+    h = C.c_int64(0)
+    pkg.check(pkg.lib.ab_poisson2d_csr(n, kext.data_ptr(), -1, C.byref(h)))
+    A = pkg.SparseTensor.from_handle(h.value)
+    f = torch.rand(n * n, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(233))
+    u = torch.empty_like(f)
+    it, rr = C.c_int(0), C.c_double(0)
+    for method in (b"CG", b"BiCGSTAB"):
+        pkg.check(pkg.lib.ab_solve(A.handle(), method, f.data_ptr(), u.data_ptr(), 1e-10, 100000, C.byref(it), C.byref(rr)))
+        res = float((A @ u - f).norm() / f.norm())
+        assert res <= TOL_SOLVE and abs(rr.value - res) <= 1e-3 * res + 1e-14, (method, res, rr.value)
+
+
 def test_spmv_all_kernel_variants(pkg, orc):
     """tile kernel (U=8, U=4, R=256/128/64) and the vector kernel give the same SpMV."""
     rng = np.random.default_rng(233)
