@@ -679,6 +679,7 @@ int ab_dist_csr_create(int64_t h_local, int64_t ilower, int64_t iupper, int64_t 
         }
         // ---- 7. peer mappings
         if (want_p2p) AB_TRY(setup_p2p(d, d->dst_off));
+        ab_set_option("dist_p2p_active", d->p2p ? 1.0 : 0.0);   // readable with ab_get_option
         AB_CUDA(cudaStreamSynchronize(stream()));
         return AB_OK;
     };

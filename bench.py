@@ -217,6 +217,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         dist.init_process_group("nccl", device_id=dev)
     pkg = ge.load_package()
     lib = pkg.lib
+    for kv in filter(None, os.environ.get("ADCME_B200_OPTS", "").split(",")):   # e.g. dist_p2p=0
+        key, val = kv.split("=")
+        pkg.check(lib.ab_set_option(key.encode(), float(val)))
     n = args.grid
     N, nnz = n ** 3, poisson_nnz(n)
     pkg.mpi_init(rank, world, local_rank)
@@ -312,6 +315,13 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             spmv_info = {"ms": t.value, "GBps": b_spmv / (t.value * 1e-3) / 1e9, "frac_of_peak": b_spmv / (t.value * 1e-3) / 1e9 / peak}
             del x, y
     iter_bytes = cg_iter_bytes(N, nnz)
+    if world == 1:
+        exchange = "none (single GPU)"
+    else:
+        act = C.c_double(0)
+        lib.ab_get_option(b"dist_p2p_active", C.byref(act))
+        exchange = ("peer-memory kernels over NVLink (CUDA IPC): halo push + 2-value all-reduce, no NCCL in the iteration"
+                    if act.value else "NCCL send/recv halos + ncclAllReduce")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -324,6 +334,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
                          "frac_of_hbm_peak": iter_bytes * value / 1e9 / (peak * world), "peak_GBps_per_gpu": peak,
                          "peak_source": peak_src},
         "relres_after_step": relres_dev, "true_relres_after_step": err,
+        "exchange": exchange,
     }
     if roof:
         line["roofline"] = roof
