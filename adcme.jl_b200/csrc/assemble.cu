@@ -133,6 +133,7 @@ constexpr int RS_WARPS   = RS_THREADS / 32;
 constexpr int RS_ITEMS   = 16;
 constexpr int RS_TILE    = RS_THREADS * RS_ITEMS;   // 4096 keys per CTA
 constexpr int RS_RADIX   = 256;
+constexpr int RS_SMEM_BYTES = RS_TILE * 12 + (RS_WARPS + 2) * RS_RADIX * 4 + RS_WARPS * 4 + 16;
 
 __global__ void __launch_bounds__(RS_THREADS)
 radix_hist_kernel(const uint64_t* __restrict__ keys, size_t n, int shift, uint32_t* __restrict__ counts,
@@ -141,39 +142,47 @@ radix_hist_kernel(const uint64_t* __restrict__ keys, size_t n, int shift, uint32
     hist[threadIdx.x] = 0;
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * RS_TILE;
-#pragma unroll 4
+    uint64_t k[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {          // all loads in flight before the first atomic
+        size_t idx = base + (size_t)i * RS_THREADS + threadIdx.x;
+        k[i] = idx < n ? keys[idx] : 0ull;
+    }
+#pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         size_t idx = base + (size_t)i * RS_THREADS + threadIdx.x;
-        bool valid = idx < n;
-        unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (valid) {
-            unsigned d     = (unsigned)(keys[idx] >> shift) & (RS_RADIX - 1);
-            unsigned peers = __match_any_sync(act, d);
-            if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&hist[d], __popc(peers));
-        }
+        if (idx < n) atomicAdd(&hist[(unsigned)(k[i] >> shift) & (RS_RADIX - 1)], 1u);
     }
     __syncthreads();
     counts[(size_t)threadIdx.x * ntiles + blockIdx.x] = hist[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 3)
 radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
                      int shift, const uint32_t* __restrict__ offsets, unsigned ntiles) {
-    __shared__ uint32_t whist[RS_WARPS][RS_RADIX];
+    // dynamic shared memory (RS_SMEM_BYTES = 58 KB > the 48 KB static limit)
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint64_t* skey = reinterpret_cast<uint64_t*>(rs_smem);                       // [RS_TILE]
+    uint32_t* sval = reinterpret_cast<uint32_t*>(skey + RS_TILE);                // [RS_TILE]
+    uint32_t (*whist)[RS_RADIX] = reinterpret_cast<uint32_t (*)[RS_RADIX]>(sval + RS_TILE);   // [RS_WARPS][RS_RADIX]
+    uint32_t* dbase = &whist[0][0] + RS_WARPS * RS_RADIX;                        // [RS_RADIX]
+    uint32_t* gbase = dbase + RS_RADIX;                                          // [RS_RADIX]
+    uint32_t* wtot  = gbase + RS_RADIX;                                          // [RS_WARPS]
     for (int i = threadIdx.x; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&whist[0][0])[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const size_t wbase = (size_t)blockIdx.x * RS_TILE + (size_t)w * (32 * RS_ITEMS);
     uint64_t key[RS_ITEMS];
-    uint32_t rank[RS_ITEMS];
+    uint32_t rank[RS_ITEMS], val[RS_ITEMS];
     // items of a warp are visited in global index order -> ranks are stable
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         size_t idx = wbase + (size_t)i * 32 + lane;
         bool valid = idx < n;
         key[i]     = valid ? keys_in[idx] : ~0ull;
+        val[i]     = (valid && vals_in) ? vals_in[idx] : (uint32_t)idx;
     }
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
@@ -194,25 +203,56 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
         __syncwarp();
     }
     __syncthreads();
-    {   // digit d = threadIdx.x: turn per-warp counts into global bases
+    {   // digit d = threadIdx.x: per-warp counts -> bases inside the digit; digit totals -> tile-local
+        // exclusive offsets (block scan); gbase[d] + (position in the locally sorted tile) = global slot
         const unsigned d = threadIdx.x;
-        uint32_t run = offsets[(size_t)d * ntiles + blockIdx.x];
+        uint32_t run = 0;
 #pragma unroll
         for (int ww = 0; ww < RS_WARPS; ++ww) {
             uint32_t t   = whist[ww][d];
             whist[ww][d] = run;
             run += t;
         }
+        uint32_t inc = run;                       // inclusive scan of the 256 digit totals
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wtot[w] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ++ww) woff += (ww < w) ? wtot[ww] : 0u;
+        const uint32_t excl = woff + inc - run;
+        dbase[d] = excl;
+        gbase[d] = offsets[(size_t)d * ntiles + blockIdx.x] - excl;
     }
     __syncthreads();
+    // local sort: every key goes to its slot of the digit-ordered tile in shared memory
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         size_t idx = wbase + (size_t)i * 32 + lane;
         if (idx < n) {
-            unsigned d   = (unsigned)(key[i] >> shift) & (RS_RADIX - 1);
-            uint32_t pos = whist[w][d] + rank[i];
-            keys_out[pos] = key[i];
-            vals_out[pos] = vals_in ? vals_in[idx] : (uint32_t)idx;
+            unsigned d    = (unsigned)(key[i] >> shift) & (RS_RADIX - 1);
+            uint32_t tpos = dbase[d] + whist[w][d] + rank[i];
+            skey[tpos] = key[i];
+            sval[tpos] = val[i];
+        }
+    }
+    __syncthreads();
+    // coalesced write-out: consecutive threads hold consecutive slots of the same digit run
+    const size_t tbase = (size_t)blockIdx.x * RS_TILE;
+    const uint32_t nvalid = (uint32_t)min((size_t)RS_TILE, n - tbase);
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const uint32_t li = (uint32_t)i * RS_THREADS + threadIdx.x;
+        if (li < nvalid) {
+            const uint64_t kk = skey[li];
+            const unsigned d  = (unsigned)(kk >> shift) & (RS_RADIX - 1);
+            const uint32_t pos = gbase[d] + li;
+            keys_out[pos] = kk;
+            vals_out[pos] = sval[li];
         }
     }
 }
@@ -230,12 +270,17 @@ int radix_sort_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t*
     AB_TRY(counts.alloc((size_t)RS_RADIX * ntiles));
     int npass = (nbits + 7) / 8;
     if (npass < 1) npass = 1;
+    static bool smem_attr_set = false;
+    if (!smem_attr_set) {
+        AB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RS_SMEM_BYTES));
+        smem_attr_set = true;
+    }
     for (int p = 0; p < npass; ++p) {
         int shift = 8 * p;
         radix_hist_kernel<<<ntiles, RS_THREADS, 0, stream()>>>(kin, n, shift, counts.p, ntiles);
         AB_LAUNCH_CHECK();
         AB_TRY(scan_exclusive_u32(counts.p, counts.p, (size_t)RS_RADIX * ntiles, nullptr));
-        radix_scatter_kernel<<<ntiles, RS_THREADS, 0, stream()>>>(kin, vin, kout, vout, n, shift, counts.p, ntiles);
+        radix_scatter_kernel<<<ntiles, RS_THREADS, RS_SMEM_BYTES, stream()>>>(kin, vin, kout, vout, n, shift, counts.p, ntiles);
         AB_LAUNCH_CHECK();
         // rotate buffers
         uint64_t* tk = kin; kin = kout; kout = tk;
@@ -279,23 +324,34 @@ __global__ void head_flags_kernel(const uint64_t* __restrict__ keys, size_t T, u
 
 // excl[k] = number of heads before k.  Head k owns stored entry e = excl[k].
 __global__ void emit_entries_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ excl,
-                                    const uint32_t* __restrict__ perm, size_t T, int colbits,
+                                    size_t T, int64_t m, int colbits,
                                     int32_t* __restrict__ colind, uint32_t* __restrict__ segstart,
-                                    int32_t* __restrict__ slot, uint32_t* __restrict__ rowcnt,
-                                    int32_t* __restrict__ entry_row) {
+                                    int32_t* __restrict__ rowptr, int32_t* __restrict__ entry_row) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= T) return;
-    uint64_t key = keys[k];
-    bool head    = (k == 0) || (key != keys[k - 1]);
-    uint32_t e   = head ? excl[k] : excl[k] - 1;
-    slot[perm[k]] = (int32_t)e;
+    const uint64_t key  = keys[k];
+    const uint64_t prev = k ? keys[k - 1] : 0ull;
+    const bool head     = (k == 0) || (key != prev);
+    const uint32_t e    = head ? excl[k] : excl[k] - 1;
+    const int64_t r     = (int64_t)(key >> colbits);
     if (head) {
-        uint32_t r  = (uint32_t)(key >> colbits);
-        colind[e]   = (int32_t)(key & ((1ull << colbits) - 1));
-        segstart[e] = (uint32_t)k;
+        colind[e]    = (int32_t)(key & ((1ull << colbits) - 1));
+        segstart[e]  = (uint32_t)k;
         entry_row[e] = (int32_t)r;
-        atomicAdd(&rowcnt[r], 1u);
+        // entries are sorted by row: this head opens every row after the previous element's row
+        const int64_t rp = k ? (int64_t)(prev >> colbits) : -1;
+        for (int64_t rr = rp + 1; rr <= r; ++rr) rowptr[rr] = (int32_t)e;
     }
+    if (k == T - 1)
+        for (int64_t rr = r + 1; rr <= m; ++rr) rowptr[rr] = (int32_t)(e + 1);   // rows after the last entry
+}
+
+// slot[t] = stored entry of input triplet t (lazy: only gradient delivery and ab_csr_export_map need it)
+__global__ void slot_kernel(const uint32_t* __restrict__ segstart, const uint32_t* __restrict__ perm, size_t nnz,
+                            int32_t* __restrict__ slot) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    for (uint32_t k = segstart[e]; k < segstart[e + 1]; ++k) slot[perm[k]] = (int32_t)e;
 }
 
 // one thread per stored entry: left-to-right (= input order) sum of its duplicates
@@ -406,23 +462,20 @@ static int csr_from_coo_impl(int64_t T, const IdxT* ii_, const IdxT* jj_, const 
         AB_TRY(dev_alloc((void**)&c->colind, ((size_t)nnz + 8) * sizeof(int32_t)));
         AB_TRY(dev_alloc((void**)&c->values, ((size_t)nnz + 8) * sizeof(double)));
         AB_TRY(dev_alloc((void**)&c->segstart, ((size_t)nnz + 1) * sizeof(uint32_t)));
-        AB_TRY(dev_alloc((void**)&c->slot, (size_t)(T > 0 ? T : 1) * sizeof(int32_t)));
         AB_TRY(dev_alloc((void**)&c->entry_row, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t)));
         AB_CUDA(cudaMemsetAsync(c->colind + nnz, 0, 8 * sizeof(int32_t), stream()));
         AB_CUDA(cudaMemsetAsync(c->values + nnz, 0, 8 * sizeof(double), stream()));
-        AB_TRY(rowcnt.alloc(m + 1));
-        AB_CUDA(cudaMemsetAsync(rowcnt.p, 0, (size_t)(m + 1) * sizeof(uint32_t), stream()));
         if (T > 0) {
             unsigned nb = (unsigned)((T + 255) / 256);
-            emit_entries_kernel<<<nb, 256, 0, stream()>>>(ks, flags.p, ps, (size_t)T, colbits, c->colind,
-                                                         c->segstart, c->slot, rowcnt.p, c->entry_row);
+            emit_entries_kernel<<<nb, 256, 0, stream()>>>(ks, flags.p, (size_t)T, m, colbits, c->colind, c->segstart,
+                                                         c->rowptr, c->entry_row);
             AB_LAUNCH_CHECK();
             uint32_t Tu = (uint32_t)T;
             AB_CUDA(cudaMemcpyAsync(c->segstart + nnz, &Tu, sizeof(uint32_t), cudaMemcpyHostToDevice, stream()));
         } else {
             AB_CUDA(cudaMemsetAsync(c->segstart, 0, sizeof(uint32_t), stream()));
+            AB_CUDA(cudaMemsetAsync(c->rowptr, 0, (size_t)(m + 1) * sizeof(int32_t), stream()));
         }
-        AB_TRY(scan_exclusive_u32(rowcnt.p, (uint32_t*)c->rowptr, (size_t)(m + 1), nullptr));
         // keep the permutation (needed by ab_csr_update_values)
         AB_TRY(dev_alloc((void**)&c->perm, (size_t)(T > 0 ? T : 1) * sizeof(uint32_t)));
         if (T > 0) {
@@ -457,6 +510,18 @@ __global__ void entry_row_kernel(const int32_t* __restrict__ rowptr, int64_t m, 
         if ((size_t)rowptr[mid] <= e) lo = mid; else hi = mid;
     }
     er[e] = (int32_t)lo;
+}
+
+// triplet -> stored-entry map, built on first use from the cached permutation (handles created
+// from CSR have no permutation: the map is the identity and slot stays null)
+int csr_ensure_slot(Csr* c) {
+    if (c->slot || !c->perm || c->T == 0) return AB_OK;
+    AB_TRY(dev_alloc((void**)&c->slot, (size_t)c->T * sizeof(int32_t)));
+    if (c->nnz) {
+        slot_kernel<<<(unsigned)((c->nnz + 255) / 256), 256, 0, stream()>>>(c->segstart, c->perm, (size_t)c->nnz, c->slot);
+        AB_LAUNCH_CHECK();
+    }
+    return AB_OK;
 }
 
 int csr_ensure_entry_row(Csr* c) {
@@ -761,6 +826,7 @@ int ab_csr_export_map(int64_t h, int32_t* slot) {
     if (!slot) return fail(AB_EINVAL, "slot is null");
     std::lock_guard<std::mutex> lk(big_lock());
     if (c->T == 0) return AB_OK;
+    AB_TRY(csr_ensure_slot(c));
     if (c->slot) {
         AB_CUDA(cudaMemcpyAsync(slot, c->slot, (size_t)c->T * sizeof(int32_t), cudaMemcpyDefault, stream()));
     } else {

@@ -164,6 +164,7 @@ int     csr_erase(int64_t h);
 int     csr_finalize(Csr* c);     // computes tiling facts after rowptr/colind/values are in place
 int     csr_ensure_dinv(Csr* c);
 int     csr_ensure_entry_row(Csr* c);
+int     csr_ensure_slot(Csr* c);  // lazy triplet -> stored-entry map (null afterwards = identity)
 int     csr_ensure_transpose(Csr* c, Csr** out);
 int     csr_ensure_work(Csr* c, size_t nvec);
 std::mutex& big_lock();

@@ -565,6 +565,7 @@ int ab_solve_grad(int64_t h, const char* method, const double* grad_u_, const do
     AB_TRY(solve_dev(ct, meth, g.d, x, tol, maxit, iters, relres));
     if (grad_vv_ && c->T > 0) {
         AB_TRY(csr_ensure_entry_row(c));
+        AB_TRY(csr_ensure_slot(c));
         Out<double> gv;
         AB_TRY(gv.bind(grad_vv_, c->T));
         grad_vv_kernel<<<(unsigned)((c->T + 255) / 256), 256, 0, stream()>>>(c->slot, c->entry_row, c->colind, x, u.d, (size_t)c->T, gv.d);

@@ -444,6 +444,7 @@ int ab_spmm_grad_values(int64_t h, const double* dY_, const double* X_, int64_t 
     In<double> dY, X; Out<double> dvv;
     AB_TRY(dY.bind(dY_, (size_t)(c->m * k))); AB_TRY(X.bind(X_, (size_t)(c->n * k)));
     AB_TRY(dvv.bind(dvv_, (size_t)c->T));
+    AB_TRY(csr_ensure_slot(c));
     if (c->slot) {
         DevBuf<double> dv;
         AB_TRY(dv.alloc((size_t)c->nnz));
