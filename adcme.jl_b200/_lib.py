@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libadcme_b200.so")
+LIB_PATH = os.environ.get("ADCME_B200_LIB", os.path.join(HERE, "libadcme_b200.so"))   # override: A/B builds
 
 AB_OK, AB_EINVAL, AB_EHANDLE, AB_ECUDA, AB_ERANGE = 0, -1, -2, -3, -4
 AB_ENOCONV, AB_EBREAKDOWN, AB_EUNSUPPORTED, AB_ENCCL = -5, -6, -7, -8

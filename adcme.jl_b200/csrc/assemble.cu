@@ -459,12 +459,12 @@ static int csr_from_coo_impl(int64_t T, const IdxT* ii_, const IdxT* jj_, const 
         }
         c->nnz = nnz;
         AB_TRY(dev_alloc((void**)&c->rowptr, (size_t)(m + 1) * sizeof(int32_t)));
-        AB_TRY(dev_alloc((void**)&c->colind, ((size_t)nnz + 8) * sizeof(int32_t)));
-        AB_TRY(dev_alloc((void**)&c->values, ((size_t)nnz + 8) * sizeof(double)));
+        AB_TRY(dev_alloc((void**)&c->colind, ((size_t)nnz + CSR_PAD) * sizeof(int32_t)));
+        AB_TRY(dev_alloc((void**)&c->values, ((size_t)nnz + CSR_PAD) * sizeof(double)));
         AB_TRY(dev_alloc((void**)&c->segstart, ((size_t)nnz + 1) * sizeof(uint32_t)));
         AB_TRY(dev_alloc((void**)&c->entry_row, (size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t)));
-        AB_CUDA(cudaMemsetAsync(c->colind + nnz, 0, 8 * sizeof(int32_t), stream()));
-        AB_CUDA(cudaMemsetAsync(c->values + nnz, 0, 8 * sizeof(double), stream()));
+        AB_CUDA(cudaMemsetAsync(c->colind + nnz, 0, CSR_PAD * sizeof(int32_t), stream()));
+        AB_CUDA(cudaMemsetAsync(c->values + nnz, 0, CSR_PAD * sizeof(double), stream()));
         if (T > 0) {
             unsigned nb = (unsigned)((T + 255) / 256);
             emit_entries_kernel<<<nb, 256, 0, stream()>>>(ks, flags.p, (size_t)T, m, colbits, c->colind, c->segstart,
@@ -563,10 +563,10 @@ static int build_transpose(Csr* c, Csr** out, uint32_t** tperm_out) {
     size_t nnz = (size_t)c->nnz;
     auto body = [&]() -> int {
         AB_TRY(dev_alloc((void**)&t->rowptr, (size_t)(t->m + 1) * sizeof(int32_t)));
-        AB_TRY(dev_alloc((void**)&t->colind, (nnz + 8) * sizeof(int32_t)));
-        AB_TRY(dev_alloc((void**)&t->values, (nnz + 8) * sizeof(double)));
-        AB_CUDA(cudaMemsetAsync(t->colind + nnz, 0, 8 * sizeof(int32_t), stream()));
-        AB_CUDA(cudaMemsetAsync(t->values + nnz, 0, 8 * sizeof(double), stream()));
+        AB_TRY(dev_alloc((void**)&t->colind, (nnz + CSR_PAD) * sizeof(int32_t)));
+        AB_TRY(dev_alloc((void**)&t->values, (nnz + CSR_PAD) * sizeof(double)));
+        AB_CUDA(cudaMemsetAsync(t->colind + nnz, 0, CSR_PAD * sizeof(int32_t), stream()));
+        AB_CUDA(cudaMemsetAsync(t->values + nnz, 0, CSR_PAD * sizeof(double), stream()));
         DevBuf<uint64_t> k0, k1; DevBuf<uint32_t> p0, p1, colcnt;
         AB_TRY(k0.alloc(nnz)); AB_TRY(k1.alloc(nnz)); AB_TRY(p0.alloc(nnz)); AB_TRY(p1.alloc(nnz));
         AB_TRY(colcnt.alloc(t->m + 1));
@@ -784,15 +784,15 @@ int ab_csr_create(int64_t m, int64_t n, int64_t nnz, const int32_t* rowptr_, con
     c->m = m; c->n = n; c->nnz = nnz; c->T = nnz;
     auto body = [&]() -> int {
         AB_TRY(dev_alloc((void**)&c->rowptr, (size_t)(m + 1) * sizeof(int32_t)));
-        AB_TRY(dev_alloc((void**)&c->colind, ((size_t)nnz + 8) * sizeof(int32_t)));
-        AB_TRY(dev_alloc((void**)&c->values, ((size_t)nnz + 8) * sizeof(double)));
+        AB_TRY(dev_alloc((void**)&c->colind, ((size_t)nnz + CSR_PAD) * sizeof(int32_t)));
+        AB_TRY(dev_alloc((void**)&c->values, ((size_t)nnz + CSR_PAD) * sizeof(double)));
         AB_CUDA(cudaMemcpyAsync(c->rowptr, rowptr_, (size_t)(m + 1) * sizeof(int32_t), cudaMemcpyDefault, stream()));
         if (nnz) {
             AB_CUDA(cudaMemcpyAsync(c->colind, colind_, (size_t)nnz * sizeof(int32_t), cudaMemcpyDefault, stream()));
             AB_CUDA(cudaMemcpyAsync(c->values, values_, (size_t)nnz * sizeof(double), cudaMemcpyDefault, stream()));
         }
-        AB_CUDA(cudaMemsetAsync(c->colind + nnz, 0, 8 * sizeof(int32_t), stream()));
-        AB_CUDA(cudaMemsetAsync(c->values + nnz, 0, 8 * sizeof(double), stream()));
+        AB_CUDA(cudaMemsetAsync(c->colind + nnz, 0, CSR_PAD * sizeof(int32_t), stream()));
+        AB_CUDA(cudaMemsetAsync(c->values + nnz, 0, CSR_PAD * sizeof(double), stream()));
         AB_TRY(csr_finalize(c));
         return AB_OK;
     };
@@ -857,12 +857,14 @@ int ab_csr_update_values(int64_t h, const double* vv_) {
         }
     }
     c->dinv_valid = false;
+    ++c->values_version;
     if (c->th) {   // refresh cached transpose values
         Csr* t = csr_get(c->th);
         if (t && c->nnz) {
             gather_values_kernel<<<(unsigned)((c->nnz + 255) / 256), 256, 0, stream()>>>(c->tperm, c->values, (size_t)c->nnz, t->values);
             AB_LAUNCH_CHECK();
             t->dinv_valid = false;
+            ++t->values_version;
         }
     }
     if (vv.tmp.p) AB_CUDA(cudaStreamSynchronize(stream()));

@@ -143,10 +143,158 @@ cg_direction_kernel(const double* __restrict__ r, const double* __restrict__ din
     }
 }
 
+// Residual replacement (van der Vorst & Ye): every `replace_every` iterations of a LONG solve the
+// recurrence residual is overwritten by the true one, r = b - A x, so it cannot drift away from
+// it on ill-conditioned systems (kappa ~ 1e7 at 4096^2: drift 1e-10 -> 1.6e-8 without this).
+// Ax holds A x (scaled system when sb != nullptr: r~ = S b - A~ x~).  Overrides rz', rr of K2.
+static __global__ void __launch_bounds__(EW_THREADS)
+cg_replace_kernel(const double* __restrict__ b, const double* __restrict__ sb, const double* __restrict__ Ax,
+                  const double* __restrict__ dz, double* __restrict__ r, size_t n, int parity, SolveScal* s,
+                  double* partials, uint32_t* ticket) {
+    __shared__ double sh[32];
+    if (s->done) return;
+    double a0 = 0.0, a1 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        const double ri = (sb ? b[i] * sb[i] : b[i]) - Ax[i];
+        r[i] = ri;
+        a0 = fma(dz ? ri * dz[i] : ri, ri, a0);
+        a1 = fma(ri, ri, a1);
+    }
+    double mine[2];
+    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
+    mine[1] = abd::block_sum<EW_THREADS>(a1, sh);
+    abd::grid_reduce<EW_THREADS, 2>(mine, partials, ticket, sh, [=](const double(&t)[2]) {
+        s->rz[parity ^ 1] = t[0];
+        s->rr = t[1];
+        if (!isfinite(t[0]) || !isfinite(t[1])) { s->breakdown = 1; s->done = 1; }
+        else if (s->thr >= 0.0 && t[1] <= s->thr) s->done = 1;
+    });
+}
+
 // distributed mode: scalar logic after the all-reduce of SolveScal::red.  which: 0 init, 1 update
 static __global__ void cg_fin_kernel(SolveScal* s, int which, int parity, double tol) {
     if (which == 0) cg_init_fin(s, tol, s->red[0], s->red[1]);
     else if (!s->done) cg_update_fin(s, parity, s->red[0], s->red[1], s->bad != 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Symmetrically scaled form of Jacobi-PCG.  With S = D^-1/2, PCG on (A, M = D) is CG on
+// A~ = S A S, x~ = S^-1 x, b~ = S b (same iterates up to rounding).  The preconditioner
+// disappears from the vector kernels: K2 streams 6 vectors instead of 7, K3 3 instead of 4, and
+// one inner product (<r~,r~>) serves both the recurrence and the stopping test:
+//     12*nnz + 4*(N+1) + 11*8*N bytes per iteration instead of ... + 13*8*N.
+// The stopping test is on ||r~||/||b~|| (= ||r||/||b|| for a constant diagonal); the caller's
+// guarantee on the TRUE residual comes from the refinement step in solve_dev.
+// ---------------------------------------------------------------------------------------------
+// r = S b ; p = r ; x = 0 ; rz = bb = <r,r>
+static __global__ void __launch_bounds__(EW_THREADS)
+cgs_init_kernel(const double* __restrict__ b, const double* __restrict__ sinv, double* __restrict__ x,
+                double* __restrict__ r, double* __restrict__ p, size_t n, double tol, SolveScal* s,
+                double* partials, uint32_t* ticket, int raw) {
+    __shared__ double sh[32];
+    double a0 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        const double ri = b[i] * sinv[i];
+        x[i] = 0.0;
+        r[i] = ri;
+        p[i] = ri;
+        a0 = fma(ri, ri, a0);
+    }
+    double mine[2];
+    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
+    mine[1] = mine[0];
+    abd::grid_reduce<EW_THREADS, 2>(mine, partials, ticket, sh, [=](const double(&t)[2]) {
+        if (raw) { s->red[0] = t[0]; s->red[1] = t[1]; s->done = 0; }
+        else cg_init_fin(s, tol, t[0], t[1]);
+    });
+}
+
+// K2: alpha = rz/pAp ; x += alpha p ; r -= alpha Ap ; rz' = rr = <r,r>
+static __global__ void __launch_bounds__(EW_THREADS)
+cgs_update_kernel(const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x,
+                  double* __restrict__ r, size_t n, int parity, SolveScal* s, double* partials, uint32_t* ticket,
+                  int raw) {
+    __shared__ double sh[32];
+    if (s->done) return;
+    const double rz = s->rz[parity], pAp = s->dots[0];
+    const bool bad = !(pAp > 0.0) || !isfinite(pAp) || !isfinite(rz);
+    const double alpha = bad ? 0.0 : rz / pAp;
+    double a0 = 0.0;
+    const size_t n2 = n >> 1;
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+    const double2* Ap2 = reinterpret_cast<const double2*>(Ap);
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+        double2 pv = p2[i], av = Ap2[i], xv = x2[i], rv = r2[i];
+        xv.x = fma(alpha, pv.x, xv.x);  xv.y = fma(alpha, pv.y, xv.y);
+        rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+        x2[i] = xv;
+        r2[i] = rv;
+        a0 = fma(rv.x, rv.x, a0); a0 = fma(rv.y, rv.y, a0);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        size_t i = n - 1;
+        double xv = fma(alpha, p[i], x[i]), rv = fma(-alpha, Ap[i], r[i]);
+        x[i] = xv; r[i] = rv;
+        a0 = fma(rv, rv, a0);
+    }
+    double mine[2];
+    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
+    mine[1] = mine[0];
+    abd::grid_reduce<EW_THREADS, 2>(mine, partials, ticket, sh, [=](const double(&t)[2]) {
+        s->alpha = alpha;
+        if (raw) { s->red[0] = t[0]; s->red[1] = t[1]; s->bad = bad ? 1 : 0; }
+        else cg_update_fin(s, parity, t[0], t[1], bad);
+    });
+}
+
+// K3: beta = rz'/rz ; p = r + beta p
+static __global__ void __launch_bounds__(EW_THREADS)
+cgs_direction_kernel(const double* __restrict__ r, double* __restrict__ p, size_t n, int parity,
+                     const SolveScal* __restrict__ s) {
+    if (s->done) return;
+    const double beta = s->rz[parity ^ 1] / s->rz[parity];
+    const size_t n2 = n >> 1;
+    const double2* r2 = reinterpret_cast<const double2*>(r);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+        double2 rv = r2[i], pv = p2[i];
+        pv.x = fma(beta, pv.x, rv.x);
+        pv.y = fma(beta, pv.y, rv.y);
+        p2[i] = pv;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        size_t i = n - 1;
+        p[i] = fma(beta, p[i], r[i]);
+    }
+}
+
+// x = S x~
+static __global__ void scale_vec_kernel(double* __restrict__ x, const double* __restrict__ sinv, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] *= sinv[i];
+}
+
+// sinv[r] = 1/sqrt(diag); *bad set when a diagonal entry is missing or not positive (not SPD)
+static __global__ void scale_diag_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                         const double* __restrict__ values, int64_t m, double* __restrict__ sinv,
+                                         int* __restrict__ bad) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    double d = 0.0;
+    for (int j = rowptr[r]; j < rowptr[r + 1]; ++j)
+        if (colind[j] == r) d += values[j];
+    if (!(d > 0.0) || !isfinite(d)) { atomicExch(bad, 1); sinv[r] = 1.0; }
+    else sinv[r] = 1.0 / sqrt(d);
+}
+// sv[e] = v[e] * sinv[row] * sinv_ext[col]   (sinv_ext covers halo columns in the distributed case)
+static __global__ void scale_values_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                           const double* __restrict__ values, int64_t m,
+                                           const double* __restrict__ sinv_ext, double* __restrict__ sv) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    const double sr = sinv_ext[r];
+    for (int j = rowptr[r]; j < rowptr[r + 1]; ++j) sv[j] = values[j] * sr * sinv_ext[colind[j]];
 }
 
 // shared host helpers implemented in solver.cu

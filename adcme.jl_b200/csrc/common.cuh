@@ -121,12 +121,18 @@ struct Out {
 };
 
 // ---------------------------------------------------------------- CSR handle
+constexpr int CSR_PAD = 32;   // entries of padding after colind/values: aligned bulk copies over-read
 struct Csr {
     int64_t m = 0, n = 0, nnz = 0, T = 0;
-    // CSR proper. colind/values are padded by 8 entries so 16-byte bulk copies may over-read.
+    // CSR proper. colind/values are padded by CSR_PAD entries so aligned bulk copies may over-read.
     int32_t* rowptr = nullptr;   // [m+1]
-    int32_t* colind = nullptr;   // [nnz+8]
-    double*  values = nullptr;   // [nnz+8]
+    int32_t* colind = nullptr;   // [nnz+CSR_PAD]
+    double*  values = nullptr;   // [nnz+CSR_PAD]
+    // offset-dictionary form of colind for the SpMV tile kernel (lazy, spmv.cu): off8[e] indexes
+    // offtab[256] = sorted distinct (col - row); noff: -1 not attempted, 0 unavailable, else count
+    uint8_t* off8   = nullptr;   // [nnz+64]
+    int32_t* offtab = nullptr;   // [256]
+    int      noff   = -1;
     // triplet bookkeeping (null when the handle was created from CSR: identity map)
     uint32_t* perm     = nullptr; // [T]  sorted position -> input triplet
     uint32_t* segstart = nullptr; // [nnz+1] first sorted position of each stored entry
@@ -138,6 +144,12 @@ struct Csr {
     // Jacobi: 1/diag (1 where the diagonal is absent or zero), lazy
     double* dinv = nullptr;
     bool    dinv_valid = false;
+    // symmetrically scaled copy for CG (lazy): svalues = S A S, sinv = diag(A)^-1/2
+    double*  svalues = nullptr;    // [nnz+8]
+    double*  sinv    = nullptr;    // [m (+ halo)]
+    uint64_t values_version = 1;   // bumped whenever `values` change
+    uint64_t scaled_version = 0;   // version svalues/sinv were built from (0 = never)
+    bool     scaled_ok = false;    // false: a diagonal entry is missing / non-positive -> classic path
     // cached transpose (lazy): handle id of A', and map tperm (A' entry -> A entry)
     int64_t   th    = 0;
     uint32_t* tperm = nullptr;
@@ -189,6 +201,12 @@ int launch_spmv_part(const Csr* c, const double* x, double* y, const double* dot
                      double* partials, uint32_t* ticket, const int* done_flag, const int32_t* tile_list,
                      int64_t nlist, int accumulate);
 int spmv_tile_rows(const Csr* c);
+// same with an explicit value array (c->values or the scaled copy c->svalues)
+int launch_spmv_vals(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
+                     double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
+                     const int32_t* tile_list, int64_t nlist, int accumulate);
+// builds / refreshes c->svalues and c->sinv; c->scaled_ok tells whether the scaled CG may be used
+int csr_ensure_scaled(Csr* c);
 int launch_spmm(const Csr* c, const double* X, int64_t k, double* Y);
 
 }  // namespace ab

@@ -329,18 +329,18 @@ static int allreduce2(DistCsr* d, double* p) {
 }
 
 // y = A_local [x_owned ; halo], halo exchange overlapped with the interior tiles when possible
-static int dist_spmv_dev(DistCsr* d, double* y, const double* dotvec, double* dots, const int* done) {
+static int dist_spmv_dev(DistCsr* d, const double* vals, double* y, const double* dotvec, double* dots, const int* done) {
     Csr* c = d->loc;
     AB_TRY(halo_begin(d));
     const bool split = g_world > 1 && d->p2p && d->tiles_int && d->n_bnd > 0;
     if (!split) {
         AB_TRY(halo_end(d));
-        return launch_spmv(c, d->xext, y, dotvec, dots, c->partials, c->ticket, done);
+        return launch_spmv_vals(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, nullptr, 0, 0);
     }
     if (d->n_int > 0)
-        AB_TRY(launch_spmv_part(c, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_int, d->n_int, 0));
+        AB_TRY(launch_spmv_vals(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_int, d->n_int, 0));
     AB_TRY(halo_end(d));
-    return launch_spmv_part(c, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_bnd, d->n_bnd,
+    return launch_spmv_vals(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_bnd, d->n_bnd,
                             d->n_int > 0 ? 1 : 0);
 }
 
@@ -353,17 +353,66 @@ static int check_p2p_err(DistCsr* d) {
     return AB_OK;
 }
 
+// S = diag(A)^-1/2 over owned AND halo columns, scaled values S A S for the local block.
+// Every rank must take the same branch afterwards: the "bad diagonal" flags are summed over the box.
+static int dist_ensure_scaled(DistCsr* d) {
+    Csr* c = d->loc;
+    if (c->scaled_version == c->values_version) return AB_OK;
+    const size_t nnz = (size_t)c->nnz, nloc = (size_t)d->nloc;
+    AB_TRY(csr_ensure_work(c, 4));
+    if (!c->sinv) AB_TRY(dev_alloc((void**)&c->sinv, (size_t)(c->n + 2) * sizeof(double)));
+    if (!c->svalues) {
+        AB_TRY(dev_alloc((void**)&c->svalues, (nnz + CSR_PAD) * sizeof(double)));
+        AB_CUDA(cudaMemsetAsync(c->svalues + nnz, 0, CSR_PAD * sizeof(double), stream()));
+    }
+    DevBuf<int> bad;
+    AB_TRY(bad.alloc(1));
+    AB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream()));
+    unsigned nb = (unsigned)((nloc + 255) / 256);
+    if (nloc) {
+        scale_diag_kernel<<<nb, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, (int64_t)nloc, c->sinv, bad.p);
+        AB_LAUNCH_CHECK();
+        AB_CUDA(cudaMemcpyAsync(d->xext, c->sinv, nloc * sizeof(double), cudaMemcpyDeviceToDevice, stream()));
+    }
+    AB_TRY(halo_begin(d));
+    AB_TRY(halo_end(d));
+    if (d->next) AB_CUDA(cudaMemcpyAsync(c->sinv + nloc, d->xext + nloc, (size_t)d->next * sizeof(double), cudaMemcpyDeviceToDevice, stream()));
+    int hb = 0;
+    AB_CUDA(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    SolveScal* s = (SolveScal*)c->scal;
+    double hv[2] = {(double)hb, 0.0};
+    AB_CUDA(cudaMemcpyAsync(s->red, hv, sizeof(hv), cudaMemcpyHostToDevice, stream()));
+    AB_TRY(allreduce2(d, s->red));    // also the rendezvous that makes the halo tail reusable
+    AB_CUDA(cudaMemcpyAsync(hv, s->red, sizeof(hv), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    c->scaled_ok = (hv[0] == 0.0);
+    if (c->scaled_ok && nloc) {
+        scale_values_kernel<<<nb, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, (int64_t)nloc, c->sinv, c->svalues);
+        AB_LAUNCH_CHECK();
+    }
+    c->scaled_version = c->values_version;
+    return AB_OK;
+}
+
 // CG over the row-block partition.  b, x: local device vectors of length nloc.  tol < 0: fixed count.
 static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int maxit, SolveScal* fin) {
     Csr* c = d->loc;
     const size_t n = (size_t)d->nloc;
-    AB_TRY(csr_ensure_dinv(c));
     AB_TRY(csr_ensure_work(c, 4));
+    bool scaled = false;
+    if (opt("cg_scaled", 1.0) != 0.0) {
+        AB_TRY(dist_ensure_scaled(d));
+        scaled = c->scaled_ok;
+    }
+    if (!scaled) AB_TRY(csr_ensure_dinv(c));
+    const double* vals = scaled ? c->svalues : c->values;
     double *r = work_vec(c, 0), *Ap = work_vec(c, 1), *p = d->xext;
     SolveScal* s = (SolveScal*)c->scal;
     const unsigned g = ew_grid(n);
     const int raw = g_world > 1 ? 1 : 0;
-    cg_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->dinv, x, r, p, n, tol, s, c->partials, c->ticket, raw);
+    if (scaled) cgs_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->sinv, x, r, p, n, tol, s, c->partials, c->ticket, raw);
+    else cg_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->dinv, x, r, p, n, tol, s, c->partials, c->ticket, raw);
     AB_LAUNCH_CHECK();
     if (raw) {
         AB_TRY(allreduce2(d, s->red));
@@ -378,21 +427,27 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
         int chunk = maxit - it < check ? maxit - it : check;
         for (int k = 0; k < chunk; ++k, ++it) {
             const int parity = it & 1;
-            AB_TRY(dist_spmv_dev(d, Ap, p, s->dots, &s->done));
+            AB_TRY(dist_spmv_dev(d, vals, Ap, p, s->dots, &s->done));
             if (raw) AB_TRY(allreduce2(d, s->dots));
-            cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, raw);
+            if (scaled) cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, raw);
+            else cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, raw);
             AB_LAUNCH_CHECK();
             if (raw) {
                 AB_TRY(allreduce2(d, s->red));
                 cg_fin_kernel<<<1, 1, 0, stream()>>>(s, 1, parity, tol);
                 AB_LAUNCH_CHECK();
             }
-            cg_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, c->dinv, p, n, parity, s);
+            if (scaled) cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, n, parity, s);
+            else cg_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, c->dinv, p, n, parity, s);
             AB_LAUNCH_CHECK();
         }
         if (tol < 0 && it < maxit) continue;
         AB_TRY(read_scal(c, &h));
         if (h.done) break;   // identical on every rank: the flags derive from all-reduced values
+    }
+    if (scaled) {
+        scale_vec_kernel<<<g, 256, 0, stream()>>>(x, c->sinv, n);   // x = S x~
+        AB_LAUNCH_CHECK();
     }
     AB_TRY(read_scal(c, fin));
     AB_TRY(check_p2p_err(d));
@@ -572,11 +627,11 @@ int ab_dist_csr_create(int64_t h_local, int64_t ilower, int64_t iupper, int64_t 
         d->loc = c;
         c->m = nloc; c->n = nloc + next; c->nnz = src->nnz; c->T = src->nnz;
         AB_TRY(dev_alloc((void**)&c->rowptr, (size_t)(nloc + 1) * sizeof(int32_t)));
-        AB_TRY(dev_alloc((void**)&c->colind, (nnz + 8) * sizeof(int32_t)));
-        AB_TRY(dev_alloc((void**)&c->values, (nnz + 8) * sizeof(double)));
+        AB_TRY(dev_alloc((void**)&c->colind, (nnz + CSR_PAD) * sizeof(int32_t)));
+        AB_TRY(dev_alloc((void**)&c->values, (nnz + CSR_PAD) * sizeof(double)));
         AB_CUDA(cudaMemcpyAsync(c->rowptr, src->rowptr, (size_t)(nloc + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream()));
-        AB_CUDA(cudaMemcpyAsync(c->values, src->values, (nnz + 8) * sizeof(double), cudaMemcpyDeviceToDevice, stream()));
-        AB_CUDA(cudaMemsetAsync(c->colind + nnz, 0, 8 * sizeof(int32_t), stream()));
+        AB_CUDA(cudaMemcpyAsync(c->values, src->values, (nnz + CSR_PAD) * sizeof(double), cudaMemcpyDeviceToDevice, stream()));
+        AB_CUDA(cudaMemsetAsync(c->colind + nnz, 0, CSR_PAD * sizeof(int32_t), stream()));
         if (nnz) {
             remap_cols_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, stream()>>>(src->colind, nnz, ilower, iupper, nloc, ext.p, next, c->colind);
             AB_LAUNCH_CHECK();
@@ -718,7 +773,7 @@ int ab_dist_spmv(int64_t dh, const double* x_, double* y_) {
     AB_TRY(y.bind(y_, (size_t)d->nloc));
     AB_TRY(csr_ensure_work(d->loc, 4));
     if (d->nloc) AB_CUDA(cudaMemcpyAsync(d->xext, x_, (size_t)d->nloc * sizeof(double), cudaMemcpyDefault, stream()));
-    AB_TRY(dist_spmv_dev(d, y.d, nullptr, nullptr, nullptr));
+    AB_TRY(dist_spmv_dev(d, d->loc->values, y.d, nullptr, nullptr, nullptr));
     if (g_world > 1 && d->p2p) {
         // box-wide rendezvous: nobody may overwrite a halo tail that a slower rank is still reading
         SolveScal* s = (SolveScal*)d->loc->scal;

@@ -3,7 +3,7 @@
 // Replaces tf.sparse.sparse_dense_matmul with k == 1 as called from
 // /root/reference/src/sparse.jl:227-241 (semantics: Y[i] += v * X[j] over stored entries).
 //
-// Two kernels, chosen per matrix from facts gathered at assembly time:
+// Kernels, chosen per matrix from facts gathered at assembly time:
 //
 //  * spmv_tile_kernel<R,U> — for matrices whose R-row tiles hold <= TILE_NNZ entries (stencil /
 //    FEM matrices; R = 256, 128 or 64 rows).  A CTA walks tiles grid-stride.  For each tile one
@@ -18,16 +18,48 @@
 //    An optional tile list restricts a launch to a subset of tiles (distributed SpMV: interior
 //    tiles run while the halo is in flight, boundary tiles afterwards, dots accumulated in order).
 //
+//  * spmv_tile8_kernel<R,U> — the same kernel on the OFFSET-DICTIONARY form of the column indices:
+//    when a matrix has at most 256 distinct (col - row) offsets (every structured-grid stencil /
+//    banded FEM matrix, including the re-indexed row blocks of the distributed path) the 4-byte
+//    colind[] stream is replaced by a 1-byte index into a 256-entry offset table held in shared
+//    memory: 9 instead of 12 bytes per stored entry move from HBM (SpMV traffic at 512^3:
+//    14.1 -> 11.6 GB measured).  Built lazily from the pattern at the first SpMV.
+//
 //  * spmv_vector_kernel<L> — general fallback (long / irregular rows): L lanes per row straight
 //    from global memory, shuffle reduction.
 //
+// Measured dead ends (B200, 512^3, kept out of the code): (1) a 2-stage TMA pipeline per CTA
+// (tile k+1 in flight while tile k is multiplied; 5 CTAs/SM) — 2.07 ms vs 2.01 ms for this
+// single-stage kernel at 8 CTAs/SM: occupancy already overlaps the three DRAM latencies of a
+// tile; (2) a hand-scheduled inner loop (inline-PTX shared loads, unconditional padded slots,
+// one IMAD.WIDE per gather: 11 instead of ~20 SASS instructions per entry) — 2.35 ms at 5, 6
+// and 8 CTAs/SM: the extra padded gather per 7-entry row costs more L1 wavefronts than the
+// instruction savings return.  ncu: the kernel is latency/LSU co-bound at 68 % of DRAM peak.
+//
 // Algorithmic bytes per launch: 12*nnz + 4*(m+1) + 8*n + 8*m.
 #include "common.cuh"
+#include <algorithm>
+#include <vector>
 
 namespace ab {
 
-constexpr int TILE_NNZ = 2048;   // staged entries per tile (incl. 16-byte alignment slack)
+constexpr int TILE_NNZ = 2048;   // staged entries per tile (incl. alignment slack)
+constexpr int TILE_PAD = 32;     // tile8 stage slack: its copies start 16-entry aligned (up to +30 entries)
 
+#define AB_TILE_EPILOGUE(R)                                                                       \
+    if (dotvec) {                                                                                 \
+        double mine[2];                                                                           \
+        mine[0] = abd::block_sum<R>(dot, s_red);                                                  \
+        mine[1] = abd::block_sum<R>(dot2, s_red);                                                 \
+        abd::grid_reduce<R, 2>(mine, partials, ticket, s_red, [=](const double(&tot)[2]) {        \
+            dot_result[0] = accumulate ? dot_result[0] + tot[0] : tot[0];                         \
+            dot_result[1] = accumulate ? dot_result[1] + tot[1] : tot[1];                         \
+        });                                                                                       \
+    }
+
+// NOTE: no minBlocksPerSM in the launch bounds.  Measured (512^3): adding (R, 8) together with a
+// slightly larger stage made the same code 15 % slower (2.53 vs 2.21 ms) although registers (32)
+// and CTAs/SM (8) were unchanged — the shared-memory carve-out the driver then picks starves L1.
 template <int R, int U>
 __global__ void __launch_bounds__(R)
 spmv_tile_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
@@ -93,15 +125,170 @@ spmv_tile_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
         }
         __syncthreads();   // smem is rewritten by the next tile
     }
-    if (dotvec) {
-        double mine[2];
-        mine[0] = abd::block_sum<R>(dot, s_red);
-        mine[1] = abd::block_sum<R>(dot2, s_red);
-        abd::grid_reduce<R, 2>(mine, partials, ticket, s_red, [=](const double(&tot)[2]) {
-            dot_result[0] = accumulate ? dot_result[0] + tot[0] : tot[0];
-            dot_result[1] = accumulate ? dot_result[1] + tot[1] : tot[1];
-        });
+    AB_TILE_EPILOGUE(R)
+}
+
+// NOTE: no minBlocksPerSM in the launch bounds.  Measured (512^3): adding (R, 8) together with a
+// slightly larger stage made the same code 15 % slower (2.53 vs 2.21 ms) although registers (32)
+// and CTAs/SM (8) were unchanged — the shared-memory carve-out the driver then picks starves L1.
+template <int R, int U>
+__global__ void __launch_bounds__(R)
+spmv_tile8_kernel(const int32_t* __restrict__ rowptr, const uint8_t* __restrict__ off8,
+                  const int32_t* __restrict__ offtab, const double* __restrict__ values,
+                  const double* __restrict__ x, double* __restrict__ y, int64_t m, unsigned ntiles,
+                  const int32_t* __restrict__ tile_list, int accumulate, const double* __restrict__ dotvec,
+                  double* partials, uint32_t* ticket, double* dot_result, const int* __restrict__ done) {
+    __shared__ alignas(16) double  s_val[TILE_NNZ + TILE_PAD];
+    __shared__ alignas(16) uint8_t s_off[TILE_NNZ + TILE_PAD];
+    __shared__ int32_t s_tab[256];
+    __shared__ int32_t s_rp[R + 1];
+    __shared__ alignas(8) uint64_t bar;
+    __shared__ double s_red[32];
+    if (done && *done) return;
+    const int t = threadIdx.x;
+    for (int i = t; i < 256; i += R) s_tab[i] = offtab[i];
+    if (t == 0) {
+        abd::mbar_init(&bar, 1);
+        abd::mbar_fence_init();
     }
+    double dot = 0.0, dot2 = 0.0;
+    unsigned phase = 0;
+    for (unsigned ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const unsigned tile = tile_list ? (unsigned)tile_list[ti] : ti;
+        const int64_t r0 = (int64_t)tile * R;
+        const int nr = (int)min((int64_t)R, m - r0);
+        if (t < nr) s_rp[t] = rowptr[r0 + t];
+        if (t == 0) s_rp[nr] = rowptr[r0 + nr];
+        __syncthreads();
+        const int a16 = s_rp[0] & ~15;
+        if (t == 0) {
+            const unsigned cnt = (unsigned)((s_rp[nr] - a16 + 15) & ~15);
+            abd::mbar_expect_tx(&bar, cnt * 9u);
+            if (cnt) {
+                abd::bulk_g2s(s_off, off8 + a16, cnt, &bar);
+                abd::bulk_g2s(s_val, values + a16, cnt * 8u, &bar);
+            }
+        }
+        abd::mbar_wait(&bar, phase);
+        phase ^= 1u;
+        if (t < nr) {
+            double acc = 0.0;
+            const int row = (int)(r0 + t);
+            const int j0 = s_rp[t] - a16, j1 = s_rp[t + 1] - a16;
+            for (int jb = j0; jb < j1; jb += U) {
+                double av[U], xv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = jb + u;
+                    if (j < j1) {
+                        av[u] = s_val[j];
+                        xv[u] = __ldg(x + (row + s_tab[s_off[j]]));
+                    } else {
+                        av[u] = 0.0;
+                        xv[u] = 0.0;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc = fma(av[u], xv[u], acc);
+            }
+            y[r0 + t] = acc;
+            if (dotvec) {
+                dot  = fma(acc, dotvec[r0 + t], dot);
+                dot2 = fma(acc, acc, dot2);
+            }
+        }
+        __syncthreads();
+    }
+    AB_TILE_EPILOGUE(R)
+}
+
+// ---- offset dictionary construction (pattern only; built lazily at the first SpMV) -------------
+constexpr int OFFSET_HASH  = 1024;
+constexpr int OFFSET_EMPTY = INT32_MIN;
+
+__device__ __forceinline__ bool hash_insert(int32_t* table, int32_t off) {   // true when newly inserted
+    unsigned h = ((unsigned)off * 2654435761u) >> 22;                         // 10 bits
+    for (int probe = 0; probe < OFFSET_HASH; ++probe) {
+        const int32_t cur = table[h];
+        if (cur == off) return false;
+        if (cur == OFFSET_EMPTY) {
+            const int32_t old = atomicCAS(&table[h], OFFSET_EMPTY, off);
+            if (old == OFFSET_EMPTY) return true;
+            if (old == off) return false;
+        }
+        h = (h + 1) & (OFFSET_HASH - 1);
+    }
+    return false;   // table full: the distinct count has long exceeded 256
+}
+
+__global__ void __launch_bounds__(256)
+offset_collect_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, int64_t m,
+                      int32_t* __restrict__ gtable, int* __restrict__ gcount) {
+    __shared__ int32_t stab[OFFSET_HASH];
+    __shared__ int scount;
+    for (int i = threadIdx.x; i < OFFSET_HASH; i += 256) stab[i] = OFFSET_EMPTY;
+    if (threadIdx.x == 0) scount = 0;
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < m; r += (int64_t)gridDim.x * 256) {
+        if (*(volatile int*)&scount > 256 || *(volatile int*)gcount > 256) break;   // already hopeless
+        for (int j = rowptr[r]; j < rowptr[r + 1]; ++j)
+            if (hash_insert(stab, colind[j] - (int32_t)r)) atomicAdd(&scount, 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < OFFSET_HASH; i += 256)
+        if (stab[i] != OFFSET_EMPTY && hash_insert(gtable, stab[i])) atomicAdd(gcount, 1);
+}
+
+__global__ void __launch_bounds__(256)
+offset_encode_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind, int64_t m,
+                     const int32_t* __restrict__ offtab, int noff, uint8_t* __restrict__ off8) {
+    __shared__ int32_t stab[256];
+    stab[threadIdx.x] = offtab[threadIdx.x];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < m; r += (int64_t)gridDim.x * 256) {
+        for (int j = rowptr[r]; j < rowptr[r + 1]; ++j) {
+            const int32_t off = colind[j] - (int32_t)r;
+            int lo = 0, hi = noff - 1;                 // offtab is sorted ascending
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (stab[mid] < off) lo = mid + 1; else hi = mid; }
+            off8[j] = (uint8_t)lo;
+        }
+    }
+}
+
+// noff > 0: dictionary available; 0: more than 256 distinct offsets (or not a tile-kernel matrix)
+static int csr_ensure_off8(Csr* c) {
+    if (c->noff >= 0) return AB_OK;
+    c->noff = 0;
+    if (c->m == 0 || c->nnz == 0 || spmv_tile_rows(c) == 0) return AB_OK;
+    DevBuf<int32_t> gtab; DevBuf<int> gcount;
+    AB_TRY(gtab.alloc(OFFSET_HASH)); AB_TRY(gcount.alloc(1));
+    std::vector<int32_t> h(OFFSET_HASH, OFFSET_EMPTY);
+    AB_CUDA(cudaMemcpyAsync(gtab.p, h.data(), OFFSET_HASH * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemsetAsync(gcount.p, 0, sizeof(int), stream()));
+    int64_t nblk = (c->m + 255) / 256, cap = (int64_t)sm_count() * 8;
+    unsigned grid = (unsigned)(nblk < cap ? nblk : cap);
+    offset_collect_kernel<<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->m, gtab.p, gcount.p);
+    AB_LAUNCH_CHECK();
+    int cnt = 0;
+    AB_CUDA(cudaMemcpyAsync(&cnt, gcount.p, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaMemcpyAsync(h.data(), gtab.p, OFFSET_HASH * sizeof(int32_t), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    if (cnt > 256 || cnt == 0) return AB_OK;
+    std::vector<int32_t> tab;
+    for (int32_t v : h) if (v != OFFSET_EMPTY) tab.push_back(v);
+    if ((int)tab.size() != cnt || tab.size() > 256) return AB_OK;
+    std::sort(tab.begin(), tab.end());
+    const int noff = (int)tab.size();
+    tab.resize(256, tab.back());
+    AB_TRY(dev_alloc((void**)&c->offtab, 256 * sizeof(int32_t)));
+    AB_TRY(dev_alloc((void**)&c->off8, (size_t)c->nnz + 64));
+    AB_CUDA(cudaMemcpyAsync(c->offtab, tab.data(), 256 * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemsetAsync(c->off8 + c->nnz, 0, 64, stream()));
+    offset_encode_kernel<<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->m, c->offtab, noff, c->off8);
+    AB_LAUNCH_CHECK();
+    AB_CUDA(cudaStreamSynchronize(stream()));   // tab (host) must outlive the copy
+    c->noff = noff;
+    return AB_OK;
 }
 
 template <int L>
@@ -160,7 +347,7 @@ int spmv_tile_rows(const Csr* c) {
 }
 
 template <int R, int U>
-static int launch_tile(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
+static int launch_tile(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec, double* dot_result,
                        double* partials, uint32_t* ticket, const int* done_flag, int ctas_per_sm,
                        const int32_t* tile_list, int64_t nlist, int accumulate) {
     unsigned ntiles = tile_list ? (unsigned)nlist : (unsigned)((c->m + R - 1) / R);
@@ -168,17 +355,22 @@ static int launch_tile(const Csr* c, const double* x, double* y, const double* d
     unsigned cap = (unsigned)(sm_count() * ctas_per_sm);
     if (cap > (unsigned)MAX_REDUCE_GRID) cap = MAX_REDUCE_GRID;
     unsigned grid = ntiles < cap ? ntiles : cap;
-    spmv_tile_kernel<R, U><<<grid, R, 0, stream()>>>(c->rowptr, c->colind, c->values, x, y, c->m, ntiles, tile_list,
-                                                     accumulate, dotvec, partials, ticket, dot_result, done_flag);
+    if (c->noff > 0 && opt("spmv_off8", 1.0) != 0.0)
+        spmv_tile8_kernel<R, U><<<grid, R, 0, stream()>>>(c->rowptr, c->off8, c->offtab, vals, x, y, c->m, ntiles, tile_list,
+                                                          accumulate, dotvec, partials, ticket, dot_result, done_flag);
+    else
+        spmv_tile_kernel<R, U><<<grid, R, 0, stream()>>>(c->rowptr, c->colind, vals, x, y, c->m, ntiles, tile_list,
+                                                         accumulate, dotvec, partials, ticket, dot_result, done_flag);
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
 
 // tile_list != nullptr: only those tiles (requires spmv_tile_rows(c) != 0); accumulate: add the
 // fused dots onto dot_result instead of overwriting.
-int launch_spmv_part(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
-                     double* partials, uint32_t* ticket, const int* done_flag, const int32_t* tile_list,
-                     int64_t nlist, int accumulate) {
+// vals: the value array to multiply with (c->values, or the symmetrically scaled copy used by CG)
+int launch_spmv_vals(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
+                     double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
+                     const int32_t* tile_list, int64_t nlist, int accumulate) {
     if (c->m == 0) return AB_OK;
     // spmv_variant: -1 auto, 0 vector kernel, 1 tile kernel U=8, 2 tile kernel U=4
     int variant = (int)opt("spmv_variant", -1);
@@ -188,7 +380,8 @@ int launch_spmv_part(const Csr* c, const double* x, double* y, const double* dot
     if (variant >= 1 && R == 0) variant = 0;
     if (variant >= 1) {
         const int cps = (int)opt("spmv_ctas_per_sm", 8);
-#define AB_T(RR, UU) launch_tile<RR, UU>(c, x, y, dotvec, dot_result, partials, ticket, done_flag, cps, tile_list, nlist, accumulate)
+        if (c->noff < 0) AB_TRY(csr_ensure_off8(const_cast<Csr*>(c)));   // pattern-only, built once
+#define AB_T(RR, UU) launch_tile<RR, UU>(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, cps * (256 / RR), tile_list, nlist, accumulate)
         if (R == 256) return variant == 2 ? AB_T(256, 4) : AB_T(256, 8);
         if (R == 128) return AB_T(128, 8);
         return AB_T(64, 8);
@@ -201,7 +394,7 @@ int launch_spmv_part(const Csr* c, const double* x, double* y, const double* dot
     if (cap > MAX_REDUCE_GRID) cap = MAX_REDUCE_GRID;
     unsigned grid = (unsigned)(nblk < cap ? nblk : cap);
 #define AB_VEC(LL)                                                                                           \
-    spmv_vector_kernel<LL><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, x, y, c->m, dotvec, \
+    spmv_vector_kernel<LL><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, vals, x, y, c->m, dotvec, \
                                                        partials, ticket, dot_result, done_flag)
     switch (L) {
         case 2: AB_VEC(2); break;
@@ -213,6 +406,12 @@ int launch_spmv_part(const Csr* c, const double* x, double* y, const double* dot
 #undef AB_VEC
     AB_LAUNCH_CHECK();
     return AB_OK;
+}
+
+int launch_spmv_part(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
+                     double* partials, uint32_t* ticket, const int* done_flag, const int32_t* tile_list,
+                     int64_t nlist, int accumulate) {
+    return launch_spmv_vals(c, c->values, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, accumulate);
 }
 
 int launch_spmv(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,

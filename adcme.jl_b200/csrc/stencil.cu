@@ -88,10 +88,10 @@ __global__ void p2d_grad_kernel(int64_t n, const double* __restrict__ xgrad, con
 }
 
 static int alloc_csr(Csr* c) {
-    AB_TRY(dev_alloc((void**)&c->colind, ((size_t)c->nnz + 8) * sizeof(int32_t)));
-    AB_TRY(dev_alloc((void**)&c->values, ((size_t)c->nnz + 8) * sizeof(double)));
-    AB_CUDA(cudaMemsetAsync(c->colind + c->nnz, 0, 8 * sizeof(int32_t), stream()));
-    AB_CUDA(cudaMemsetAsync(c->values + c->nnz, 0, 8 * sizeof(double), stream()));
+    AB_TRY(dev_alloc((void**)&c->colind, ((size_t)c->nnz + CSR_PAD) * sizeof(int32_t)));
+    AB_TRY(dev_alloc((void**)&c->values, ((size_t)c->nnz + CSR_PAD) * sizeof(double)));
+    AB_CUDA(cudaMemsetAsync(c->colind + c->nnz, 0, CSR_PAD * sizeof(int32_t), stream()));
+    AB_CUDA(cudaMemsetAsync(c->values + c->nnz, 0, CSR_PAD * sizeof(double), stream()));
     return AB_OK;
 }
 
@@ -182,6 +182,7 @@ int ab_poisson2d_update(int64_t h, int64_t n, const double* kext_, int sign) {
     p2d_fill_kernel<<<(unsigned)((c->m + 255) / 256), 256, 0, stream()>>>(n, kext.d, (double)sign, c->rowptr, c->colind, c->values, 0);
     AB_LAUNCH_CHECK();
     c->dinv_valid = false;
+    ++c->values_version;
     if (c->th) { csr_erase(c->th); c->th = 0; dev_free(c->tperm); c->tperm = nullptr; }
     if (kext.tmp.p) AB_CUDA(cudaStreamSynchronize(stream()));
     return AB_OK;
