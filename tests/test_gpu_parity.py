@@ -282,11 +282,14 @@ def test_spmv_all_kernel_variants(pkg, orc):
         x = rng.uniform(-1, 1, N)
         y0 = orc.spmm_coo(np.stack([ii - 1, jj - 1], 1), vv, N, x)
         for variant in (-1, 0, 1, 2):
-            pkg.check(pkg.lib.ab_set_option(b"spmv_variant", float(variant)))
-            try:
-                assert rel_err(A @ x, y0) <= TOL_VAL, (N, variant)
-            finally:
-                pkg.check(pkg.lib.ab_set_option(b"spmv_variant", -1.0))
+            for off8 in (1.0, 0.0):           # offset-dictionary form of colind on / off
+                pkg.check(pkg.lib.ab_set_option(b"spmv_variant", float(variant)))
+                pkg.check(pkg.lib.ab_set_option(b"spmv_off8", off8))
+                try:
+                    assert rel_err(A @ x, y0) <= TOL_VAL, (N, variant, off8)
+                finally:
+                    pkg.check(pkg.lib.ab_set_option(b"spmv_variant", -1.0))
+                    pkg.check(pkg.lib.ab_set_option(b"spmv_off8", 1.0))
 
 
 def test_spmv_torch_device_tensors_and_autograd(pkg, orc):
@@ -342,6 +345,35 @@ def test_solve_c1_poisson_all_methods(pkg, orc):
     # op-level call with the reference signature
     u = pkg.load_system_op("sparse_solver")(ii, jj, vv, f, "SparseLU")
     assert np.linalg.norm(orc.csr_spmm(rp, ci, va, u) - f) / np.linalg.norm(f) <= TOL_SOLVE
+
+
+def test_cg_scaled_form_matches_classic_pcg(pkg, orc):
+    """CG runs on the symmetrically scaled system S A S (11 vector passes); it must agree with the
+    classic Jacobi-PCG recurrence and with the direct oracle on a strongly varying diagonal."""
+    rng = np.random.default_rng(233)
+    n = 40
+    kext = np.exp(rng.uniform(-2, 2, (n + 2, n + 2)))        # diagonal spans ~e^4
+    h = C.c_int64(0)
+    pkg.check(pkg.lib.ab_poisson2d_csr(n, kext.ctypes.data, -1, C.byref(h)))
+    A = pkg.SparseTensor.from_handle(h.value)
+    S = A.to_scipy().tocoo()
+    f = rng.uniform(size=n * n)
+    u0 = orc.sparse_solver(S.row + 1, S.col + 1, S.data, f)
+    sols = []
+    for scaled in (1.0, 0.0):
+        pkg.check(pkg.lib.ab_set_option(b"cg_scaled", scaled))
+        try:
+            u = pkg.backslash(A, f, "CG")
+        finally:
+            pkg.check(pkg.lib.ab_set_option(b"cg_scaled", 1.0))
+        assert np.linalg.norm(S @ u - f) / np.linalg.norm(f) <= TOL_SOLVE, scaled
+        assert np.linalg.norm(u - u0) / np.linalg.norm(u0) <= 1e-8, scaled
+        sols.append(u)
+    assert np.linalg.norm(sols[0] - sols[1]) / np.linalg.norm(u0) <= 1e-8
+    # a non-positive diagonal entry cannot be scaled (sqrt): the classic recurrence takes over
+    ii = np.array([1, 2, 3]); vv = np.array([1.0, -2.0, 3.0])
+    u = pkg.backslash(pkg.SparseTensor(ii, ii, vv, 3, 3), np.ones(3), "CG")
+    assert np.allclose(u, [1.0, -0.5, 1.0 / 3.0], rtol=1e-12)
 
 
 def test_solve_random_nonsymmetric_like_reference_test(pkg, orc):
