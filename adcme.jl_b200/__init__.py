@@ -14,6 +14,9 @@ from .sparse import (                                           # noqa: F401
     SparseTensor, SparseAssembler, accumulate, assemble, backslash, compress, compress_grad,
     compress_indices, factorize, find, rows, cols, values, mul, rmul, solve,
 )
+from .structure import (                                        # noqa: F401
+    zero_out_row, scatter_update, scatter_add, getindex, add, matmul, spdiag, spzero,
+)
 from .extra import (                                            # noqa: F401
     load_op, load_op_and_grad, load_system_op, get_library_symbols, libadcme,
 )
@@ -22,5 +25,6 @@ from .mpi import mpi_init, mpi_finalize, mpi_rank, mpi_size, mpi_SparseTensor, r
 __all__ = [
     "ADCMEError", "SparseTensor", "SparseAssembler", "accumulate", "assemble", "backslash", "compress",
     "factorize", "find", "rows", "cols", "values", "solve", "load_op", "load_op_and_grad", "load_system_op",
-    "mpi_init", "mpi_finalize", "mpi_SparseTensor", "options",
+    "mpi_init", "mpi_finalize", "mpi_SparseTensor", "options", "zero_out_row", "scatter_update", "scatter_add",
+    "getindex", "spdiag", "spzero",
 ]

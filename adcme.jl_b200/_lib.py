@@ -60,6 +60,21 @@ SIGNATURES = {
     "ab_factorize": (C.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr]),
     "ab_factorized_solve": (C.c_int, [_i64, _ptr, _i64, _ptr]),
     "ab_factorized_solve_grad": (C.c_int, [_i64, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr]),
+    "ab_trip_size": (_i64, [_i64]),
+    "ab_trip_fetch": (C.c_int, [_i64, _ptr, _ptr, _ptr]),
+    "ab_trip_fetch_idx2": (C.c_int, [_i64, _ptr, _ptr]),
+    "ab_trip_destroy": (C.c_int, [_i64]),
+    "ab_csr_from_trip": (C.c_int, [_i64, _i64, _i64, C.c_int, _ptr]),
+    "ab_zero_out_row": (C.c_int, [_i64, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ab_zero_out_row_grad": (C.c_int, [_i64, _ptr, _ptr, _i64, _ptr, _i64, _ptr]),
+    "ab_scatter_update": (C.c_int, [_i64, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr]),
+    "ab_scatter_update_grad": (C.c_int, [_i64, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr]),
+    "ab_sparse_indexing": (C.c_int, [_i64, _ptr, _i64, _ptr, _i64, _ptr]),
+    "ab_sparse_indexing_grad": (C.c_int, [_i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ab_csr_export_coo": (C.c_int, [_i64, _ptr, _ptr, _ptr, C.c_int]),
+    "ab_coo_scale": (C.c_int, [_i64, _ptr, _ptr, _ptr, _i64, C.c_int, _ptr]),
+    "ab_csr_axpby": (C.c_int, [_i64, _dbl, _i64, _dbl, _ptr]),
+    "ab_spgemm": (C.c_int, [_i64, _i64, C.c_int, _ptr]),
     "ab_poisson3d_csr": (C.c_int, [_i64, _i64, _i64, _i64, _i64, _ptr]),
     "ab_poisson2d_csr": (C.c_int, [_i64, _ptr, C.c_int, _ptr]),
     "ab_poisson2d_update": (C.c_int, [_i64, _i64, _ptr, C.c_int]),

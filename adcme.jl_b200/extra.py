@@ -14,6 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import sparse as _sp
+from . import structure as _st
 from ._lib import LIB_PATH, as_array, check, empty_like_kind, lib, ptr
 
 libadcme = LIB_PATH
@@ -125,6 +126,12 @@ _OPS = {
     "sparse_factorization": (sparse_factorization, None),
     "solve": (solve, solve_grad),
     "mpi_create_matrix": (mpi_create_matrix, None),
+    "zero_out_row": (_st.zero_out_row_op, _st.zero_out_row_grad),
+    "sparse_scatter_update": (_st.sparse_scatter_update_op, _st.sparse_scatter_update_grad),
+    "sparse_indexing": (_st.sparse_indexing_op, _st.sparse_indexing_grad),
+    "sparse_sparse_mat_mul": (_st.sparse_sparse_mat_mul_op, None),
+    "diag_sparse_mat_mul": (_st.diag_sparse_mat_mul_op, None),
+    "sparse_diag_mat_mul": (_st.sparse_diag_mat_mul_op, None),
 }
 
 

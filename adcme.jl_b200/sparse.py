@@ -121,6 +121,16 @@ class SparseTensor:
         check(lib.ab_csr_export(self.handle(), ptr(rp), ptr(ci), ptr(va)))
         return rp, ci, va
 
+    def triplets(self):
+        """(ii, jj, vv), 1-based, in stored order.  A pattern-only tensor (built from a device handle)
+        materialises them once from its CSR (row-major, duplicates already summed)."""
+        if self.ii is None:
+            m, n, nnz, T = self.query()
+            ii, jj, vv = np.empty(nnz, np.int64), np.empty(nnz, np.int64), np.empty(nnz, np.float64)
+            check(lib.ab_csr_export_coo(self.handle(), ptr(ii), ptr(jj), ptr(vv), 1))
+            self.ii, self.jj, self.vv = ii, jj, vv
+        return self.ii, self.jj, self.vv
+
     def slot_map(self):
         m, n, nnz, T = self.query()
         s = np.empty(T, np.int32)
@@ -149,12 +159,48 @@ class SparseTensor:
     T = property(adjoint)
 
     def __matmul__(self, o):
+        if isinstance(o, SparseTensor):
+            from . import structure
+
+            return structure.matmul(self, o)
         return mul(self, o)
 
     def __mul__(self, o):
         if np.isscalar(o):
-            return SparseTensor(self.ii, self.jj, self.vv * float(o), self.m, self.n, is_diag=self._diag)
-        return mul(self, o)
+            ii, jj, vv = self.triplets()
+            return SparseTensor(ii, jj, vv * float(o), self.m, self.n, is_diag=self._diag)
+        return self.__matmul__(o)
+
+    def __truediv__(self, o):
+        return self * (1.0 / float(o))          # sparse.jl:225
+
+    def __add__(self, o):
+        from . import structure
+
+        if isinstance(o, SparseTensor) or hasattr(o, "tocoo"):
+            return structure.add(self, o)       # sparse.jl:217
+        if tuple(o.shape) != self.shape:        # sparse.jl:203-209: SparseTensor + dense -> dense
+            raise ValueError(f"size {self.shape} and {tuple(o.shape)} does not match")
+        return self.toarray() + (o.detach().cpu().numpy() if _is_torch(o) else np.asarray(o))
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        if isinstance(o, SparseTensor) or hasattr(o, "tocoo"):
+            from . import structure
+
+            return structure.add(self, o, 1.0, -1.0)   # s1 + (-s2), sparse.jl:218
+        return self + (-o)
+
+    def __rsub__(self, o):
+        return (-self) + o
+
+    def __getitem__(self, key):
+        from . import structure
+
+        if not isinstance(key, tuple) or len(key) != 2:
+            raise IndexError("SparseTensor indexing takes two indices: A[i1, i2]")
+        return structure.getindex(self, key[0], key[1])
 
     def __rmatmul__(self, o):
         return rmul(o, self)
@@ -175,7 +221,7 @@ class SparseTensor:
 def find(s: SparseTensor):
     """(ii, jj, vv), 1-based; row-major sorted when options.sparse.auto_reorder (tf.sparse.reorder
     is a stable lexicographic sort, duplicates kept: sparse.jl:62-76,93-99)."""
-    ii, jj, vv = s.ii, s.jj, s.vv
+    ii, jj, vv = s.triplets()
     if options.sparse.auto_reorder:
         i_np = np.asarray(ii.cpu() if _is_torch(ii) else ii)
         j_np = np.asarray(jj.cpu() if _is_torch(jj) else jj)

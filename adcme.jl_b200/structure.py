@@ -1,0 +1,457 @@
+"""Host-side mirror of the structural SparseTensor ops of /root/reference/src/sparse.jl that sit
+between assembly and solve and the remaining sparse algebra (N4), over the C-ABI
+of csrc/structure.cu.  Nothing here computes; every function is one or two library calls.
+
+    zero_out_row(A, bd)                  src/sparse.jl:790-797   -> ab_zero_out_row
+    scatter_update / scatter_add         src/sparse.jl:340-386   -> ab_scatter_update
+    getindex  A[i1, i2]                  src/sparse.jl:303-327   -> ab_sparse_indexing
+    A + B, A - B                         src/sparse.jl:203-218   -> triplet concatenation / ab_csr_axpby
+    A * B (SparseTensor x SparseTensor)  src/sparse.jl:579-595   -> ab_spgemm / ab_coo_scale
+    spdiag, spzero                       src/sparse.jl:540-575, 631-658
+
+Index conventions follow the reference: triplets and index lists are 1-based; `zero_out_row`'s
+op-level `indices` are the 0-based [N,2] matrix of a tf.SparseTensor.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import as_array, check, empty_like_kind, lib, ptr
+
+
+def _is_torch(x) -> bool:
+    return _lib._is_torch(x)
+
+
+def _n(x) -> int:
+    return int(x.numel()) if _is_torch(x) else int(np.asarray(x).size)
+
+
+def _fetch_trip(th: int, like, idx2: bool = False):
+    """Length query -> caller-side allocation (where `like` lives) -> fetch; the handle is consumed."""
+    k = lib.ab_trip_size(th)
+    if k < 0:
+        check(int(k))
+    vv = empty_like_kind(like, (k,), np.float64)
+    if idx2:
+        ind = empty_like_kind(like, (k, 2), np.int64)
+        check(lib.ab_trip_fetch_idx2(th, ptr(ind), ptr(vv)))
+        return ind, vv
+    ii = empty_like_kind(like, (k,), np.int64)
+    jj = empty_like_kind(like, (k,), np.int64)
+    check(lib.ab_trip_fetch(th, ptr(ii), ptr(jj), ptr(vv)))
+    return ii, jj, vv
+
+
+# ---------------------------------------------------------------------- op level (reference signatures)
+def zero_out_row_op(indices, vv, bd):
+    """ZeroOutRow(indices, vv, bd) -> (oindices, ovv)   (ZeroOutRow.cpp:14-19, ZeroOutRow.h:28-48)."""
+    ki, pi = as_array(indices, np.int64)
+    kv, pv = as_array(vv, np.float64)
+    kb, pb = as_array(bd, np.int64)
+    th = C.c_int64(0)
+    check(lib.ab_zero_out_row(_n(kv), pi, pv, pb, _n(kb), C.byref(th)))
+    return _fetch_trip(th.value, kv, idx2=True)
+
+
+def zero_out_row_grad(grad_ovv, oindices, ovv, indices, vv, bd):
+    """ZeroOutRowGrad -> (grad_indices, grad_vv, grad_bd); only grad_vv is defined (ZeroOutRow.h:50-57)."""
+    kg, pg = as_array(grad_ovv, np.float64)
+    ki, pi = as_array(indices, np.int64)
+    kb, pb = as_array(bd, np.int64)
+    N = _n(ki) // 2
+    out = empty_like_kind(kg, (N,), np.float64)
+    check(lib.ab_zero_out_row_grad(N, pi, pb, _n(kb), pg, _n(kg), ptr(out)))
+    return None, out, None
+
+
+def sparse_scatter_update_op(ii1, jj1, vv1, m1, n1, ii2, jj2, vv2, ii, jj):
+    """SparseScatterUpdate -> (nii, njj, nvv)   (SparseScatterUpdate.cpp:20-34, .h:20-37)."""
+    k1i, p1i = as_array(ii1, np.int64); k1j, p1j = as_array(jj1, np.int64); k1v, p1v = as_array(vv1, np.float64)
+    k2i, p2i = as_array(ii2, np.int64); k2j, p2j = as_array(jj2, np.int64); k2v, p2v = as_array(vv2, np.float64)
+    ki, pi = as_array(ii, np.int64); kj, pj = as_array(jj, np.int64)
+    th = C.c_int64(0)
+    check(lib.ab_scatter_update(_n(k1v), p1i, p1j, p1v, _n(k2v), p2i, p2j, p2v, int(m1), int(n1),
+                                pi, _n(ki), pj, _n(kj), C.byref(th)))
+    return _fetch_trip(th.value, k1v)
+
+
+def sparse_scatter_update_grad(grad_nvv, nii, njj, nvv, ii1, jj1, vv1, m1, n1, ii2, jj2, vv2, ii, jj):
+    """SparseScatterUpdateGrad -> 10 gradients, only grad_vv1 / grad_vv2 defined (.h:39-60)."""
+    kg, pg = as_array(grad_nvv, np.float64)
+    k1i, p1i = as_array(ii1, np.int64); k1j, p1j = as_array(jj1, np.int64)
+    ki, pi = as_array(ii, np.int64); kj, pj = as_array(jj, np.int64)
+    on, un = _n(k1i), _n(ii2)
+    g1 = empty_like_kind(kg, (on,), np.float64)
+    g2 = empty_like_kind(kg, (un,), np.float64)
+    check(lib.ab_scatter_update_grad(on, p1i, p1j, un, int(m1), int(n1), pi, _n(ki), pj, _n(kj), pg, _n(kg),
+                                     ptr(g1), ptr(g2)))
+    return None, None, g1, None, None, None, None, g2, None, None
+
+
+def _coo_handle(ii, jj, vv, m, n, base=1) -> int:
+    ki, pi = as_array(ii, np.int64); kj, pj = as_array(jj, np.int64); kv, pv = as_array(vv, np.float64)
+    h = C.c_int64(0)
+    check(lib.ab_csr_from_coo(_n(kv), pi, pj, pv, int(m), int(n), base, C.byref(h)))
+    return h.value
+
+
+def sparse_indexing_op(ii1, jj1, vv1, m, n, ii, jj):
+    """SparseIndexing -> (ii2, jj2, vv2)   (SparseIndexing.cpp:13-24, .h:23-63)."""
+    h = _coo_handle(ii1, jj1, vv1, m, n)
+    try:
+        ki, pi = as_array(ii, np.int64); kj, pj = as_array(jj, np.int64)
+        th = C.c_int64(0)
+        check(lib.ab_sparse_indexing(h, pi, _n(ki), pj, _n(kj), C.byref(th)))
+        like = vv1 if _is_torch(vv1) else np.empty(0)
+        return _fetch_trip(th.value, like)
+    finally:
+        lib.ab_csr_destroy(h)
+
+
+def sparse_indexing_grad(grad_vv2, ii2, jj2, vv2, ii1, jj1, vv1, m, n, ii, jj):
+    """SparseIndexingGrad -> 7 gradients, only grad_vv1 defined (.h:66-83)."""
+    h = _coo_handle(ii1, jj1, vv1, m, n)
+    try:
+        kg, pg = as_array(grad_vv2, np.float64)
+        ki, pi = as_array(ii, np.int64); kj, pj = as_array(jj, np.int64)
+        k0i, p0i = as_array(ii2, np.int64); k0j, p0j = as_array(jj2, np.int64)
+        out = empty_like_kind(kg, (_n(ii1),), np.float64)
+        check(lib.ab_sparse_indexing_grad(h, pi, _n(ki), pj, _n(kj), p0i, p0j, pg, _n(kg), ptr(out)))
+        return None, None, out, None, None, None, None
+    finally:
+        lib.ab_csr_destroy(h)
+
+
+def _matmul_colmajor(hA: int, hB: int, like):
+    """(A*B) as 1-based triplets in column-major order — what the reference ops emit by walking the
+    column-major Eigen result (SparseMatMul.cpp: `for k in outerSize: for InnerIterator`)."""
+    hc = C.c_int64(0)
+    check(lib.ab_spgemm(hA, hB, 1, C.byref(hc)))      # CSR of C' : its rows are C's columns
+    try:
+        m, n, nnz, T = (C.c_int64() for _ in range(4))
+        check(lib.ab_csr_query(hc.value, C.byref(m), C.byref(n), C.byref(nnz), C.byref(T)))
+        jj3 = empty_like_kind(like, (nnz.value,), np.int64)
+        ii3 = empty_like_kind(like, (nnz.value,), np.int64)
+        vv3 = empty_like_kind(like, (nnz.value,), np.float64)
+        check(lib.ab_csr_export_coo(hc.value, ptr(jj3), ptr(ii3), ptr(vv3), 1))
+        return ii3, jj3, vv3
+    finally:
+        lib.ab_csr_destroy(hc.value)
+
+
+def sparse_sparse_mat_mul_op(ii1, jj1, vv1, ii2, jj2, vv2, m, n, k):
+    """SparseSparseMatMul(ii1,jj1,vv1,ii2,jj2,vv2,m,n,k) -> (ii3,jj3,vv3); inputs 0-based, outputs
+    1-based column-major (SparseMatMul.cpp:12-24; SparseMatMul.h:11-32)."""
+    hA = _coo_handle(ii1, jj1, vv1, m, n, base=0)
+    hB = _coo_handle(ii2, jj2, vv2, n, k, base=0)
+    try:
+        return _matmul_colmajor(hA, hB, vv1 if _is_torch(vv1) else np.empty(0))
+    finally:
+        lib.ab_csr_destroy(hA); lib.ab_csr_destroy(hB)
+
+
+def _scaled_colmajor(ii, jj, vv, idx, d, m, k):
+    kx, px = as_array(idx, np.int64); kv, pv = as_array(vv, np.float64); kd, pd = as_array(d, np.float64)
+    out = empty_like_kind(kv, (_n(kv),), np.float64)
+    check(lib.ab_coo_scale(_n(kv), px, pv, pd, _n(kd), 0, ptr(out)))
+    # setFromTriplets of the scaled triplets, emitted column-major: assemble the transpose
+    h = _coo_handle(jj, ii, out, k, m, base=0)
+    try:
+        nnz = C.c_int64()
+        check(lib.ab_csr_query(h, None, None, C.byref(nnz), None))
+        ii3, jj3 = empty_like_kind(kv, (nnz.value,), np.int64), empty_like_kind(kv, (nnz.value,), np.int64)
+        vv3 = empty_like_kind(kv, (nnz.value,), np.float64)
+        check(lib.ab_csr_export_coo(h, ptr(jj3), ptr(ii3), ptr(vv3), 1))
+        return ii3, jj3, vv3
+    finally:
+        lib.ab_csr_destroy(h)
+
+
+def diag_sparse_mat_mul_op(ii1, jj1, vv1, ii2, jj2, vv2, m, n, k):
+    """DiagSparseMatMul: C = diag(vv1) * B, triplets (ii2, jj2, vv2*vv1[ii2]) (SparseMatMul.h:34-42)."""
+    return _scaled_colmajor(ii2, jj2, vv2, ii2, vv1, m, k)
+
+
+def sparse_diag_mat_mul_op(ii1, jj1, vv1, ii2, jj2, vv2, m, n, k):
+    """SparseDiagMatMul: C = A * diag(vv2), triplets (ii1, jj1, vv1*vv2[jj1]) (SparseMatMul.h:44-52)."""
+    return _scaled_colmajor(ii1, jj1, vv1, jj1, vv2, m, k)
+
+
+# ---------------------------------------------------------------------- SparseTensor level
+def _index_list(ix, dim: int):
+    """Julia-style index argument -> 1-based int64 list (sparse.jl:305-314): Colon (None / ':' /
+    slice(None)), integer, range / 1-based inclusive slice, integer array, Bool mask."""
+    if ix is None or (isinstance(ix, str) and ix == ":") or (isinstance(ix, slice) and ix == slice(None)):
+        return np.arange(1, dim + 1, dtype=np.int64), False
+    if isinstance(ix, (int, np.integer)) and not isinstance(ix, (bool, np.bool_)):
+        return np.array([int(ix)], dtype=np.int64), True
+    if isinstance(ix, slice):       # a:b and a:s:b are Julia ranges: 1-based, inclusive
+        step = 1 if ix.step is None else int(ix.step)
+        lo = 1 if ix.start is None else int(ix.start)
+        hi = dim if ix.stop is None else int(ix.stop)
+        return np.arange(lo, hi + (1 if step > 0 else -1), step, dtype=np.int64), False
+    if isinstance(ix, range):
+        return np.asarray(list(ix), dtype=np.int64), False
+    a = ix.cpu().numpy() if _is_torch(ix) else np.asarray(ix)
+    if a.dtype == np.bool_:
+        return (np.flatnonzero(a) + 1).astype(np.int64), False     # findall
+    return a.astype(np.int64).ravel(), False
+
+
+def _autograd():
+    import torch
+
+    class ZeroOutRowFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, vv, indices, bd):
+            oind, ovv = zero_out_row_op(indices, vv.detach(), bd)
+            ctx.indices, ctx.bd = indices, bd
+            ctx.mark_non_differentiable(oind)
+            return oind, ovv
+
+        @staticmethod
+        def backward(ctx, _gi, govv):
+            return zero_out_row_grad(govv.contiguous(), None, None, ctx.indices, None, ctx.bd)[1], None, None
+
+    class ScatterUpdateFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, vv1, vv2, ii1, jj1, m, n, ii2, jj2, ii, jj):
+            nii, njj, nvv = sparse_scatter_update_op(ii1, jj1, vv1.detach(), m, n, ii2, jj2, vv2.detach(), ii, jj)
+            ctx.args = (ii1, jj1, m, n, ii2, jj2, ii, jj)
+            ctx.mark_non_differentiable(nii, njj)
+            return nii, njj, nvv
+
+        @staticmethod
+        def backward(ctx, _a, _b, g):
+            ii1, jj1, m, n, ii2, jj2, ii, jj = ctx.args
+            r = sparse_scatter_update_grad(g.contiguous(), None, None, None, ii1, jj1, None, m, n, ii2, jj2, None, ii, jj)
+            return (r[2], r[7]) + (None,) * 8
+
+    class IndexingFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, vv1, ii1, jj1, m, n, ii, jj):
+            ii2, jj2, vv2 = sparse_indexing_op(ii1, jj1, vv1.detach(), m, n, ii, jj)
+            ctx.args = (ii1, jj1, m, n, ii, jj, ii2, jj2)
+            ctx.save_for_backward(vv1)
+            ctx.mark_non_differentiable(ii2, jj2)
+            return ii2, jj2, vv2
+
+        @staticmethod
+        def backward(ctx, _a, _b, g):
+            ii1, jj1, m, n, ii, jj, ii2, jj2 = ctx.args
+            (vv1,) = ctx.saved_tensors
+            r = sparse_indexing_grad(g.contiguous(), ii2, jj2, None, ii1, jj1, vv1.detach(), m, n, ii, jj)
+            return (r[2],) + (None,) * 6
+
+    return ZeroOutRowFn, ScatterUpdateFn, IndexingFn
+
+
+_AG = None
+
+
+def _ag():
+    global _AG
+    if _AG is None:
+        _AG = _autograd()
+    return _AG
+
+
+def _req(x) -> bool:
+    return _is_torch(x) and x.requires_grad
+
+
+def _sparse():
+    from . import sparse as sp
+
+    return sp
+
+
+def _as_st(A):
+    sp = _sparse()
+    return A if isinstance(A, sp.SparseTensor) else sp.SparseTensor(A)
+
+
+def zero_out_row(A, bd):
+    """zero_out_row(A, bd) (sparse.jl:790-797): drop every stored entry in the rows `bd` (1-based)."""
+    sp = _sparse()
+    A = _as_st(A)
+    ii, jj, vv = A.triplets()
+    if _is_torch(vv):
+        import torch
+
+        ind = torch.stack([torch.as_tensor(ii, device=vv.device).to(torch.int64) - 1,
+                           torch.as_tensor(jj, device=vv.device).to(torch.int64) - 1], dim=1).contiguous()
+    else:
+        ind = np.stack([np.asarray(ii, np.int64) - 1, np.asarray(jj, np.int64) - 1], axis=1)
+    bd = np.asarray(bd, dtype=np.int64).ravel()
+    if _req(vv):
+        oind, ovv = _ag()[0].apply(vv, ind, bd)
+    else:
+        oind, ovv = zero_out_row_op(ind, vv, bd)
+    return sp.SparseTensor(oind[:, 0] + 1, oind[:, 1] + 1, ovv, A.m, A.n)
+
+
+def scatter_update(A, i1, i2, B):
+    """A[i1, i2] = B (sparse.jl:340-364)."""
+    sp = _sparse()
+    A, B = _as_st(A), _as_st(B)
+    ii, _ = _index_list(i1, A.m)
+    jj, _ = _index_list(i2, A.n)
+    ii1, jj1, vv1 = A.triplets()
+    ii2, jj2, vv2 = B.triplets()
+    if _req(vv1) or _req(vv2):
+        import torch
+
+        dev = vv1.device if _is_torch(vv1) else vv2.device
+        vv1 = vv1 if _is_torch(vv1) else torch.as_tensor(np.asarray(vv1, np.float64), device=dev)
+        vv2 = vv2 if _is_torch(vv2) else torch.as_tensor(np.asarray(vv2, np.float64), device=dev)
+        nii, njj, nvv = _ag()[1].apply(vv1, vv2, ii1, jj1, A.m, A.n, ii2, jj2, ii, jj)
+    else:
+        nii, njj, nvv = sparse_scatter_update_op(ii1, jj1, vv1, A.m, A.n, ii2, jj2, vv2, ii, jj)
+    return sp.SparseTensor(nii, njj, nvv, A.m, A.n)
+
+
+def scatter_add(A, i1, i2, B):
+    """A[i1, i2] += B (sparse.jl:377-386): C = A[i1,i2]; D = B + C; scatter_update(A, i1, i2, D)."""
+    A, B = _as_st(A), _as_st(B)
+    return scatter_update(A, i1, i2, add(B, getindex(A, i1, i2)))
+
+
+def getindex(A, i1, i2):
+    """A[i1, i2] (sparse.jl:303-327).  Integer arguments squeeze that dimension and the result is dense
+    (the reference returns squeeze(Array(ret)))."""
+    sp = _sparse()
+    A = _as_st(A)
+    ii, sq1 = _index_list(i1, A.m)
+    jj, sq2 = _index_list(i2, A.n)
+    ii1, jj1, vv1 = A.triplets()
+    if _req(vv1):
+        ii2, jj2, vv2 = _ag()[2].apply(vv1, ii1, jj1, A.m, A.n, ii, jj)
+    else:
+        ii2, jj2, vv2 = sparse_indexing_op(ii1, jj1, vv1, A.m, A.n, ii, jj)
+    ret = sp.SparseTensor(ii2, jj2, vv2, len(ii), len(jj))
+    if sq1 or sq2:
+        d = ret.toarray()
+        return d.squeeze(axis=tuple(k for k, s in enumerate((sq1, sq2)) if s))
+    return ret
+
+
+def _cat(a, b, dtype):
+    if _is_torch(a) or _is_torch(b):
+        import torch
+
+        dev = a.device if _is_torch(a) else b.device
+        tdt = torch.float64 if dtype == np.float64 else torch.int64
+        ta = a if _is_torch(a) else torch.as_tensor(np.asarray(a, dtype), device=dev)
+        tb = b if _is_torch(b) else torch.as_tensor(np.asarray(b, dtype), device=dev)
+        return torch.cat([ta.to(tdt), tb.to(tdt)])
+    return np.concatenate([np.asarray(a, dtype), np.asarray(b, dtype)])
+
+
+def add(A, B, alpha: float = 1.0, beta: float = 1.0):
+    """A + B on the union pattern (sparse.jl:217 -> tf.sparse.add).  With triplets at hand the sum is
+    the concatenated stream (duplicates are summed by every consumer, A's term first); two
+    pattern-only (device-handle) operands go through ab_csr_axpby."""
+    sp = _sparse()
+    A, B = _as_st(A), _as_st(B)
+    if A.shape != B.shape:
+        raise ValueError(f"size {A.shape} and {B.shape} does not match")
+    if A._pattern_only and B._pattern_only:
+        h = C.c_int64(0)
+        check(lib.ab_csr_axpby(A.handle(), float(alpha), B.handle(), float(beta), C.byref(h)))
+        return sp.SparseTensor.from_handle(h.value)
+    ii1, jj1, vv1 = A.triplets()
+    ii2, jj2, vv2 = B.triplets()
+    v1 = vv1 if alpha == 1.0 else vv1 * alpha
+    v2 = vv2 if beta == 1.0 else vv2 * beta
+    return sp.SparseTensor(_cat(ii1, ii2, np.int64), _cat(jj1, jj2, np.int64), _cat(v1, v2, np.float64), A.m, A.n,
+                           is_diag=A._diag and B._diag)
+
+
+def matmul(A, B):
+    """SparseTensor * SparseTensor (sparse.jl:579-595): SpGEMM, with the reference's diagonal fast
+    paths when either factor carries `_diag`.  No gradient is registered (as in the reference)."""
+    sp = _sparse()
+    A, B = _as_st(A), _as_st(B)
+    if A.n != B.m:
+        raise ValueError(f"matrix size mismatch: ({A.m}, {A.n}) vs ({B.m}, {B.n})")
+    if A._diag and not A._pattern_only and not B._pattern_only and _n(A.vv) == A.m:
+        ii2, jj2, vv2 = B.triplets()
+        i3, j3, v3 = diag_sparse_mat_mul_op(None, None, _diag_values(A), _z(ii2), _z(jj2), vv2, A.m, A.n, B.n)
+        return sp.SparseTensor(i3, j3, v3, A.m, B.n, is_diag=A._diag and B._diag)
+    if B._diag and not A._pattern_only and not B._pattern_only and _n(B.vv) == B.m:
+        ii1, jj1, vv1 = A.triplets()
+        i3, j3, v3 = sparse_diag_mat_mul_op(_z(ii1), _z(jj1), vv1, None, None, _diag_values(B), A.m, A.n, B.n)
+        return sp.SparseTensor(i3, j3, v3, A.m, B.n, is_diag=False)
+    h = C.c_int64(0)
+    check(lib.ab_spgemm(A.handle(), B.handle(), 0, C.byref(h)))
+    return sp.SparseTensor.from_handle(h.value)
+
+
+def _z(ix):
+    """1-based -> 0-based index array (the matmul ops take `ii-1`, sparse.jl:593)."""
+    return ix - 1 if _is_torch(ix) else np.asarray(ix, np.int64) - 1
+
+
+def _diag_values(D):
+    """Values of a `_diag` SparseTensor ordered by row — the reference indexes vv by row directly,
+    which assumes this order (spdiag builds it so, sparse.jl:553-559)."""
+    ii, jj, vv = D.triplets()
+    if _is_torch(vv):
+        import torch
+
+        out = torch.zeros(D.m, dtype=torch.float64, device=vv.device)
+        out[torch.as_tensor(ii, device=vv.device).to(torch.int64) - 1] = vv.detach()
+        return out
+    out = np.zeros(D.m)
+    out[np.asarray(ii, np.int64) - 1] = np.asarray(vv, np.float64)
+    return out
+
+
+def spdiag(*args):
+    """spdiag(n) identity, spdiag(o) diagonal matrix from a vector, spdiag(n, k1=>v1, ...) banded
+    matrix from (offset, values) pairs (sparse.jl:544-561, 631-658)."""
+    sp = _sparse()
+    if len(args) == 1 and isinstance(args[0], (int, np.integer)):
+        n = int(args[0])
+        i = np.arange(1, n + 1, dtype=np.int64)
+        return sp.SparseTensor(i, i.copy(), np.ones(n), n, n)
+    if len(args) == 1:
+        o = args[0]
+        if len(tuple(o.shape)) != 1:
+            raise ValueError("ADCME: input `o` must be a vector")
+        n = int(o.shape[0])
+        i = np.arange(1, n + 1, dtype=np.int64)
+        return sp.SparseTensor(i, i.copy(), o, n, n, is_diag=True)
+    n, pairs = int(args[0]), args[1:]
+    I, J, V = [], [], []
+    for k, v in pairs:
+        k = int(k)
+        if not -(n - 1) <= k <= n - 1:
+            raise ValueError("spdiag: offset out of range")
+        if _n(v) != n - abs(k):
+            raise ValueError(f"spdiag: diagonal {k} needs {n - abs(k)} values")
+        if k >= 0:
+            I.append(np.arange(1, n - k + 1, dtype=np.int64)); J.append(np.arange(k + 1, n + 1, dtype=np.int64))
+        else:
+            I.append(np.arange(-k + 1, n + 1, dtype=np.int64)); J.append(np.arange(1, n + k + 1, dtype=np.int64))
+        V.append(v)
+    if any(_is_torch(v) for v in V):
+        import torch
+
+        dev = next(v.device for v in V if _is_torch(v))
+        vv = torch.cat([v if _is_torch(v) else torch.as_tensor(np.asarray(v, np.float64), device=dev) for v in V])
+    else:
+        vv = np.concatenate([np.asarray(v, np.float64) for v in V])
+    return sp.SparseTensor(np.concatenate(I), np.concatenate(J), vv, n, n)
+
+
+def spzero(m: int, n: int | None = None):
+    """spzero(m, n=m) (sparse.jl:568-575)."""
+    sp = _sparse()
+    n = m if n is None else n
+    return sp.SparseTensor(np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0), int(m), int(n), is_diag=True)

@@ -181,6 +181,64 @@ int ab_poisson2d_update(int64_t h, int64_t n, const double* kext, int sign);
 int ab_poisson2d_grad(int64_t n, const double* xgrad, const double* uext, int sign,
                       double* grad_kext /*[(n+2)*(n+2)]*/);
 
+/* ---- structural edits between assembly and solve and the remaining
+ *      SparseTensor algebra (N4) — csrc/structure.cu ---------------------------------
+ * The reference ops below return triplet lists whose length is known only after the op ran (they
+ * size allocate_output from op-private state, e.g. IJV.get_size()).  Here such a result is parked
+ * on the device under a TRIPLET HANDLE: ab_trip_size -> caller allocates -> ab_trip_fetch (which
+ * frees the handle, like ab_asm_copy), or ab_csr_from_trip assembles it without leaving the GPU. */
+int64_t ab_trip_size(int64_t th);                                   /* <0: error code            */
+int     ab_trip_fetch(int64_t th, int64_t* ii, int64_t* jj, double* vv);   /* outputs may be NULL */
+int     ab_trip_fetch_idx2(int64_t th, int64_t* idx2 /*[n,2]*/, double* vv);
+int     ab_trip_destroy(int64_t th);
+int     ab_csr_from_trip(int64_t th, int64_t m, int64_t n, int base, int64_t* out_h); /* consumes th */
+
+/* zero_out_row (src/sparse.jl:790-797; deps/CustomOps/ZeroOutRow/ZeroOutRow.h:28-57):
+ * idx2 = 0-based [N,2] indices, bd = 1-based rows to drop; kept entries keep their order.
+ * grad: grad_v[i] = grad_oval[k] for the k-th kept entry, 0 for dropped ones. */
+int ab_zero_out_row(int64_t N, const int64_t* idx2, const double* v, const int64_t* bd, int64_t nbd,
+                    int64_t* out_th);
+int ab_zero_out_row_grad(int64_t N, const int64_t* idx2, const int64_t* bd, int64_t nbd,
+                         const double* grad_oval, int64_t nout, double* grad_v /*[N]*/);
+
+/* sparse_scatter_update, A[ii,jj] = B (src/sparse.jl:340-364;
+ * deps/CustomOps/SparseScatterUpdate/SparseScatterUpdate.h:20-60).  All indices 1-based;
+ * (uii,ujj) are positions inside the block.  Output = entries of A outside ii x jj in input
+ * order, followed by (ii[uii-1], jj[ujj-1], uvv) in input order.
+ * grad: grad_ovv = grad_out for kept entries / 0 for replaced ones; grad_uvv = the tail. */
+int ab_scatter_update(int64_t on, const int64_t* oii, const int64_t* ojj, const double* ovv,
+                      int64_t un, const int64_t* uii, const int64_t* ujj, const double* uvv,
+                      int64_t m, int64_t n, const int64_t* ii, int64_t ni, const int64_t* jj, int64_t nj,
+                      int64_t* out_th);
+int ab_scatter_update_grad(int64_t on, const int64_t* oii, const int64_t* ojj, int64_t un,
+                           int64_t m, int64_t n, const int64_t* ii, int64_t ni, const int64_t* jj, int64_t nj,
+                           const double* grad_out, int64_t nout,
+                           double* grad_ovv /*[on] or NULL*/, double* grad_uvv /*[un] or NULL*/);
+
+/* sparse_indexing, A[ii,jj] (src/sparse.jl:303-327; deps/CustomOps/SparseIndexing/SparseIndexing.h:23-83).
+ * h = assembled A (duplicates summed, as the op's setFromTriplets does); ii, jj 1-based, without
+ * repeats.  Output triplets are 1-based positions inside the block, ordered by position in jj, then
+ * by ascending row of A (the reference's column walk).
+ * grad: the gradient of output k goes to the LAST input triplet of A at (ii[ii0-1], jj[jj0-1]). */
+int ab_sparse_indexing(int64_t h, const int64_t* ii, int64_t ni, const int64_t* jj, int64_t nj,
+                       int64_t* out_th);
+int ab_sparse_indexing_grad(int64_t h, const int64_t* ii, int64_t ni, const int64_t* jj, int64_t nj,
+                            const int64_t* ii0, const int64_t* jj0, const double* grad_vv0, int64_t nout,
+                            double* grad_vv1 /*[T]*/);
+
+/* stored entries of a CSR handle as triplets in row-major order (find(), src/sparse.jl:93-99) */
+int ab_csr_export_coo(int64_t h, int64_t* ii, int64_t* jj, double* vv, int base);
+/* out[t] = vv[t] * d[idx[t] - base]: diag_sparse_mat_mul (idx = rows) / sparse_diag_mat_mul
+ * (idx = cols), deps/CustomOps/SparseMatMul/SparseMatMul.h:34-52 */
+int ab_coo_scale(int64_t T, const int64_t* idx, const double* vv, const double* d, int64_t nd,
+                 int base, double* out);
+/* C = alpha*A + beta*B on the union pattern (A + B: src/sparse.jl:203-218 -> tf.sparse.add) */
+int ab_csr_axpby(int64_t ha, double alpha, int64_t hb, double beta, int64_t* out_h);
+/* C = A*B (sparse_sparse_mat_mul, SparseMatMul.h:11-32; src/sparse.jl:579-595).  transpose_out != 0
+ * returns C' — whose row-major entries are C's column-major ones, the order the reference op emits.
+ * Each C(i,j) is summed in k-ascending order (Eigen's column-major product order). */
+int ab_spgemm(int64_t ha, int64_t hb, int transpose_out, int64_t* out_h);
+
 /* ---- row-block distributed CSR + solve (a12) --------------------------
  * Replaces mpi_SparseTensor `\` (src/mpi.jl:420-508; MPITensor.h:103-152):
  * one process per GPU, rank r owns rows [ilower, iupper] (Hypre IJ layout,

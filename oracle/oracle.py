@@ -210,6 +210,133 @@ def _splu_solve(ii, jj, vv, f, d, transpose):
     return x
 
 
+# ---------------------------------------------------------------- structural ops
+# Plain-Python restatements (small cases only) of the reference loops, line by line.
+def zero_out_row(indices, vv, bd):
+    """ZeroOutRow::forward + move_data (deps/CustomOps/ZeroOutRow/ZeroOutRow.h:19-48): indices are the
+    0-based [N,2] matrix, bd is 1-based; entries whose row is in {bd-1} are skipped, order kept."""
+    indices, vv = _i64(indices).reshape(-1, 2), _f64(vv)
+    bdset = {int(b) - 1 for b in np.asarray(bd).ravel()}
+    keep = [i for i in range(len(vv)) if int(indices[i, 0]) not in bdset]
+    return indices[keep].copy().reshape(-1, 2), vv[keep].copy()
+
+
+def zero_out_row_grad(indices, bd, grad_oval):
+    """ZeroOutRow::backward (ZeroOutRow.h:50-57); dropped slots (left unwritten there) are 0 here."""
+    indices, g = _i64(indices).reshape(-1, 2), _f64(grad_oval)
+    bdset = {int(b) - 1 for b in np.asarray(bd).ravel()}
+    out, k = np.zeros(indices.shape[0]), 0
+    for i in range(indices.shape[0]):
+        if int(indices[i, 0]) in bdset:
+            continue
+        out[i] = g[k]
+        k += 1
+    return out
+
+
+def sparse_scatter_update(oii, ojj, ovv, uii, ujj, uvv, m, n, ii, jj):
+    """forward (deps/CustomOps/SparseScatterUpdate/SparseScatterUpdate.h:20-37), all 1-based."""
+    oii, ojj, ovv = _i64(oii), _i64(ojj), _f64(ovv)
+    uii, ujj, uvv = _i64(uii), _i64(ujj), _f64(uvv)
+    ii, jj = _i64(ii), _i64(jj)
+    iset, jset = set(ii.tolist()), set(jj.tolist())
+    I, J, V = [], [], []
+    for i in range(len(ovv)):
+        if int(oii[i]) in iset and int(ojj[i]) in jset:
+            continue
+        I.append(oii[i]); J.append(ojj[i]); V.append(ovv[i])
+    for i in range(len(uvv)):
+        I.append(ii[uii[i] - 1]); J.append(jj[ujj[i] - 1]); V.append(uvv[i])
+    return np.array(I, np.int64), np.array(J, np.int64), np.array(V, np.float64)
+
+
+def sparse_scatter_update_grad(grad_out, oii, ojj, un, ii, jj):
+    """backward (SparseScatterUpdate.h:39-60) -> (grad_ovv, grad_uvv)."""
+    g, oii, ojj = _f64(grad_out), _i64(oii), _i64(ojj)
+    iset, jset = set(_i64(ii).tolist()), set(_i64(jj).tolist())
+    govv, k0 = np.zeros(len(oii)), 0
+    for i in range(len(oii)):
+        if int(oii[i]) in iset and int(ojj[i]) in jset:
+            govv[i] = 0.0
+        else:
+            govv[i] = g[k0]; k0 += 1
+    return govv, g[k0:k0 + un].copy()
+
+
+def _csc_from_triplets(ii, jj, vv, m, n, base):
+    """Eigen setFromTriplets into a column-major matrix = our CSR restatement with the roles of the
+    two indices swapped: -> (colptr, rowind, values), rows sorted, duplicates summed in input order."""
+    cp, ri, va, _ = coo_to_csr(jj, ii, vv, n, m, base=base)
+    return cp, ri, va
+
+
+def sparse_indexing(ii1, jj1, vv1, m, n, ii, jj):
+    """forward (deps/CustomOps/SparseIndexing/SparseIndexing.h:23-63): 1-based in, 1-based block
+    positions out, ordered by position in jj then ascending row."""
+    ii, jj = _i64(ii), _i64(jj)
+    ii_map = {int(v): p for p, v in enumerate(ii.tolist())}      # later duplicates overwrite
+    jj_map = {int(v): p for p, v in enumerate(jj.tolist())}
+    cp, ri, va = _csc_from_triplets(ii1, jj1, vv1, m, n, base=1)
+    ii_sorted = sorted(ii.tolist())
+    I, J, V = [], [], []
+    for k in range(len(jj)):
+        col = int(jj[k])
+        rows = {int(ri[q]) + 1: va[q] for q in range(cp[col - 1], cp[col])}
+        for r in ii_sorted:                       # std::set_intersection of two sorted lists
+            if r in rows:
+                I.append(ii_map[r] + 1); J.append(jj_map[col] + 1); V.append(rows[r])
+    return np.array(I, np.int64), np.array(J, np.int64), np.array(V, np.float64)
+
+
+def sparse_indexing_grad(grad_vv0, ii0, jj0, ii1, jj1, ii, jj):
+    """backward (SparseIndexing.h:66-83): the std::map keeps the LAST triplet index of each (i,j)."""
+    g, ii0, jj0 = _f64(grad_vv0), _i64(ii0), _i64(jj0)
+    ii1, jj1, ii, jj = _i64(ii1), _i64(jj1), _i64(ii), _i64(jj)
+    mp = {(int(a), int(b)): k for k, (a, b) in enumerate(zip(ii1.tolist(), jj1.tolist()))}
+    out = np.zeros(len(ii1))
+    for i in range(len(g)):
+        out[mp[(int(ii[ii0[i] - 1]), int(jj[jj0[i] - 1]))]] += g[i]
+    return out
+
+
+def sparse_sparse_mat_mul(ii1, jj1, vv1, ii2, jj2, vv2, m, n, k):
+    """forward (deps/CustomOps/SparseMatMul/SparseMatMul.h:11-32) + the emission loop of
+    SparseMatMul.cpp: 0-based triplets in, C = A*B by Eigen's column-major conservative product
+    (for each column j of B, for each stored B(kk,j) in ascending kk, for each stored A(i,kk):
+    C(i,j) += A(i,kk)*B(kk,j)), 1-based column-major triplets out, structural zeros kept."""
+    acp, ari, ava = _csc_from_triplets(ii1, jj1, vv1, m, n, base=0)
+    bcp, bri, bva = _csc_from_triplets(ii2, jj2, vv2, n, k, base=0)
+    I, J, V = [], [], []
+    for j in range(k):
+        acc = {}
+        for q in range(bcp[j], bcp[j + 1]):
+            kk, y = int(bri[q]), bva[q]
+            for p in range(acp[kk], acp[kk + 1]):
+                i, x = int(ari[p]), ava[p]
+                acc[i] = acc[i] + x * y if i in acc else x * y
+        for i in sorted(acc):
+            I.append(i + 1); J.append(j + 1); V.append(acc[i])
+    return np.array(I, np.int64), np.array(J, np.int64), np.array(V, np.float64)
+
+
+def _colmajor_from_triplets(ii, jj, vv, m, k):
+    cp, ri, va = _csc_from_triplets(ii, jj, vv, m, k, base=0)
+    J = np.repeat(np.arange(k, dtype=np.int64), np.diff(cp)) + 1
+    return ri.astype(np.int64) + 1, J, va
+
+
+def diag_sparse_mat_mul(vv1, ii2, jj2, vv2, m, k):
+    """forward_diag_sparse (SparseMatMul.h:34-42): triplets (ii2, jj2, vv2*vv1[ii2]) -> setFromTriplets."""
+    ii2, jj2 = _i64(ii2), _i64(jj2)
+    return _colmajor_from_triplets(ii2, jj2, _f64(vv2) * _f64(vv1)[ii2], m, k)
+
+
+def sparse_diag_mat_mul(ii1, jj1, vv1, vv2, m, k):
+    """forward_sparse_diag (SparseMatMul.h:44-52): triplets (ii1, jj1, vv1*vv2[jj1])."""
+    ii1, jj1 = _i64(ii1), _i64(jj1)
+    return _colmajor_from_triplets(ii1, jj1, _f64(vv1) * _f64(vv2)[jj1], m, k)
+
+
 # ---------------------------------------------------------------- Poisson generators
 def poisson2d_matrix(n: int, kext):
     """GetPoissonMatrixForward (GetPoissonMatrix.h:15-51), single-rank colext."""

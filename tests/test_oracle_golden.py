@@ -186,3 +186,57 @@ def test_pcg_port_matches_direct_solve(orc):
     rp4, ci4, va4 = orc.poisson3d_csr(4, 4, 4)
     assert np.array_equal(rpf, rp4) and np.array_equal(cif, ci4) and np.array_equal(vaf, va4)
     assert rp3[-1] == 7 * 60 - 2 * (20 + 12 + 15)
+
+
+# ======================================================================== structural ops (N2, N4)
+def test_get_index_golden(orc, golden):
+    g = golden["get_index_bool_mask"]                         # test/sparse.jl:316-321
+    sel = np.flatnonzero(g["idof"]) + 1                       # findall(idof)
+    I, J, V = orc.sparse_indexing([1, 2], [1, 2], g["diag"], 2, 2, sel, sel)
+    assert _dense_from_triplets(I, J, V, 1, 1).tolist() == g["expect_dense"]
+
+
+def test_structural_oracle_vs_scipy(orc, golden):
+    rng = np.random.default_rng(233)
+    A = sp.random(10, 10, 0.3, random_state=1, format="coo")
+    B = sp.random(3, 3, 0.6, random_state=2, format="coo")
+    g = golden["scatter_update_shape"]                        # test/sparse.jl:294-308
+    ii, jj = np.array(g["ii"]), np.array(g["jj"])
+    I, J, V = orc.sparse_scatter_update(A.row + 1, A.col + 1, A.data, B.row + 1, B.col + 1, B.data, 10, 10, ii, jj)
+    C = A.toarray().copy()
+    C[np.ix_(ii - 1, jj - 1)] = B.toarray()
+    assert np.array_equal(_dense_from_triplets(I, J, V, 10, 10), C)
+    # gradient bookkeeping: kept entries first (input order), block entries after
+    gout = rng.standard_normal(len(V))
+    govv, guvv = orc.sparse_scatter_update_grad(gout, A.row + 1, A.col + 1, B.nnz, ii, jj)
+    inside = np.isin(A.row + 1, ii) & np.isin(A.col + 1, jj)
+    assert np.all(govv[inside] == 0) and np.array_equal(govv[~inside], gout[: (~inside).sum()])
+    assert np.array_equal(guvv, gout[(~inside).sum():])
+    z = golden["zero_out_row_shape"]                          # test/sparse.jl:383-389
+    oi, ov = orc.zero_out_row(np.stack([A.row, A.col], 1), A.data, z["bd"])
+    Z = A.toarray().copy()
+    Z[np.array(z["bd"]) - 1, :] = 0
+    assert np.array_equal(_dense_from_triplets(oi[:, 0] + 1, oi[:, 1] + 1, ov, 10, 10), Z)
+    gz = orc.zero_out_row_grad(np.stack([A.row, A.col], 1), z["bd"], np.arange(1.0, len(ov) + 1))
+    assert np.array_equal(gz[gz != 0], np.arange(1.0, len(ov) + 1)) and np.all(gz[np.isin(A.row + 1, z["bd"])] == 0)
+    # A[i1, j1] on a 20 x 30 matrix (test/sparse.jl:181-190)
+    A2 = sp.random(20, 30, 0.3, random_state=3, format="coo")
+    i1, j1 = np.array([17, 3, 9]), np.array([30, 1, 12])
+    I, J, V = orc.sparse_indexing(A2.row + 1, A2.col + 1, A2.data, 20, 30, i1, j1)
+    assert np.array_equal(_dense_from_triplets(I, J, V, 3, 3), A2.tocsr()[i1 - 1][:, j1 - 1].toarray())
+    gi = orc.sparse_indexing_grad(np.ones(len(V)), I, J, A2.row + 1, A2.col + 1, i1, j1)
+    assert gi.sum() == len(V) and np.all(gi[~(np.isin(A2.row + 1, i1) & np.isin(A2.col + 1, j1))] == 0)
+
+
+def test_spgemm_oracle_vs_scipy(orc):
+    # test/sparse.jl:141-162: A(10x5)*B(5x20), diag*B, A*diag
+    A = sp.random(10, 5, 0.3, random_state=5, format="coo")
+    B = sp.random(5, 20, 0.3, random_state=6, format="coo")
+    I, J, V = orc.sparse_sparse_mat_mul(A.row, A.col, A.data, B.row, B.col, B.data, 10, 5, 20)
+    assert np.allclose(_dense_from_triplets(I, J, V, 10, 20), (A @ B).toarray(), rtol=1e-15, atol=0)
+    assert np.all(np.diff(J * 100 + I) > 0), "emission is column-major"
+    d = np.array([1.0, 2, 3, 4, 5])
+    I, J, V = orc.diag_sparse_mat_mul(d, B.row, B.col, B.data, 5, 20)
+    assert np.allclose(_dense_from_triplets(I, J, V, 5, 20), (sp.diags(d) @ B).toarray(), rtol=1e-15, atol=0)
+    I, J, V = orc.sparse_diag_mat_mul(A.row, A.col, A.data, d, 10, 5)
+    assert np.allclose(_dense_from_triplets(I, J, V, 10, 5), (A @ sp.diags(d)).toarray(), rtol=1e-15, atol=0)
