@@ -133,6 +133,15 @@ struct Csr {
     uint8_t* off8   = nullptr;   // [nnz+64]
     int32_t* offtab = nullptr;   // [256]
     int      noff   = -1;
+    // pattern-code form for the iterative solvers (lazy, spmv.cu): when the value array a solver
+    // multiplies with (the scaled copy svalues) has so few distinct (offset, value) pairs that one
+    // byte names the pair, code8[e] indexes codetab[256] = {value, offset}: 1 instead of 9 bytes per
+    // stored entry.  ncode: -1 not attempted, 0 unavailable, else number of pairs.
+    uint8_t* code8   = nullptr;    // [nnz+64]
+    void*    codetab = nullptr;    // [256] x {double value; int32 offset; int32 pad}
+    int      ncode   = -1;
+    uint64_t code_version = 0;     // values_version the codes were built from
+    const double* code_src = nullptr;   // the value array they encode
     // triplet bookkeeping (null when the handle was created from CSR: identity map)
     uint32_t* perm     = nullptr; // [T]  sorted position -> input triplet
     uint32_t* segstart = nullptr; // [nnz+1] first sorted position of each stored entry

@@ -271,6 +271,10 @@ int ab_bench_spmv(int64_t h, const double* x, double* y, int reps, int with_dot,
 int ab_bench_cg_kernels(int64_t h, int reps, double* ms_spmv_dot, double* ms_update,
                         double* ms_direction);
 int64_t ab_launch_count(void);   /* kernels launched by this library since ab_init */
+/* which SpMV form a handle currently uses: "noff" (offset-dictionary size, 0 = int32 colind),
+ * "ncode" (pattern-code dictionary size of the solver values, 0 = none), "tile_rows",
+ * "max_row_nnz", "scaled" (1 when CG runs on the symmetrically scaled copy) */
+int ab_csr_get_info(int64_t h, const char* key, double* value);
 
 #ifdef __cplusplus
 }

@@ -629,6 +629,54 @@ def test_c3_cg_solve_converges_128cubed(pkg):
     assert torch.equal(u, u2)
 
 
+def test_pattern_code_spmv_is_lossless(pkg):
+    """The solver's pattern-code SpMV (1 byte per entry naming an {offset, value} pair) must give the
+    same bits as the offset-dictionary and plain kernels, and must step aside by itself when the
+    values do not admit a 256-entry dictionary (variable coefficients)."""
+    import torch
+
+    outs = {}
+    for n in (48, 67):                         # 67: tiles straddle planes, odd sizes
+        N = n ** 3
+        h = C.c_int64(0)
+        pkg.check(pkg.lib.ab_poisson3d_csr(n, n, n, 0, N, C.byref(h)))
+        A = pkg.SparseTensor.from_handle(h.value)
+        f = torch.rand(N, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(233))
+        rr = C.c_double(0)
+        for name, code, off8 in (("code", 1.0, 1.0), ("off8", 0.0, 1.0), ("plain", 0.0, 0.0)):
+            pkg.check(pkg.lib.ab_set_option(b"spmv_code", code))
+            pkg.check(pkg.lib.ab_set_option(b"spmv_off8", off8))
+            try:
+                u = torch.empty_like(f)
+                pkg.check(pkg.lib.ab_cg_fixed(A.handle(), f.data_ptr(), u.data_ptr(), 40, C.byref(rr)))
+                outs[name] = (u, rr.value)
+            finally:
+                pkg.check(pkg.lib.ab_set_option(b"spmv_code", 1.0))
+                pkg.check(pkg.lib.ab_set_option(b"spmv_off8", 1.0))
+        assert torch.equal(outs["code"][0], outs["off8"][0]) and torch.equal(outs["code"][0], outs["plain"][0])
+        assert outs["code"][1] == outs["plain"][1]
+        A.close()
+    # variable coefficients: > 256 distinct values -> the dictionary is refused, the solve is unchanged
+    rng = np.random.default_rng(233)
+    n = 64
+    kext = np.exp(rng.uniform(-1, 1, (n + 2, n + 2)))
+    h = C.c_int64(0)
+    pkg.check(pkg.lib.ab_poisson2d_csr(n, kext.ctypes.data, -1, C.byref(h)))
+    A = pkg.SparseTensor.from_handle(h.value)
+    S = A.to_scipy()
+    f = rng.uniform(size=n * n)
+    u = pkg.backslash(A, f, "CG")
+    assert np.linalg.norm(S @ u - f) / np.linalg.norm(f) <= TOL_SOLVE
+    # new values on the same pattern invalidate the codes (values_version): constant -> scaled by 3
+    h2 = C.c_int64(0)
+    pkg.check(pkg.lib.ab_poisson2d_csr(n, np.ones((n + 2, n + 2)).ctypes.data, -1, C.byref(h2)))
+    B = pkg.SparseTensor.from_handle(h2.value)
+    u1 = pkg.backslash(B, f, "CG")
+    pkg.check(pkg.lib.ab_poisson2d_update(h2.value, n, (3.0 * np.ones((n + 2, n + 2))).ctypes.data, -1))
+    u3 = pkg.backslash(B, f, "CG")
+    assert np.linalg.norm(3.0 * u3 - u1) / np.linalg.norm(u1) <= 1e-9
+
+
 def test_dist_path_world1_equals_single_gpu(pkg):
     """ab_dist_* with one rank must reproduce the single-GPU solver bit for bit."""
     import torch
