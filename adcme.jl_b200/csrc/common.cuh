@@ -142,6 +142,13 @@ struct Csr {
     int      ncode   = -1;
     uint64_t code_version = 0;     // values_version the codes were built from
     const double* code_src = nullptr;   // the value array they encode
+    // row-pattern form on top of the pattern codes (lazy, spmv.cu): when the rows' code sequences
+    // come from at most 256 distinct patterns (a 3-D 7-point stencil has 27), rowcode[r] names the
+    // pattern and pat_ent / pat_info hold the patterns: 1 byte per ROW instead of per entry, no rowptr.
+    uint8_t*  rowcode  = nullptr;  // [m]
+    void*     pat_ent  = nullptr;  // [npat_ent] x {double value; int32 offset; int32 pad}, patterns back to back
+    uint32_t* pat_info = nullptr;  // [256] start | len << 16
+    int       npat = -1, npat_ent = 0;   // npat: -1 not attempted, 0 unavailable
     // triplet bookkeeping (null when the handle was created from CSR: identity map)
     uint32_t* perm     = nullptr; // [T]  sorted position -> input triplet
     uint32_t* segstart = nullptr; // [nnz+1] first sorted position of each stored entry

@@ -34,6 +34,16 @@
 //    Built lazily per values_version (hash-collect distinct values -> pair census -> encode); any
 //    matrix with more pairs silently keeps the tile8 / tile kernels.
 //
+//  * spmv_rowpat_kernel<R> — one level further for the same solver path: when the rows' sequences
+//    of pattern codes come from at most 256 distinct ROW PATTERNS (a 3-D 7-point stencil has 27:
+//    interior plus the face/edge/corner variants) one byte per ROW names the pattern and the
+//    patterns' {value, offset} lists (<= 2048 entries in total) sit in shared memory.  No rowptr, no
+//    staging, no barrier: lane = row reads its byte (coalesced), walks the pattern (warp-uniform
+//    LDS.128 broadcasts) and gathers x.  HBM traffic per row: 1 + 8 (x) + 8 (y) bytes.  The build
+//    hashes every row's code sequence, keeps <= 256 representatives, and VERIFIES every row against
+//    its pattern byte by byte, so the form is lossless or not used; summation order inside a row is
+//    the stored order, hence results are bit-identical to the other kernels.
+//
 //  * spmv_vector_kernel<L> — general fallback (long / irregular rows): L lanes per row straight
 //    from global memory, shuffle reduction.
 //
@@ -447,6 +457,7 @@ pair_encode_kernel(const uint8_t* __restrict__ off8, size_t nnz, const uint8_t* 
 static int csr_ensure_code(Csr* c, const double* vals) {
     if (c->ncode >= 0 && c->code_version == c->values_version && c->code_src == vals) return AB_OK;
     c->ncode = 0; c->code_version = c->values_version; c->code_src = vals;
+    c->npat = -1;
     if (c->noff <= 0 || c->nnz == 0) return AB_OK;
     const size_t nnz = (size_t)c->nnz;
     DevBuf<unsigned long long> gtab; DevBuf<int> gcount;
@@ -505,6 +516,214 @@ static int csr_ensure_code(Csr* c, const double* vals) {
     AB_LAUNCH_CHECK();
     AB_CUDA(cudaStreamSynchronize(stream()));   // host tables must outlive the copies
     c->ncode = ncode;
+    return AB_OK;
+}
+
+// ---- row-pattern form ---------------------------------------------------------------------------
+constexpr int PAT_MAX_ENT = 2048;   // total {value, offset} entries over all patterns (32 KB of shared memory)
+constexpr int PAT_MAX_LEN = 255;
+
+template <int R>
+__global__ void __launch_bounds__(R)
+spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__ pat_ent, int npat_ent,
+                   const uint32_t* __restrict__ pat_info, const double* __restrict__ x, double* __restrict__ y,
+                   int64_t m, unsigned ntiles, const int32_t* __restrict__ tile_list, int accumulate,
+                   const double* __restrict__ dotvec, double* partials, uint32_t* ticket, double* dot_result,
+                   const int* __restrict__ done) {
+    extern __shared__ __align__(16) unsigned char rp_smem[];
+    int4* s_ent = reinterpret_cast<int4*>(rp_smem);                                  // [npat_ent]
+    uint32_t* s_info = reinterpret_cast<uint32_t*>(rp_smem + (size_t)npat_ent * 16);  // [256]
+    __shared__ double s_red[32];
+    if (done && *done) return;
+    const int t = threadIdx.x;
+    for (int i = t; i < npat_ent; i += R) s_ent[i] = pat_ent[i];
+    for (int i = t; i < 256; i += R) s_info[i] = pat_info[i];
+    __syncthreads();
+    double dot = 0.0, dot2 = 0.0;
+    for (unsigned ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const unsigned tile = tile_list ? (unsigned)tile_list[ti] : ti;
+        const int64_t row = (int64_t)tile * R + t;
+        if (row < m) {
+            const uint32_t info = s_info[rowcode[row]];
+            const int4* e = s_ent + (info & 0xffffu);
+            const int len = (int)(info >> 16);
+            const double* xr = x + row;
+            double acc = 0.0;
+            int k = 0;
+            for (; k + 4 <= len; k += 4) {
+                const int4 c0 = e[k], c1 = e[k + 1], c2 = e[k + 2], c3 = e[k + 3];
+                const double x0 = __ldg(xr + c0.z), x1 = __ldg(xr + c1.z), x2 = __ldg(xr + c2.z), x3 = __ldg(xr + c3.z);
+                acc = fma(__hiloint2double(c0.y, c0.x), x0, acc);
+                acc = fma(__hiloint2double(c1.y, c1.x), x1, acc);
+                acc = fma(__hiloint2double(c2.y, c2.x), x2, acc);
+                acc = fma(__hiloint2double(c3.y, c3.x), x3, acc);
+            }
+            for (; k < len; ++k) {
+                const int4 c0 = e[k];
+                acc = fma(__hiloint2double(c0.y, c0.x), __ldg(xr + c0.z), acc);
+            }
+            y[row] = acc;
+            if (dotvec) {
+                dot  = fma(acc, dotvec[row], dot);
+                dot2 = fma(acc, acc, dot2);
+            }
+        }
+    }
+    AB_TILE_EPILOGUE(R)
+}
+
+__device__ __forceinline__ unsigned long long row_code_hash(const uint8_t* __restrict__ code8, int a, int b) {
+    unsigned long long h = 0xCBF29CE484222325ull ^ (unsigned long long)(b - a);
+    for (int j = a; j < b; ++j) { h ^= code8[j]; h *= 0x100000001B3ull; }   // FNV-1a over (len, codes)
+    h ^= h >> 29;
+    return h == VAL_EMPTY ? 0ull : h;
+}
+
+// distinct row hashes + the smallest row carrying each (its representative)
+__global__ void __launch_bounds__(256)
+rowpat_collect_kernel(const int32_t* __restrict__ rowptr, const uint8_t* __restrict__ code8, int64_t m,
+                      unsigned long long* __restrict__ gtable, int* __restrict__ grep, int* __restrict__ gcount) {
+    __shared__ unsigned long long stab[VAL_HASH];
+    __shared__ int srep[VAL_HASH];
+    __shared__ int scount;
+    for (int i = threadIdx.x; i < VAL_HASH; i += 256) { stab[i] = VAL_EMPTY; srep[i] = INT32_MAX; }
+    if (threadIdx.x == 0) scount = 0;
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < m; r += (int64_t)gridDim.x * 256) {
+        if (*(volatile int*)&scount > 256 || *(volatile int*)gcount > 256) break;
+        const int a = rowptr[r], b = rowptr[r + 1];
+        if (b - a > PAT_MAX_LEN) { atomicAdd(&scount, 1000); break; }
+        const unsigned long long key = row_code_hash(code8, a, b);
+        unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 54);
+        bool placed = false;
+        for (int probe = 0; probe < VAL_HASH && !placed; ++probe) {
+            unsigned long long cur = stab[h];
+            if (cur == VAL_EMPTY) {
+                const unsigned long long old = atomicCAS(&stab[h], VAL_EMPTY, key);
+                if (old == VAL_EMPTY) { atomicAdd(&scount, 1); cur = key; } else cur = old;
+            }
+            if (cur == key) { atomicMin(&srep[h], (int)r); placed = true; }
+            h = (h + 1) & (VAL_HASH - 1);
+        }
+        if (!placed) atomicAdd(&scount, 1000);
+    }
+    __syncthreads();
+    if (scount > 256) { if (threadIdx.x == 0) atomicAdd(gcount, 1000); return; }
+    for (int i = threadIdx.x; i < VAL_HASH; i += 256) {
+        const unsigned long long key = stab[i];
+        if (key == VAL_EMPTY) continue;
+        unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> 54);
+        bool placed = false;
+        for (int probe = 0; probe < VAL_HASH && !placed; ++probe) {
+            unsigned long long cur = gtable[h];
+            if (cur == VAL_EMPTY) {
+                const unsigned long long old = atomicCAS(&gtable[h], VAL_EMPTY, key);
+                if (old == VAL_EMPTY) { atomicAdd(gcount, 1); cur = key; } else cur = old;
+            }
+            if (cur == key) { atomicMin(&grep[h], srep[i]); placed = true; }
+            h = (h + 1) & (VAL_HASH - 1);
+        }
+        if (!placed) atomicAdd(gcount, 1000);
+    }
+}
+
+// rowcode[r] = pattern id of row r; every row is compared byte by byte with its pattern (lossless or *bad)
+__global__ void __launch_bounds__(256)
+rowpat_assign_kernel(const int32_t* __restrict__ rowptr, const uint8_t* __restrict__ code8, int64_t m,
+                     const unsigned long long* __restrict__ phash, int npat, const uint32_t* __restrict__ pinfo,
+                     const uint8_t* __restrict__ pcodes, int npcodes, uint8_t* __restrict__ rowcode,
+                     int* __restrict__ bad) {
+    __shared__ unsigned long long s_hash[256];
+    __shared__ uint32_t s_info[256];
+    __shared__ uint8_t s_codes[PAT_MAX_ENT];
+    s_hash[threadIdx.x] = phash[threadIdx.x];
+    s_info[threadIdx.x] = pinfo[threadIdx.x];
+    for (int i = threadIdx.x; i < npcodes; i += 256) s_codes[i] = pcodes[i];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < m; r += (int64_t)gridDim.x * 256) {
+        const int a = rowptr[r], b = rowptr[r + 1];
+        const unsigned long long key = row_code_hash(code8, a, b);
+        int lo = 0, hi = npat - 1;                      // phash is sorted ascending
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_hash[mid] < key) lo = mid + 1; else hi = mid; }
+        const uint32_t info = s_info[lo];
+        bool ok = (s_hash[lo] == key) && ((int)(info >> 16) == b - a);
+        if (ok) {
+            const uint8_t* pc = s_codes + (info & 0xffffu);
+            for (int j = a; j < b; ++j) ok = ok && (pc[j - a] == code8[j]);
+        }
+        if (!ok) atomicExch(bad, 1);
+        rowcode[r] = (uint8_t)lo;
+    }
+}
+
+// npat > 0 afterwards: rowcode/pat_ent/pat_info encode the matrix the pattern codes encode
+static int csr_ensure_rowpat(Csr* c) {
+    if (c->npat >= 0 && c->ncode > 0) return AB_OK;     // csr_ensure_code resets npat when it rebuilds
+    c->npat = 0;
+    if (c->ncode <= 0 || c->m == 0) return AB_OK;
+    DevBuf<unsigned long long> gtab; DevBuf<int> grep, gcount;
+    AB_TRY(gtab.alloc(VAL_HASH)); AB_TRY(grep.alloc(VAL_HASH)); AB_TRY(gcount.alloc(1));
+    AB_CUDA(cudaMemsetAsync(gtab.p, 0xff, VAL_HASH * sizeof(unsigned long long), stream()));
+    std::vector<int> hrep(VAL_HASH, INT32_MAX);
+    AB_CUDA(cudaMemcpyAsync(grep.p, hrep.data(), VAL_HASH * sizeof(int), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemsetAsync(gcount.p, 0, sizeof(int), stream()));
+    int64_t nblk = (c->m + 255) / 256, cap = (int64_t)sm_count() * 8;
+    unsigned grid = (unsigned)(nblk < cap ? nblk : cap);
+    rowpat_collect_kernel<<<grid, 256, 0, stream()>>>(c->rowptr, c->code8, c->m, gtab.p, grep.p, gcount.p);
+    AB_LAUNCH_CHECK();
+    int cnt = 0;
+    std::vector<unsigned long long> hkey(VAL_HASH);
+    AB_CUDA(cudaMemcpyAsync(&cnt, gcount.p, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaMemcpyAsync(hkey.data(), gtab.p, VAL_HASH * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaMemcpyAsync(hrep.data(), grep.p, VAL_HASH * sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    if (cnt > 256 || cnt <= 0) return AB_OK;
+    std::vector<std::pair<unsigned long long, int>> pats;      // (hash, representative row), sorted by hash
+    for (int i = 0; i < VAL_HASH; ++i) if (hkey[i] != VAL_EMPTY) pats.push_back({hkey[i], hrep[i]});
+    if ((int)pats.size() != cnt) return AB_OK;
+    std::sort(pats.begin(), pats.end());
+    CodeEnt htab[256];
+    AB_CUDA(cudaMemcpyAsync(htab, c->codetab, sizeof(htab), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    std::vector<unsigned long long> phash(256, pats.back().first);
+    std::vector<uint32_t> pinfo(256, 0);
+    std::vector<uint8_t> pcodes;
+    std::vector<CodeEnt> pent;
+    for (int p = 0; p < cnt; ++p) {
+        const int r = pats[p].second;
+        int32_t rp[2];
+        AB_CUDA(cudaMemcpy(rp, c->rowptr + r, sizeof(rp), cudaMemcpyDeviceToHost));
+        const int len = rp[1] - rp[0];
+        if (len > PAT_MAX_LEN || (int)pcodes.size() + len > PAT_MAX_ENT) return AB_OK;
+        uint8_t codes[PAT_MAX_LEN];
+        if (len) AB_CUDA(cudaMemcpy(codes, c->code8 + rp[0], (size_t)len, cudaMemcpyDeviceToHost));
+        phash[p] = pats[p].first;
+        pinfo[p] = (uint32_t)pcodes.size() | ((uint32_t)len << 16);
+        for (int k = 0; k < len; ++k) { pcodes.push_back(codes[k]); pent.push_back(htab[codes[k]]); }
+    }
+    for (int p = cnt; p < 256; ++p) pinfo[p] = pinfo[cnt - 1];
+    const int nent = (int)pent.size();
+    DevBuf<unsigned long long> dphash; DevBuf<uint8_t> dpcodes; DevBuf<int> bad;
+    AB_TRY(dphash.alloc(256)); AB_TRY(dpcodes.alloc(nent)); AB_TRY(bad.alloc(1));
+    if (!c->pat_info) AB_TRY(dev_alloc((void**)&c->pat_info, 256 * sizeof(uint32_t)));
+    dev_free(c->pat_ent); c->pat_ent = nullptr;
+    AB_TRY(dev_alloc(&c->pat_ent, (size_t)(nent > 0 ? nent : 1) * sizeof(CodeEnt)));
+    if (!c->rowcode) AB_TRY(dev_alloc((void**)&c->rowcode, (size_t)c->m));
+    AB_CUDA(cudaMemcpyAsync(dphash.p, phash.data(), 256 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemcpyAsync(c->pat_info, pinfo.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream()));
+    if (nent) {
+        AB_CUDA(cudaMemcpyAsync(dpcodes.p, pcodes.data(), (size_t)nent, cudaMemcpyHostToDevice, stream()));
+        AB_CUDA(cudaMemcpyAsync(c->pat_ent, pent.data(), (size_t)nent * sizeof(CodeEnt), cudaMemcpyHostToDevice, stream()));
+    }
+    AB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream()));
+    rowpat_assign_kernel<<<grid, 256, 0, stream()>>>(c->rowptr, c->code8, c->m, dphash.p, cnt, c->pat_info, dpcodes.p, nent,
+                                                    c->rowcode, bad.p);
+    AB_LAUNCH_CHECK();
+    int hbad = 0;
+    AB_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    if (hbad) return AB_OK;                               // a hash collision: keep the per-entry codes
+    c->npat = cnt; c->npat_ent = nent;
     return AB_OK;
 }
 
@@ -572,7 +791,20 @@ static int launch_tile(const Csr* c, const double* vals, const double* x, double
     unsigned cap = (unsigned)(sm_count() * ctas_per_sm);
     if (cap > (unsigned)MAX_REDUCE_GRID) cap = MAX_REDUCE_GRID;
     unsigned grid = ntiles < cap ? ntiles : cap;
-    if (c->ncode > 0 && c->code_src == vals && c->code_version == c->values_version && opt("spmv_code", 1.0) != 0.0)
+    const bool coded = c->ncode > 0 && c->code_src == vals && c->code_version == c->values_version &&
+                       opt("spmv_code", 1.0) != 0.0;
+    if (coded && c->npat > 0 && opt("spmv_rowpat", 1.0) != 0.0) {
+        const size_t smem = (size_t)c->npat_ent * 16 + 1024;
+        static size_t smem_set[3] = {0, 0, 0};
+        const int slot = R == 256 ? 0 : (R == 128 ? 1 : 2);
+        if (smem > 48 * 1024 - 512 && smem > smem_set[slot]) {
+            AB_CUDA(cudaFuncSetAttribute(spmv_rowpat_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            smem_set[slot] = smem;
+        }
+        spmv_rowpat_kernel<R><<<grid, R, smem, stream()>>>(c->rowcode, (const int4*)c->pat_ent, c->npat_ent, c->pat_info, x, y,
+                                                           c->m, ntiles, tile_list, accumulate, dotvec, partials, ticket,
+                                                           dot_result, done_flag);
+    } else if (coded)
         spmv_code_kernel<R, U><<<grid, R, 0, stream()>>>(c->rowptr, c->code8, (const CodeEnt*)c->codetab, x, y, c->m, ntiles,
                                                          tile_list, accumulate, dotvec, partials, ticket, dot_result, done_flag);
     else if (c->noff > 0 && opt("spmv_off8", 1.0) != 0.0)
@@ -603,7 +835,10 @@ int launch_spmv_vals(const Csr* c, const double* vals, const double* x, double* 
         if (c->noff < 0) AB_TRY(csr_ensure_off8(const_cast<Csr*>(c)));   // pattern-only, built once
         // the pattern-code form pays for itself only over many launches: solver value arrays only
         if (vals == c->svalues && vals != nullptr && opt("spmv_code", 1.0) != 0.0)
+        {
             AB_TRY(csr_ensure_code(const_cast<Csr*>(c), vals));
+            if (c->ncode > 0 && c->npat < 0) AB_TRY(csr_ensure_rowpat(const_cast<Csr*>(c)));
+        }
 #define AB_T(RR, UU) launch_tile<RR, UU>(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, cps * (256 / RR), tile_list, nlist, accumulate)
         if (R == 256) return variant == 2 ? AB_T(256, 4) : AB_T(256, 8);
         if (R == 128) return AB_T(128, 8);
@@ -649,6 +884,7 @@ extern "C" int ab_csr_get_info(int64_t h, const char* key, double* value) {
     if (!c) return AB_EHANDLE;
     if (!key || !value) return ab::fail(AB_EINVAL, "null argument");
     if (!strcmp(key, "noff")) *value = c->noff;
+    else if (!strcmp(key, "npat")) *value = (c->code_version == c->values_version && c->ncode > 0) ? c->npat : -1;
     else if (!strcmp(key, "ncode")) *value = (c->code_version == c->values_version) ? c->ncode : -1;
     else if (!strcmp(key, "tile_rows")) *value = ab::spmv_tile_rows(c);
     else if (!strcmp(key, "max_row_nnz")) *value = c->max_row_nnz;

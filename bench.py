@@ -302,12 +302,14 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             info = C.c_double(0)
             lib.ab_csr_get_info(hloc, b"ncode", C.byref(info)); ncode = int(info.value)
             lib.ab_csr_get_info(hloc, b"noff", C.byref(info)); noff = int(info.value)
+            lib.ab_csr_get_info(hloc, b"npat", C.byref(info)); npat = int(info.value)
             # bytes the kernel that actually ran has to move: index+value bytes per stored entry differ by form
-            per_entry = 1 if ncode > 0 else (9 if noff > 0 else 12)
-            kname = ("spmv_code_kernel<256,8> (1-byte {offset,value} pattern codes)" if ncode > 0 else
+            per_entry = 0 if npat > 0 else 1 if ncode > 0 else (9 if noff > 0 else 12)
+            kname = ("spmv_rowpat_kernel<256> (1 byte per ROW names its {offset,value} pattern)" if npat > 0 else
+                     "spmv_code_kernel<256,8> (1-byte {offset,value} pattern codes)" if ncode > 0 else
                      "spmv_tile8_kernel<256,8> (1-byte offset dictionary + fp64 values)" if noff > 0 else
                      "spmv_tile_kernel<256,8> (int32 colind + fp64 values)")
-            streamed = per_entry * nnz_loc + 4.0 * (nloc + 1) + 16.0 * nloc
+            streamed = (17.0 * nloc if npat > 0 else per_entry * nnz_loc + 4.0 * (nloc + 1) + 16.0 * nloc)
             if traffic is not None and json.load(open(tp)).get("bytes_per_entry") != per_entry:
                 traffic = None          # the committed ncu capture is of a different kernel form
             roof = {"bound": "hbm", "kernel": kname + " + fused <p,Ap>,<Ap,Ap>", "achieved": ach, "peak": peak,

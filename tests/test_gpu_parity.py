@@ -643,7 +643,9 @@ def test_pattern_code_spmv_is_lossless(pkg):
         A = pkg.SparseTensor.from_handle(h.value)
         f = torch.rand(N, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(233))
         rr = C.c_double(0)
-        for name, code, off8 in (("code", 1.0, 1.0), ("off8", 0.0, 1.0), ("plain", 0.0, 0.0)):
+        for name, rowpat, code, off8 in (("rowpat", 1.0, 1.0, 1.0), ("code", 0.0, 1.0, 1.0), ("off8", 0.0, 0.0, 1.0),
+                                         ("plain", 0.0, 0.0, 0.0)):
+            pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", rowpat))
             pkg.check(pkg.lib.ab_set_option(b"spmv_code", code))
             pkg.check(pkg.lib.ab_set_option(b"spmv_off8", off8))
             try:
@@ -651,10 +653,17 @@ def test_pattern_code_spmv_is_lossless(pkg):
                 pkg.check(pkg.lib.ab_cg_fixed(A.handle(), f.data_ptr(), u.data_ptr(), 40, C.byref(rr)))
                 outs[name] = (u, rr.value)
             finally:
+                pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", 1.0))
                 pkg.check(pkg.lib.ab_set_option(b"spmv_code", 1.0))
                 pkg.check(pkg.lib.ab_set_option(b"spmv_off8", 1.0))
-        assert torch.equal(outs["code"][0], outs["off8"][0]) and torch.equal(outs["code"][0], outs["plain"][0])
-        assert outs["code"][1] == outs["plain"][1]
+        for name in ("code", "off8", "plain"):
+            assert torch.equal(outs["rowpat"][0], outs[name][0]), name
+        assert outs["rowpat"][1] == outs["plain"][1]
+        info = C.c_double(0)
+        pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"npat", C.byref(info)))
+        assert info.value == 27                # interior + face / edge / corner variants of the 7-point stencil
+        pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"ncode", C.byref(info)))
+        assert info.value == 7
         A.close()
     # variable coefficients: > 256 distinct values -> the dictionary is refused, the solve is unchanged
     rng = np.random.default_rng(233)
