@@ -182,7 +182,8 @@ static __global__ void cg_fin_kernel(SolveScal* s, int which, int parity, double
 // A~ = S A S, x~ = S^-1 x, b~ = S b (same iterates up to rounding).  The preconditioner
 // disappears from the vector kernels: K2 streams 6 vectors instead of 7, K3 3 instead of 4, and
 // one inner product (<r~,r~>) serves both the recurrence and the stopping test:
-//     12*nnz + 4*(N+1) + 11*8*N bytes per iteration instead of ... + 13*8*N.
+//     12*nnz + 4*(N+1) + 11*8*N bytes per iteration instead of ... + 13*8*N;
+// with the x update deferred into K3 (defer_x) K2 streams 3 and K3 5: 10*8*N.
 // The stopping test is on ||r~||/||b~|| (= ||r||/||b|| for a constant diagonal); the caller's
 // guarantee on the TRUE residual comes from the refinement step in solve_dev.
 // ---------------------------------------------------------------------------------------------
@@ -209,11 +210,13 @@ cgs_init_kernel(const double* __restrict__ b, const double* __restrict__ sinv, d
     });
 }
 
-// K2: alpha = rz/pAp ; x += alpha p ; r -= alpha Ap ; rz' = rr = <r,r>
+// K2: alpha = rz/pAp ; r -= alpha Ap ; rz' = rr = <r,r> ; and, unless defer_x, x += alpha p.
+// defer_x != 0 moves the x update into K3, which streams p anyway: K2 then touches 3 vectors and K3 5,
+// i.e. 10 instead of 11 vector passes per iteration (12*nnz-equivalent matrix bytes + 10*8*N).
 static __global__ void __launch_bounds__(EW_THREADS)
 cgs_update_kernel(const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x,
                   double* __restrict__ r, size_t n, int parity, SolveScal* s, double* partials, uint32_t* ticket,
-                  int raw) {
+                  int raw, int defer_x) {
     __shared__ double sh[32];
     if (s->done) return;
     const double rz = s->rz[parity], pAp = s->dots[0];
@@ -225,18 +228,28 @@ cgs_update_kernel(const double* __restrict__ p, const double* __restrict__ Ap, d
     const double2* Ap2 = reinterpret_cast<const double2*>(Ap);
     double2* x2 = reinterpret_cast<double2*>(x);
     double2* r2 = reinterpret_cast<double2*>(r);
-    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
-        double2 pv = p2[i], av = Ap2[i], xv = x2[i], rv = r2[i];
-        xv.x = fma(alpha, pv.x, xv.x);  xv.y = fma(alpha, pv.y, xv.y);
-        rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
-        x2[i] = xv;
-        r2[i] = rv;
-        a0 = fma(rv.x, rv.x, a0); a0 = fma(rv.y, rv.y, a0);
+    if (defer_x) {
+        for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+            double2 av = Ap2[i], rv = r2[i];
+            rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+            r2[i] = rv;
+            a0 = fma(rv.x, rv.x, a0); a0 = fma(rv.y, rv.y, a0);
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+            double2 pv = p2[i], av = Ap2[i], xv = x2[i], rv = r2[i];
+            xv.x = fma(alpha, pv.x, xv.x);  xv.y = fma(alpha, pv.y, xv.y);
+            rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+            x2[i] = xv;
+            r2[i] = rv;
+            a0 = fma(rv.x, rv.x, a0); a0 = fma(rv.y, rv.y, a0);
+        }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         size_t i = n - 1;
-        double xv = fma(alpha, p[i], x[i]), rv = fma(-alpha, Ap[i], r[i]);
-        x[i] = xv; r[i] = rv;
+        double rv = fma(-alpha, Ap[i], r[i]);
+        if (!defer_x) x[i] = fma(alpha, p[i], x[i]);
+        r[i] = rv;
         a0 = fma(rv, rv, a0);
     }
     double mine[2];
@@ -249,24 +262,49 @@ cgs_update_kernel(const double* __restrict__ p, const double* __restrict__ Ap, d
     });
 }
 
-// K3: beta = rz'/rz ; p = r + beta p
+// K3: beta = rz'/rz ; p = r + beta p ; with defer_x also x += alpha p_old (the update K2 left out).
+// `it` is the 0-based iteration this launch belongs to: s->iters == it + 1 says K2 of this iteration
+// really ran (it did not early-exit on `done`), so its x update is still owed even when that same K2
+// detected convergence; launches of later iterations see iters unchanged and do nothing.
 static __global__ void __launch_bounds__(EW_THREADS)
-cgs_direction_kernel(const double* __restrict__ r, double* __restrict__ p, size_t n, int parity,
-                     const SolveScal* __restrict__ s) {
-    if (s->done) return;
-    const double beta = s->rz[parity ^ 1] / s->rz[parity];
+cgs_direction_kernel(const double* __restrict__ r, double* __restrict__ p, double* __restrict__ x, size_t n,
+                     int parity, int it, int defer_x, const SolveScal* __restrict__ s) {
+    const bool upd_x = defer_x && (s->iters == it + 1);
+    const bool upd_p = !s->done;
+    if (!upd_x && !upd_p) return;
+    const double alpha = s->alpha;
+    const double beta = upd_p ? s->rz[parity ^ 1] / s->rz[parity] : 0.0;
     const size_t n2 = n >> 1;
     const double2* r2 = reinterpret_cast<const double2*>(r);
     double2* p2 = reinterpret_cast<double2*>(p);
-    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
-        double2 rv = r2[i], pv = p2[i];
-        pv.x = fma(beta, pv.x, rv.x);
-        pv.y = fma(beta, pv.y, rv.y);
-        p2[i] = pv;
+    double2* x2 = reinterpret_cast<double2*>(x);
+    if (upd_x && upd_p) {
+        for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+            double2 rv = r2[i], pv = p2[i], xv = x2[i];
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            pv.x = fma(beta, pv.x, rv.x);  pv.y = fma(beta, pv.y, rv.y);
+            x2[i] = xv;
+            p2[i] = pv;
+        }
+    } else if (upd_p) {
+        for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+            double2 rv = r2[i], pv = p2[i];
+            pv.x = fma(beta, pv.x, rv.x);
+            pv.y = fma(beta, pv.y, rv.y);
+            p2[i] = pv;
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+            double2 pv = p2[i], xv = x2[i];
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            x2[i] = xv;
+        }
     }
     if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         size_t i = n - 1;
-        p[i] = fma(beta, p[i], r[i]);
+        const double pv = p[i];
+        if (upd_x) x[i] = fma(alpha, pv, x[i]);
+        if (upd_p) p[i] = fma(beta, pv, r[i]);
     }
 }
 

@@ -421,6 +421,7 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
     }
     int check = (int)opt("check_every", 0);
     if (check <= 0) check = 16;
+    const int defer_x = opt("cg_defer_x", 1.0) != 0.0 ? 1 : 0;   // x += alpha p rides in K3 (cg_kernels.cuh)
     int it = 0;
     SolveScal h;
     while (it < maxit) {
@@ -429,7 +430,7 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
             const int parity = it & 1;
             AB_TRY(dist_spmv_dev(d, vals, Ap, p, s->dots, &s->done));
             if (raw) AB_TRY(allreduce2(d, s->dots));
-            if (scaled) cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, raw);
+            if (scaled) cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, raw, defer_x);
             else cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, raw);
             AB_LAUNCH_CHECK();
             if (raw) {
@@ -437,7 +438,7 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
                 cg_fin_kernel<<<1, 1, 0, stream()>>>(s, 1, parity, tol);
                 AB_LAUNCH_CHECK();
             }
-            if (scaled) cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, n, parity, s);
+            if (scaled) cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, it, defer_x, s);
             else cg_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, c->dinv, p, n, parity, s);
             AB_LAUNCH_CHECK();
         }

@@ -264,6 +264,8 @@ static int run_cg_scaled(Csr* c, const double* b, double* x, double tol, int max
     AB_LAUNCH_CHECK();
     int check = (int)opt("check_every", 0);
     if (check <= 0) check = n > (size_t)4000000 ? 16 : 64;
+    // x += alpha p rides in K3 (10 vector passes) unless residual replacement needs x between K2 and K3
+    const int defer_x = (opt("cg_defer_x", 1.0) != 0.0 && opt("replace_every", 0.0) <= 0.0) ? 1 : 0;
     int it = 0;
     SolveScal h;
     while (it < maxit) {
@@ -271,7 +273,7 @@ static int run_cg_scaled(Csr* c, const double* b, double* x, double tol, int max
         for (int k = 0; k < chunk; ++k, ++it) {
             const int parity = it & 1;
             AB_TRY(launch_spmv_vals(c, c->svalues, p, Ap, p, s->dots, c->partials, c->ticket, &s->done, nullptr, 0, 0));
-            cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, 0);
+            cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, 0, defer_x);
             AB_LAUNCH_CHECK();
             if (replace_due(tol, it + 1)) {
                 double* Ax = work_vec(c, 5);
@@ -279,7 +281,7 @@ static int run_cg_scaled(Csr* c, const double* b, double* x, double tol, int max
                 cg_replace_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->sinv, Ax, nullptr, r, n, parity, s, c->partials, c->ticket);
                 AB_LAUNCH_CHECK();
             }
-            cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, n, parity, s);
+            cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, it, defer_x, s);
             AB_LAUNCH_CHECK();
         }
         if (tol < 0 && it < maxit) continue;   // fixed-count run: no polling
@@ -787,6 +789,7 @@ extern "C" int ab_bench_cg_kernels(int64_t h, int reps, double* ms_spmv_dot, dou
     AB_LAUNCH_CHECK();
     // untimed warm-up launch (builds the lazy offset dictionary, loads the kernel image)
     AB_TRY(launch_spmv_vals(c, scaled ? c->svalues : c->values, p, Ap, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0));
+    const int defer_x = (opt("cg_defer_x", 1.0) != 0.0 && opt("replace_every", 0.0) <= 0.0) ? 1 : 0;
     std::vector<cudaEvent_t> ev(4 * (size_t)reps);
     for (auto& e : ev) AB_CUDA(cudaEventCreate(&e));
     for (int it = 0; it < reps; ++it) {
@@ -794,11 +797,11 @@ extern "C" int ab_bench_cg_kernels(int64_t h, int reps, double* ms_spmv_dot, dou
         AB_CUDA(cudaEventRecord(ev[4 * it + 0], stream()));
         AB_TRY(launch_spmv_vals(c, scaled ? c->svalues : c->values, p, Ap, p, s->dots, c->partials, c->ticket, &s->done, nullptr, 0, 0));
         AB_CUDA(cudaEventRecord(ev[4 * it + 1], stream()));
-        if (scaled) cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, 0);
+        if (scaled) cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, 0, defer_x);
         else cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, 0);
         AB_LAUNCH_CHECK();
         AB_CUDA(cudaEventRecord(ev[4 * it + 2], stream()));
-        if (scaled) cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, n, parity, s);
+        if (scaled) cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, it, defer_x, s);
         else cg_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, c->dinv, p, n, parity, s);
         AB_LAUNCH_CHECK();
         AB_CUDA(cudaEventRecord(ev[4 * it + 3], stream()));

@@ -524,7 +524,7 @@ constexpr int PAT_MAX_ENT = 2048;   // total {value, offset} entries over all pa
 constexpr int PAT_MAX_LEN = 255;
 
 template <int R>
-__global__ void __launch_bounds__(R)
+__global__ void __launch_bounds__(R, 2048 / R)
 spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__ pat_ent, int npat_ent,
                    const uint32_t* __restrict__ pat_info, const double* __restrict__ x, double* __restrict__ y,
                    int64_t m, unsigned ntiles, const int32_t* __restrict__ tile_list, int accumulate,
@@ -540,11 +540,27 @@ spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__
     for (int i = t; i < 256; i += R) s_info[i] = pat_info[i];
     __syncthreads();
     double dot = 0.0, dot2 = 0.0;
-    for (unsigned ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
-        const unsigned tile = tile_list ? (unsigned)tile_list[ti] : ti;
-        const int64_t row = (int64_t)tile * R + t;
+    // Each CTA walks a CONTIGUOUS run of tiles: for a grid-ordered stencil the x values gathered at
+    // row+n were (or will be) the centre values of a neighbouring tile of the same CTA, so they are
+    // served by this SM's L1 instead of L2; the next tile's pattern byte is fetched before the current
+    // tile's gathers are issued, which takes one dependent DRAM round trip out of every tile.
+    const unsigned per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const unsigned t_lo = min(blockIdx.x * per, ntiles), t_hi = min(t_lo + per, ntiles);
+    int64_t row_nx = -1;
+    unsigned code_nx = 0;
+    if (t_lo < t_hi) {
+        row_nx = (int64_t)(tile_list ? (unsigned)tile_list[t_lo] : t_lo) * R + t;
+        code_nx = row_nx < m ? rowcode[row_nx] : 0u;
+    }
+    for (unsigned ti = t_lo; ti < t_hi; ++ti) {
+        const int64_t row = row_nx;
+        const unsigned code = code_nx;
+        if (ti + 1 < t_hi) {
+            row_nx = (int64_t)(tile_list ? (unsigned)tile_list[ti + 1] : ti + 1) * R + t;
+            code_nx = row_nx < m ? rowcode[row_nx] : 0u;
+        }
         if (row < m) {
-            const uint32_t info = s_info[rowcode[row]];
+            const uint32_t info = s_info[code];
             const int4* e = s_ent + (info & 0xffffu);
             const int len = (int)(info >> 16);
             const double* xr = x + row;
@@ -797,8 +813,14 @@ static int launch_tile(const Csr* c, const double* vals, const double* x, double
         const size_t smem = (size_t)c->npat_ent * 16 + 1024;
         static size_t smem_set[3] = {0, 0, 0};
         const int slot = R == 256 ? 0 : (R == 128 ? 1 : 2);
-        if (smem > 48 * 1024 - 512 && smem > smem_set[slot]) {
-            AB_CUDA(cudaFuncSetAttribute(spmv_rowpat_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (smem > smem_set[slot]) {
+            if (smem > 48 * 1024 - 512)
+                AB_CUDA(cudaFuncSetAttribute(spmv_rowpat_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // shared memory holds only the pattern table: leave the rest of the 256 KB to L1 (x gathers)
+            const size_t need = (size_t)(2048 / R) * (smem + 1024 + 512);
+            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+            if (pct > 100) pct = 100;
+            AB_CUDA(cudaFuncSetAttribute(spmv_rowpat_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
             smem_set[slot] = smem;
         }
         spmv_rowpat_kernel<R><<<grid, R, smem, stream()>>>(c->rowcode, (const int4*)c->pat_ent, c->npat_ent, c->pat_info, x, y,

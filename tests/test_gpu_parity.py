@@ -658,6 +658,22 @@ def test_pattern_code_spmv_is_lossless(pkg):
                 pkg.check(pkg.lib.ab_set_option(b"spmv_off8", 1.0))
         for name in ("code", "off8", "plain"):
             assert torch.equal(outs["rowpat"][0], outs[name][0]), name
+        # the x update riding in K3 (10 vector passes) is the same arithmetic, only moved
+        pkg.check(pkg.lib.ab_set_option(b"cg_defer_x", 0.0))
+        try:
+            u = torch.empty_like(f)
+            pkg.check(pkg.lib.ab_cg_fixed(A.handle(), f.data_ptr(), u.data_ptr(), 40, C.byref(rr)))
+            assert torch.equal(u, outs["rowpat"][0])
+            it, r2 = C.c_int(0), C.c_double(0)
+            us = []
+            for d in (0.0, 1.0):               # and a converged solve stops with the last update applied
+                pkg.check(pkg.lib.ab_set_option(b"cg_defer_x", d))
+                u = torch.empty_like(f)
+                pkg.check(pkg.lib.ab_solve(A.handle(), b"CG", f.data_ptr(), u.data_ptr(), 1e-9, 4000, C.byref(it), C.byref(r2)))
+                us.append((u, it.value))
+            assert us[0][1] == us[1][1] and torch.equal(us[0][0], us[1][0])
+        finally:
+            pkg.check(pkg.lib.ab_set_option(b"cg_defer_x", 1.0))
         assert outs["rowpat"][1] == outs["plain"][1]
         info = C.c_double(0)
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"npat", C.byref(info)))
