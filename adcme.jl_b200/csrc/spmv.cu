@@ -523,11 +523,21 @@ static int csr_ensure_code(Csr* c, const double* vals) {
 constexpr int PAT_MAX_ENT = 2048;   // total {value, offset} entries over all patterns (32 KB of shared memory)
 constexpr int PAT_MAX_LEN = 255;
 
-template <int R>
-__global__ void __launch_bounds__(R, 2048 / R)
+// Tiles are visited in runs of `run` consecutive tiles per CTA, runs grid-strided: consecutive tiles
+// of a run reuse each other's x lines in this SM's L1 (row+n of one tile is the centre of a later one)
+// while all CTAs together still sweep one compact window of x that stays in L2 (measured: one
+// contiguous chunk per CTA tripled the DRAM traffic — every CTA then drags its own +-n^2 planes).
+// All gathers of a row (up to 8) are issued before the first FMA needs one: one memory latency per
+// row, not one per unrolled remainder; the next tile's pattern byte is fetched a tile ahead.
+// NOTE: no minBlocksPerSM (as for the tile kernels).  Measured at 512^3: __launch_bounds__(R, 8) —
+// same 32 registers — 1.23 ms vs 0.95 ms without; sizing the registers for 6 or 4 CTAs/SM (40 / 64
+// registers, ptxas then batches all 8 gathers) 1.08-1.15 ms; exact-length unrolled bodies behind a
+// switch 1.35 ms.  The kernel is issue/LSU co-bound, not latency-bound: fewer instructions win.
+template <int R, bool LIST>
+__global__ void __launch_bounds__(R)
 spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__ pat_ent, int npat_ent,
                    const uint32_t* __restrict__ pat_info, const double* __restrict__ x, double* __restrict__ y,
-                   int64_t m, unsigned ntiles, const int32_t* __restrict__ tile_list, int accumulate,
+                   unsigned m, unsigned ntiles, unsigned run, const int32_t* __restrict__ tile_list, int accumulate,
                    const double* __restrict__ dotvec, double* partials, uint32_t* ticket, double* dot_result,
                    const int* __restrict__ done) {
     extern __shared__ __align__(16) unsigned char rp_smem[];
@@ -535,28 +545,24 @@ spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__
     uint32_t* s_info = reinterpret_cast<uint32_t*>(rp_smem + (size_t)npat_ent * 16);  // [256]
     __shared__ double s_red[32];
     if (done && *done) return;
-    const int t = threadIdx.x;
+    const unsigned t = threadIdx.x;
     for (int i = t; i < npat_ent; i += R) s_ent[i] = pat_ent[i];
     for (int i = t; i < 256; i += R) s_info[i] = pat_info[i];
     __syncthreads();
     double dot = 0.0, dot2 = 0.0;
-    // Each CTA walks a CONTIGUOUS run of tiles: for a grid-ordered stencil the x values gathered at
-    // row+n were (or will be) the centre values of a neighbouring tile of the same CTA, so they are
-    // served by this SM's L1 instead of L2; the next tile's pattern byte is fetched before the current
-    // tile's gathers are issued, which takes one dependent DRAM round trip out of every tile.
-    const unsigned per = (ntiles + gridDim.x - 1) / gridDim.x;
-    const unsigned t_lo = min(blockIdx.x * per, ntiles), t_hi = min(t_lo + per, ntiles);
-    int64_t row_nx = -1;
-    unsigned code_nx = 0;
-    if (t_lo < t_hi) {
-        row_nx = (int64_t)(tile_list ? (unsigned)tile_list[t_lo] : t_lo) * R + t;
+    const unsigned stride = gridDim.x * run;
+    unsigned ti = blockIdx.x * run, left = run;          // position in the tile sequence, tiles left in this run
+    unsigned row_nx = 0xffffffffu, code_nx = 0;
+    if (ti < ntiles) {
+        row_nx = (LIST ? (unsigned)tile_list[ti] : ti) * R + t;
         code_nx = row_nx < m ? rowcode[row_nx] : 0u;
     }
-    for (unsigned ti = t_lo; ti < t_hi; ++ti) {
-        const int64_t row = row_nx;
-        const unsigned code = code_nx;
-        if (ti + 1 < t_hi) {
-            row_nx = (int64_t)(tile_list ? (unsigned)tile_list[ti + 1] : ti + 1) * R + t;
+    while (ti < ntiles) {
+        const unsigned row = row_nx, code = code_nx;
+        // advance to the next tile of this CTA and fetch its pattern byte now
+        if (--left == 0) { ti += stride - run + 1; left = run; } else ++ti;
+        if (ti < ntiles) {
+            row_nx = (LIST ? (unsigned)tile_list[ti] : ti) * R + t;
             code_nx = row_nx < m ? rowcode[row_nx] : 0u;
         }
         if (row < m) {
@@ -565,18 +571,19 @@ spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__
             const int len = (int)(info >> 16);
             const double* xr = x + row;
             double acc = 0.0;
-            int k = 0;
-            for (; k + 4 <= len; k += 4) {
-                const int4 c0 = e[k], c1 = e[k + 1], c2 = e[k + 2], c3 = e[k + 3];
-                const double x0 = __ldg(xr + c0.z), x1 = __ldg(xr + c1.z), x2 = __ldg(xr + c2.z), x3 = __ldg(xr + c3.z);
-                acc = fma(__hiloint2double(c0.y, c0.x), x0, acc);
-                acc = fma(__hiloint2double(c1.y, c1.x), x1, acc);
-                acc = fma(__hiloint2double(c2.y, c2.x), x2, acc);
-                acc = fma(__hiloint2double(c3.y, c3.x), x3, acc);
-            }
-            for (; k < len; ++k) {
-                const int4 c0 = e[k];
-                acc = fma(__hiloint2double(c0.y, c0.x), __ldg(xr + c0.z), acc);
+            for (int kb = 0; kb < len; kb += 8) {
+                double xv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int k = kb + u < len ? kb + u : kb;          // clamp: a valid (cached) address, product dropped
+                    xv[u] = __ldg(xr + e[k].z);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int4 c = e[kb + u < len ? kb + u : kb];
+                    const double v = __hiloint2double(c.y, c.x);
+                    acc = kb + u < len ? fma(v, xv[u], acc) : acc;
+                }
             }
             y[row] = acc;
             if (dotvec) {
@@ -811,21 +818,28 @@ static int launch_tile(const Csr* c, const double* vals, const double* x, double
                        opt("spmv_code", 1.0) != 0.0;
     if (coded && c->npat > 0 && opt("spmv_rowpat", 1.0) != 0.0) {
         const size_t smem = (size_t)c->npat_ent * 16 + 1024;
-        static size_t smem_set[3] = {0, 0, 0};
-        const int slot = R == 256 ? 0 : (R == 128 ? 1 : 2);
-        if (smem > smem_set[slot]) {
-            if (smem > 48 * 1024 - 512)
-                AB_CUDA(cudaFuncSetAttribute(spmv_rowpat_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            // shared memory holds only the pattern table: leave the rest of the 256 KB to L1 (x gathers)
-            const size_t need = (size_t)(2048 / R) * (smem + 1024 + 512);
-            int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
-            if (pct > 100) pct = 100;
-            AB_CUDA(cudaFuncSetAttribute(spmv_rowpat_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-            smem_set[slot] = smem;
-        }
-        spmv_rowpat_kernel<R><<<grid, R, smem, stream()>>>(c->rowcode, (const int4*)c->pat_ent, c->npat_ent, c->pat_info, x, y,
-                                                           c->m, ntiles, tile_list, accumulate, dotvec, partials, ticket,
-                                                           dot_result, done_flag);
+        unsigned run = (unsigned)opt("spmv_rowpat_run", 4.0);
+        if (run < 1) run = 1;
+        // shared memory holds only the pattern table: leave the rest of the 256 KB to L1 (x gathers)
+        const size_t need = (size_t)(2048 / R) * (smem + 1024 + 512);
+        int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+        if (pct > 100) pct = 100;
+#define AB_ROWPAT(LISTV)                                                                                                    \
+    do {                                                                                                                    \
+        auto kern = spmv_rowpat_kernel<R, LISTV>;                                                                           \
+        static size_t smem_set = 0;                                                                                         \
+        if (smem > smem_set) {                                                                                              \
+            if (smem > 48 * 1024 - 512)                                                                                     \
+                AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+            AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));                       \
+            smem_set = smem;                                                                                                \
+        }                                                                                                                   \
+        kern<<<grid, R, smem, stream()>>>(c->rowcode, (const int4*)c->pat_ent, c->npat_ent, c->pat_info, x, y,              \
+                                          (unsigned)c->m, ntiles, run, tile_list, accumulate, dotvec, partials, ticket,     \
+                                          dot_result, done_flag);                                                           \
+    } while (0)
+        if (tile_list) AB_ROWPAT(true); else AB_ROWPAT(false);
+#undef AB_ROWPAT
     } else if (coded)
         spmv_code_kernel<R, U><<<grid, R, 0, stream()>>>(c->rowptr, c->code8, (const CodeEnt*)c->codetab, x, y, c->m, ntiles,
                                                          tile_list, accumulate, dotvec, partials, ticket, dot_result, done_flag);
