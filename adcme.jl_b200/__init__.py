@@ -17,6 +17,7 @@ from .sparse import (                                           # noqa: F401
 from .structure import (                                        # noqa: F401
     zero_out_row, scatter_update, scatter_add, getindex, add, matmul, spdiag, spzero,
 )
+from .optim import NRResult, backtracking, newton_raphson, newton_raphson_with_grad   # noqa: F401
 from .extra import (                                            # noqa: F401
     load_op, load_op_and_grad, load_system_op, get_library_symbols, libadcme,
 )
@@ -26,5 +27,5 @@ __all__ = [
     "ADCMEError", "SparseTensor", "SparseAssembler", "accumulate", "assemble", "backslash", "compress",
     "factorize", "find", "rows", "cols", "values", "solve", "load_op", "load_op_and_grad", "load_system_op",
     "mpi_init", "mpi_finalize", "mpi_SparseTensor", "options", "zero_out_row", "scatter_update", "scatter_add",
-    "getindex", "spdiag", "spzero",
+    "getindex", "spdiag", "spzero", "newton_raphson", "newton_raphson_with_grad", "NRResult",
 ]

@@ -239,6 +239,17 @@ int ab_csr_axpby(int64_t ha, double alpha, int64_t hb, double beta, int64_t* out
  * Each C(i,j) is summed in k-ascending order (Eigen's column-major product order). */
 int ab_spgemm(int64_t ha, int64_t hb, int transpose_out, int64_t* out_h);
 
+/* ---- Newton-Raphson inner loop on the device — csrc/newton.cu ----------
+ * src/optim.jl:462-592 (newton_raphson), :364-426 (backtracking).  The residual/Jacobian callback
+ * stays in the host language; the linear solve, the update u - step*delta, ||r|| and the
+ * line-search reductions run here on device-resident vectors.
+ * ab_newton_step: delta = J \ r with any `\` method (J = handle h, LM shift already added by the
+ * caller as J + mu*I); u_new = u - step*delta (may alias u); *rnorm = ||r||_2.  delta may be NULL. */
+int ab_newton_step(int64_t h, const char* method, const double* r, const double* u, double step,
+                   double* u_new, double* delta, double* rnorm, double tol, int maxit, int* lin_iters);
+int ab_vec_axpby(int64_t n, double a, const double* x, double b, const double* y, double* out); /* a*x+b*y */
+int ab_vec_dot(int64_t n, const double* x, const double* y, double* result);   /* fixed-order reduction */
+
 /* ---- row-block distributed CSR + solve (a12) --------------------------
  * Replaces mpi_SparseTensor `\` (src/mpi.jl:420-508; MPITensor.h:103-152):
  * one process per GPU, rank r owns rows [ilower, iupper] (Hypre IJ layout,

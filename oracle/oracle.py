@@ -337,6 +337,50 @@ def sparse_diag_mat_mul(ii1, jj1, vv1, vv2, m, k):
     return _colmajor_from_triplets(ii1, jj1, _f64(vv1) * _f64(vv2)[jj1], m, k)
 
 
+# ---------------------------------------------------------------- Newton-Raphson
+def newton_raphson(func, u0, theta=None, max_iter=100, tol=1e-12, rtol=1e-12, LM=0.0):
+    """Restatement of the newton_raphson while-loop (src/optim.jl:462-592) with a direct solve
+    (scipy SuperLU standing in for Eigen SparseLU).  func(theta, u) -> (r, J) with J a scipy sparse
+    matrix.  Returns (x, res, U, converged, iter) exactly as NRResult is filled (optim.jl:560-591):
+    ta_r[i] holds ||r(u_{i-2})||, the loop continues while ta_r[i-1] >= tol and ta_r[i-2] >= rtol and
+    i <= max_iter, the answer is ta_u[i_-1]."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    u = _f64(u0).copy()
+    r0, _ = func(theta, u)
+    tol0 = float(np.linalg.norm(r0))
+    ta_r, ta_u, i = {1: tol0}, {1: u}, 2
+    while True:
+        cont = (i < max_iter + 1) if i == 2 else (ta_r[i - 1] >= tol and ta_r[i - 2] >= rtol and i <= max_iter)
+        if not cont:
+            break
+        u_ = ta_u[i - 1]
+        r_, J = func(theta, u_)
+        J = sp.csc_matrix(J)
+        if LM > 0.0:
+            J = J + LM * sp.identity(J.shape[0], format="csc")       # optim.jl:520-524
+        delta = spla.splu(J).solve(_f64(r_))
+        ta_r[i] = float(np.linalg.norm(r_))
+        ta_u[i] = u_ - delta
+        i += 1
+    if tol0 < tol:
+        return u, np.array([tol0]), u.reshape(-1, 1), i < max_iter, 1
+    res = np.array([ta_r[k] for k in range(2, i)])
+    U = np.stack([ta_u[k] for k in range(1, i - 1)], axis=1)
+    return ta_u[i - 1], res, U, i < max_iter, i - 2
+
+
+def newton_adjoint_grad(func_r_theta_jac, A, dy):
+    """newton_raphson_with_grad backward (optim.jl:628-638): g = A'^-1 dy ; grad_theta = -(dr/dtheta)' g.
+    `func_r_theta_jac` is the dense/sparse Jacobian of r with respect to theta at the solution."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    g = spla.splu(sp.csc_matrix(A).T.tocsc()).solve(_f64(dy))
+    return -(func_r_theta_jac.T @ g)
+
+
 # ---------------------------------------------------------------- Poisson generators
 def poisson2d_matrix(n: int, kext):
     """GetPoissonMatrixForward (GetPoissonMatrix.h:15-51), single-rank colext."""

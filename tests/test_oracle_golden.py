@@ -240,3 +240,23 @@ def test_spgemm_oracle_vs_scipy(orc):
     assert np.allclose(_dense_from_triplets(I, J, V, 5, 20), (sp.diags(d) @ B).toarray(), rtol=1e-15, atol=0)
     I, J, V = orc.sparse_diag_mat_mul(A.row, A.col, A.data, d, 10, 5)
     assert np.allclose(_dense_from_triplets(I, J, V, 10, 5), (A @ sp.diags(d)).toarray(), rtol=1e-15, atol=0)
+
+
+# ======================================================================== Newton-Raphson (N3)
+def test_newton_oracle_golden(orc, golden):
+    g = golden["newton_cuberoot_adjoint"]                      # test/optim.jl:235-249
+    theta = np.array(g["theta"], float)
+
+    def f(th, x):
+        return x ** 3 - th, sp.diags(3 * x ** 2)
+
+    x, res, U, conv, it = orc.newton_raphson(f, np.ones(3), theta)
+    assert np.allclose(x, g["expect_x"], rtol=1e-12) and conv and it == len(res) == U.shape[1]
+    assert res[-1] < 1e-12 <= res[-2]                         # stops one step after the residual passed tol
+    grad = orc.newton_adjoint_grad(-sp.identity(3), sp.diags(3 * x ** 2), np.ones(3))
+    assert np.allclose(grad, g["expect_grad"], rtol=1e-12)
+    r = golden["register_newton_gradient"]                    # test/extra.jl:28-49: y^3 + 1 - θ - x = 0, x = 8, θ = 1
+    y, *_ = orc.newton_raphson(lambda th, y: (y ** 3 + 1.0 - th - 8.0, sp.diags(3 * y ** 2)), np.ones(5), np.ones(5))
+    assert np.allclose(y, 2.0, rtol=1e-12)
+    gth = orc.newton_adjoint_grad(-sp.identity(5), sp.diags(3 * y ** 2), np.ones(5))
+    assert np.allclose(gth, r["expect_grad_each"], rtol=1e-12)
