@@ -95,6 +95,7 @@ SIGNATURES = {
     "ab_bench_spmv": (C.c_int, [_i64, _ptr, _ptr, C.c_int, C.c_int, _ptr]),
     "ab_bench_cg_kernels": (C.c_int, [_i64, C.c_int, _ptr, _ptr, _ptr]),
     "ab_launch_count": (_i64, []),
+    "ab_spmv_solver_form": (C.c_int, [_i64, _ptr, _ptr]),
     "ab_csr_get_info": (C.c_int, [_i64, _str, _ptr]),
 }
 

@@ -757,6 +757,26 @@ int ab_factorized_solve_grad(int64_t id, const double* grad_out, const double* o
 
 }  // extern "C"
 
+// ---- test hook: y = (S A S) x through exactly the SpMV form the CG solver would use for this handle
+// (row-pattern / pattern-code / offset-dictionary / int32), without the fused dots.  Lets the parity
+// tests check that every compressed form reproduces the plain kernel bit for bit.
+extern "C" int ab_spmv_solver_form(int64_t h, const double* x_, double* y_) {
+    AB_TRY(ensure_device());
+    Csr* c = csr_get(h);
+    if (!c) return AB_EHANDLE;
+    if (c->m != c->n) return fail(AB_EINVAL, "square matrix required");
+    if (c->m > 0 && (!x_ || !y_)) return fail(AB_EINVAL, "null vector");
+    std::lock_guard<std::mutex> lk(big_lock());
+    AB_TRY(csr_ensure_scaled(c));
+    if (!c->scaled_ok) return fail(AB_EUNSUPPORTED, "the matrix has no positive diagonal: CG would not use the scaled form");
+    In<double> x; Out<double> y;
+    AB_TRY(x.bind(x_, c->n)); AB_TRY(y.bind(y_, c->m));
+    AB_TRY(launch_spmv_vals(c, c->svalues, x.d, y.d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0));
+    AB_TRY(y.commit());
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    return AB_OK;
+}
+
 // ---- measurement hook: per-kernel durations of the CG iteration (bench.py roofline) ----------
 namespace ab {
 __global__ void fill_kernel(double* p, size_t n, double v) {

@@ -523,6 +523,24 @@ static int csr_ensure_code(Csr* c, const double* vals) {
 constexpr int PAT_MAX_ENT = 2048;   // total {value, offset} entries over all patterns (32 KB of shared memory)
 constexpr int PAT_MAX_LEN = 255;
 
+// x[row + off] through ONE integer instruction for the address (IMAD.WIDE off*8 + xr); left to itself
+// the compiler re-associates to x + (row + off) and spends four (IADD3, LEA.HI.X.SX32, LEA, LEA.HI.X).
+__device__ __forceinline__ double rowpat_gather(const double* xr, int off) {
+    const double* p;
+    asm("mad.wide.s32 %0, %1, 8, %2;" : "=l"(p) : "r"(off), "l"(xr));
+    return __ldg(p);
+}
+// L consecutive pattern entries: L gathers, then L FMAs in stored order.  No predicates, no clamping.
+template <int L>
+__device__ __forceinline__ double rowpat_chunk(const int4* __restrict__ e, const double* xr, double acc) {
+    double xv[L];
+#pragma unroll
+    for (int u = 0; u < L; ++u) xv[u] = rowpat_gather(xr, e[u].z);
+#pragma unroll
+    for (int u = 0; u < L; ++u) acc = fma(*reinterpret_cast<const double*>(e + u), xv[u], acc);
+    return acc;
+}
+
 // Tiles are visited in runs of `run` consecutive tiles per CTA, runs grid-strided: consecutive tiles
 // of a run reuse each other's x lines in this SM's L1 (row+n of one tile is the centre of a later one)
 // while all CTAs together still sweep one compact window of x that stays in L2 (measured: one
@@ -571,20 +589,10 @@ spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__
             const int len = (int)(info >> 16);
             const double* xr = x + row;
             double acc = 0.0;
-            for (int kb = 0; kb < len; kb += 8) {
-                double xv[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int k = kb + u < len ? kb + u : kb;          // clamp: a valid (cached) address, product dropped
-                    xv[u] = __ldg(xr + e[k].z);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int4 c = e[kb + u < len ? kb + u : kb];
-                    const double v = __hiloint2double(c.y, c.x);
-                    acc = kb + u < len ? fma(v, xv[u], acc) : acc;
-                }
-            }
+            int k = 0;
+            for (; k + 4 <= len; k += 4) acc = rowpat_chunk<4>(e + k, xr, acc);     // branches are warp-uniform
+            if (len & 2) { acc = rowpat_chunk<2>(e + k, xr, acc); k += 2; }         // wherever the warp's rows
+            if (len & 1) acc = rowpat_chunk<1>(e + k, xr, acc);                     // share a pattern
             y[row] = acc;
             if (dotvec) {
                 dot  = fma(acc, dotvec[row], dot);

@@ -282,6 +282,9 @@ int ab_bench_spmv(int64_t h, const double* x, double* y, int reps, int with_dot,
 int ab_bench_cg_kernels(int64_t h, int reps, double* ms_spmv_dot, double* ms_update,
                         double* ms_direction);
 int64_t ab_launch_count(void);   /* kernels launched by this library since ab_init */
+/* test hook: y = (S A S) x, S = diag(A)^-1/2, through exactly the SpMV form (row-pattern / pattern-code /
+ * offset-dictionary / int32) the CG solver uses for this handle, without the fused inner products */
+int ab_spmv_solver_form(int64_t h, const double* x, double* y);
 /* which SpMV form a handle currently uses: "noff" (offset-dictionary size, 0 = int32 colind),
  * "ncode" (pattern-code dictionary size of the solver values, 0 = none), "tile_rows",
  * "max_row_nnz", "scaled" (1 when CG runs on the symmetrically scaled copy) */

@@ -630,51 +630,72 @@ def test_c3_cg_solve_converges_128cubed(pkg):
 
 
 def test_pattern_code_spmv_is_lossless(pkg):
-    """The solver's pattern-code SpMV (1 byte per entry naming an {offset, value} pair) must give the
-    same bits as the offset-dictionary and plain kernels, and must step aside by itself when the
-    values do not admit a 256-entry dictionary (variable coefficients)."""
+    """The solver's compressed SpMV forms — row patterns (1 byte per row), pattern codes (1 byte per
+    entry naming an {offset, value} pair), offset dictionary — must reproduce the plain int32 kernel
+    BIT FOR BIT on y = (S A S) x, and must step aside by themselves when the values do not admit a
+    256-entry dictionary (variable coefficients).  CG iterates of the different forms agree to rounding
+    only (the fused inner products are summed in each kernel's own fixed tile order); every form is
+    run-to-run deterministic."""
     import torch
 
-    outs = {}
+    forms = (("rowpat", 1.0, 1.0, 1.0), ("code", 0.0, 1.0, 1.0), ("off8", 0.0, 0.0, 1.0), ("plain", 0.0, 0.0, 0.0))
+
+    def with_form(rowpat, code, off8, fn):
+        pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", rowpat))
+        pkg.check(pkg.lib.ab_set_option(b"spmv_code", code))
+        pkg.check(pkg.lib.ab_set_option(b"spmv_off8", off8))
+        try:
+            return fn()
+        finally:
+            pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", 1.0))
+            pkg.check(pkg.lib.ab_set_option(b"spmv_code", 1.0))
+            pkg.check(pkg.lib.ab_set_option(b"spmv_off8", 1.0))
+
     for n in (48, 67):                         # 67: tiles straddle planes, odd sizes
         N = n ** 3
         h = C.c_int64(0)
         pkg.check(pkg.lib.ab_poisson3d_csr(n, n, n, 0, N, C.byref(h)))
         A = pkg.SparseTensor.from_handle(h.value)
-        f = torch.rand(N, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(233))
+        gen = torch.Generator(device="cuda").manual_seed(233)
+        f = torch.rand(N, dtype=torch.float64, device="cuda", generator=gen)
+        x = torch.randn(N, dtype=torch.float64, device="cuda", generator=gen)
         rr = C.c_double(0)
-        for name, rowpat, code, off8 in (("rowpat", 1.0, 1.0, 1.0), ("code", 0.0, 1.0, 1.0), ("off8", 0.0, 0.0, 1.0),
-                                         ("plain", 0.0, 0.0, 0.0)):
-            pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", rowpat))
-            pkg.check(pkg.lib.ab_set_option(b"spmv_code", code))
-            pkg.check(pkg.lib.ab_set_option(b"spmv_off8", off8))
-            try:
-                u = torch.empty_like(f)
-                pkg.check(pkg.lib.ab_cg_fixed(A.handle(), f.data_ptr(), u.data_ptr(), 40, C.byref(rr)))
-                outs[name] = (u, rr.value)
-            finally:
-                pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", 1.0))
-                pkg.check(pkg.lib.ab_set_option(b"spmv_code", 1.0))
-                pkg.check(pkg.lib.ab_set_option(b"spmv_off8", 1.0))
-        for name in ("code", "off8", "plain"):
-            assert torch.equal(outs["rowpat"][0], outs[name][0]), name
+
+        def spmv():
+            y = torch.empty_like(x)
+            pkg.check(pkg.lib.ab_spmv_solver_form(A.handle(), x.data_ptr(), y.data_ptr()))
+            return y
+
+        def cg():
+            u = torch.empty_like(f)
+            pkg.check(pkg.lib.ab_cg_fixed(A.handle(), f.data_ptr(), u.data_ptr(), 40, C.byref(rr)))
+            return u
+
+        ys = {name: with_form(a, b, c, spmv) for name, a, b, c in forms}
+        for name in ("rowpat", "code", "off8"):
+            assert torch.equal(ys[name], ys["plain"]), name                      # lossless: same bits
+        S = A.to_scipy()
+        dinv = 1.0 / np.sqrt(S.diagonal())
+        y0 = dinv * (S @ (dinv * x.cpu().numpy()))
+        assert np.max(np.abs(ys["plain"].cpu().numpy() - y0)) <= 1e-13 * np.max(np.abs(y0))
+        us = {name: with_form(a, b, c, cg) for name, a, b, c in forms}
+        for name in ("rowpat", "code", "off8"):
+            assert float((us[name] - us["plain"]).abs().max() / us["plain"].abs().max()) <= 1e-11, name
+        assert torch.equal(with_form(1.0, 1.0, 1.0, cg), us["rowpat"])          # deterministic run to run
         # the x update riding in K3 (10 vector passes) is the same arithmetic, only moved
         pkg.check(pkg.lib.ab_set_option(b"cg_defer_x", 0.0))
         try:
-            u = torch.empty_like(f)
-            pkg.check(pkg.lib.ab_cg_fixed(A.handle(), f.data_ptr(), u.data_ptr(), 40, C.byref(rr)))
-            assert torch.equal(u, outs["rowpat"][0])
+            assert torch.equal(cg(), us["rowpat"])
             it, r2 = C.c_int(0), C.c_double(0)
-            us = []
+            sols = []
             for d in (0.0, 1.0):               # and a converged solve stops with the last update applied
                 pkg.check(pkg.lib.ab_set_option(b"cg_defer_x", d))
                 u = torch.empty_like(f)
                 pkg.check(pkg.lib.ab_solve(A.handle(), b"CG", f.data_ptr(), u.data_ptr(), 1e-9, 4000, C.byref(it), C.byref(r2)))
-                us.append((u, it.value))
-            assert us[0][1] == us[1][1] and torch.equal(us[0][0], us[1][0])
+                sols.append((u, it.value))
+            assert sols[0][1] == sols[1][1] and torch.equal(sols[0][0], sols[1][0])
         finally:
             pkg.check(pkg.lib.ab_set_option(b"cg_defer_x", 1.0))
-        assert outs["rowpat"][1] == outs["plain"][1]
         info = C.c_double(0)
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"npat", C.byref(info)))
         assert info.value == 27                # interior + face / edge / corner variants of the 7-point stencil
