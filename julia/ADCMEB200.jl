@@ -10,7 +10,8 @@ module ADCMEB200
 
 using SparseArrays
 export B200SparseTensor, b200_spmm, b200_solve, b200_solve_grad, B200Assembler, b200_accumulate!,
-       b200_assemble, b200_compress, b200_factorize, b200_fsolve
+       b200_assemble, b200_compress, b200_factorize, b200_fsolve, b200_zero_out_row, b200_scatter_update,
+       b200_getindex, b200_spgemm, b200_add, b200_newton_step
 
 const LIB = get(ENV, "ADCME_B200_LIB", joinpath(@__DIR__, "..", "adcme.jl_b200", "libadcme_b200.so"))
 
@@ -145,6 +146,67 @@ function b200_fsolve(id::Int64, rhs::Vector{Float64})
     out = similar(rhs)
     chk(ccall((:ab_factorized_solve, LIB), Cint, (Int64, Ptr{Cdouble}, Int64, Ptr{Cdouble}), id, rhs, length(rhs), out))
     out
+end
+
+# ---- structural ops between assembly and solve (SURVEY §8f N2/N4) — csrc/structure.cu ---------------
+# Variable-length triplet results come back through a triplet handle: size -> allocate -> fetch.
+function fetch_trip(th::Int64)
+    k = ccall((:ab_trip_size, LIB), Int64, (Int64,), th)
+    k < 0 && chk(Cint(k))
+    ii, jj, vv = Vector{Int64}(undef, k), Vector{Int64}(undef, k), Vector{Float64}(undef, k)
+    chk(ccall((:ab_trip_fetch, LIB), Cint, (Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}), th, ii, jj, vv))
+    ii, jj, vv
+end
+
+"zero_out_row(A, bd) — src/sparse.jl:790-797.  `indices` is the 0-based [N,2] matrix of the tf.SparseTensor."
+function b200_zero_out_row(indices::Array{Int64,2}, vv::Vector{Float64}, bd::Vector{Int64})
+    idx = permutedims(indices); th = Ref{Int64}(0)
+    chk(ccall((:ab_zero_out_row, LIB), Cint, (Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}, Int64, Ref{Int64}),
+              length(vv), idx, vv, bd, length(bd), th))
+    ii, jj, ov = fetch_trip(th[])
+    hcat(ii, jj), ov
+end
+
+"scatter_update(A, i1, i2, B) — src/sparse.jl:340-364 (all 1-based; (uii,ujj) are positions inside the block)."
+function b200_scatter_update(oii, ojj, ovv, m, n, uii, ujj, uvv, ii::Vector{Int64}, jj::Vector{Int64})
+    th = Ref{Int64}(0)
+    chk(ccall((:ab_scatter_update, LIB), Cint,
+              (Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}, Int64, Int64,
+               Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ref{Int64}),
+              length(ovv), oii, ojj, ovv, length(uvv), uii, ujj, uvv, m, n, ii, length(ii), jj, length(jj), th))
+    fetch_trip(th[])
+end
+
+"A[i1, i2] — src/sparse.jl:303-327: 1-based triplets of the sub-block, in the reference op's order."
+function b200_getindex(s::B200SparseTensor, ii::Vector{Int64}, jj::Vector{Int64})
+    th = Ref{Int64}(0)
+    chk(ccall((:ab_sparse_indexing, LIB), Cint, (Int64, Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ref{Int64}),
+              s.h, ii, length(ii), jj, length(jj), th))
+    fetch_trip(th[])
+end
+
+"SparseTensor * SparseTensor — src/sparse.jl:579-595; returns the handle of C = A*B (kept on the device)."
+function b200_spgemm(a::B200SparseTensor, b::B200SparseTensor)
+    h = Ref{Int64}(0)
+    chk(ccall((:ab_spgemm, LIB), Cint, (Int64, Int64, Cint, Ref{Int64}), a.h, b.h, 0, h))
+    h[]
+end
+
+"A + B (tf.sparse.add, src/sparse.jl:217): handle of alpha*A + beta*B on the union pattern."
+function b200_add(a::B200SparseTensor, b::B200SparseTensor, alpha::Real=1.0, beta::Real=1.0)
+    h = Ref{Int64}(0)
+    chk(ccall((:ab_csr_axpby, LIB), Cint, (Int64, Cdouble, Int64, Cdouble, Ref{Int64}), a.h, alpha, b.h, beta, h))
+    h[]
+end
+
+# ---- Newton-Raphson inner loop (SURVEY §8f N3) — csrc/newton.cu; src/optim.jl:509-539 --------------
+"δ = J \\ r ; u_new = u - step*δ ; returns (u_new, δ, ‖r‖).  The residual/Jacobian callback stays in Julia."
+function b200_newton_step(J::B200SparseTensor, r::Vector{Float64}, u::Vector{Float64}; step::Real=1.0, method::String="SparseLU")
+    unew, delta, rn = similar(u), similar(u), Ref{Cdouble}(0.0)
+    chk(ccall((:ab_newton_step, LIB), Cint,
+              (Int64, Cstring, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Cdouble, Cint, Ptr{Cint}),
+              J.h, method, r, u, step, unew, delta, rn, 0.0, 0, C_NULL))
+    unew, delta, rn[]
 end
 
 end # module
