@@ -376,6 +376,68 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+def cpu_config_samples(path: str):
+    """cpu_baseline leg for BASELINE.json's secondary configs (C2 assembly + SpMV, C4 direct solve, C5
+    SpMM): the oracle / scipy timed on this box's host cores on BOUNDED samples of the same workloads.
+    Single-threaded like the reference ops (Eigen setFromTriplets / SparseLU and the TF sparse matmul
+    CPU functor do not shard).  Writes one JSON object; rank 0 only, no GPU needed."""
+    import numpy as np
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+
+    import __graft_entry__ as ge
+
+    orc = ge.load_oracle()
+    out = {"cores": 1, "kind": "port", "host_threads_available": os.cpu_count()}
+
+    def best(fn, reps=2):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter(); r = fn(); ts.append(time.perf_counter() - t0)
+        return min(ts), r
+
+    n = 96                                                     # C2 sample: 96^3 face-wise stream
+    ii, jj, vv = orc.facewise_triplets_3d(n, seed=233)
+    N = n ** 3
+    t_asm, (rp, ci, va, _) = best(lambda: orc.coo_to_csr(ii, jj, vv, N, N, base=1))
+    x = np.random.default_rng(233).uniform(-1, 1, N)
+    t_spmv, _ = best(lambda: orc.csr_spmm(rp, ci, va, x), reps=3)
+    out["c2"] = {"sample": f"{n}^3 face-wise stream, {len(vv)} triplets -> nnz {len(va)} (config: 256^3)",
+                 "assembly_s": t_asm, "assembly_Mtriplets_per_s": len(vv) / t_asm / 1e6,
+                 "spmv_s": t_spmv, "spmv_GBps": (12.0 * len(va) + 4.0 * (N + 1) + 16.0 * N) / t_spmv / 1e9}
+    m = 512                                                    # C4 sample: the reference's direct solve on 512^2
+    h_ = 1.0 / (m + 1)
+    xs = np.arange(m + 2) * h_
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    kext = 1 + X ** 2 + Y ** 2
+    cols, val, ncols = orc.poisson2d_matrix(m, kext)
+    rowptr = np.concatenate([[0], np.cumsum(ncols)])
+    A = -sp.csr_matrix((val, cols, rowptr), shape=(m * m, m * m))
+    f = np.random.default_rng(233).uniform(size=m * m)
+    t_fac, lu = best(lambda: spla.splu(A.tocsc()), reps=1)
+    t_sol, u = best(lambda: lu.solve(f), reps=2)
+    t_adj, _ = best(lambda: spla.splu(A.T.tocsc()).solve(u), reps=1)     # SparseSolverGrad refactorises A' (SparseSolver.h:46-70)
+    out["c4"] = {"sample": f"{m}^2 variable-coefficient 5-point system, SuperLU direct solve (config: 4096^2 = 64x the unknowns)",
+                 "factorize_s": t_fac, "solve_s": t_sol, "adjoint_factorize_and_solve_s": t_adj,
+                 "relres": float(np.linalg.norm(A @ u - f) / np.linalg.norm(f))}
+    rows, k = 1_000_000, 32                                    # C5 sample: 1 M power-law rows
+    rng = np.random.default_rng(233)
+    deg = np.clip(np.floor(np.clip(rng.uniform(size=rows), 1e-12, None) ** (-1.0 / 1.1)), 1, 1e5)
+    deg = np.clip(np.round(deg * (16 / deg.mean())), 1, 1e5).astype(np.int64)
+    rp5 = np.concatenate([[0], np.cumsum(deg)])
+    nnz5 = int(rp5[-1])
+    idx2 = np.stack([np.repeat(np.arange(rows), deg), rng.integers(0, rows, nnz5)], axis=1).astype(np.int64)
+    v5 = rng.uniform(-1, 1, nnz5)
+    X5 = rng.uniform(-1, 1, (rows, k))
+    t_spmm, Y5 = best(lambda: orc.spmm_coo(idx2, v5, rows, X5), reps=2)
+    t_sddmm, _ = best(lambda: orc.spmm_grad_values(idx2, Y5, X5), reps=2)
+    out["c5"] = {"sample": f"{rows} power-law rows, nnz {nnz5}, k = {k} (config: 50 M rows)",
+                 "spmm_s": t_spmm, "spmm_Mnnz_per_s": nnz5 / t_spmm / 1e6,
+                 "value_grad_s": t_sddmm, "value_grad_Mnnz_per_s": nnz5 / t_sddmm / 1e6}
+    json.dump(out, open(path, "w"), indent=1)
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -384,7 +446,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", type=int, default=512, help="grid edge n of the n^3 Poisson system (BASELINE: 512)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-configs", metavar="OUT.json", default=None,
+                    help="cpu_baseline leg of the secondary configs (C2/C4/C5 bounded samples); writes OUT.json and exits")
     args = ap.parse_args()
+    if args.cpu_configs:
+        if int(os.environ.get("RANK", 0)) == 0:
+            cpu_config_samples(args.cpu_configs)
+        return
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))

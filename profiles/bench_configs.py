@@ -142,7 +142,7 @@ def c4(n=4096):
     pkg.check(lib.ab_solve(h.value, b"CG", f.data_ptr(), u.data_ptr(), 1e-10, 200000, C.byref(it), C.byref(rr)))
     torch.cuda.synchronize(); t_f = time.perf_counter() - t0
     res = float(((A @ u) - f).norm() / f.norm())
-    ib = 12.0 * nnz + 4.0 * (N + 1) + 13.0 * 8.0 * N
+    ib = 12.0 * nnz + 4.0 * (N + 1) + 13.0 * 8.0 * N          # SURVEY §8d algorithmic bytes per PCG iteration
     out["forward"] = {"iters": it.value, "relres": rr.value, "true_relres": res, "seconds": t_f, "iters_per_s": it.value / t_f,
                       "GBps": ib * it.value / t_f / 1e9, "frac_of_peak": ib * it.value / t_f / 1e9 / PEAK}
     uex = (Xi * (1 - Xi) * Yi * (1 - Yi)).reshape(-1)
@@ -205,8 +205,10 @@ def c5(rows=50_000_000, mean=16, k=32):
     e = torch.randint(0, nnz, (1000,), device=dev, generator=g)
     rows_of = torch.searchsorted(rp64, e, right=True) - 1
     ref = (Y[rows_of] * X[colind[e].long()]).sum(1)
+    gath2 = 4.0 * nnz + 4.0 * (rows + 1) + 8.0 * k * (nnz + rows) + 8.0 * nnz     # X row per entry, dY row once per row
     out["sddmm"] = {"ms": ms2, "GBps_compulsory": comp / ms2 / 1e6, "frac_compulsory": comp / ms2 / 1e6 / PEAK,
-                    "GBps_gather_model": (12.0 * nnz + 8.0 * k * 2 * nnz) / ms2 / 1e6,
+                    "no_reuse_gather_GB": gath2 / 1e9, "GBps_gather_model": gath2 / ms2 / 1e6,
+                    "frac_gather_model": gath2 / ms2 / 1e6 / PEAK,
                     "max_rel_err_sampled": float(((dv[e] - ref).abs() / (ref.abs() + 1e-300)).max())}
     pkg.check(lib.ab_csr_destroy(h.value))
     return out
