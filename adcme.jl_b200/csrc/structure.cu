@@ -320,6 +320,31 @@ __global__ void coo_scale_kernel(const int64_t* __restrict__ idx, const double* 
     if (k < 0 || k >= nd) { atomicExch(err, 1); out[t] = 0.0; return; }
     out[t] = vv[t] * d[k];
 }
+// [ii1; ii2 + di], [jj1; jj2 + dj], [vv1; vv2]   (SparseConcate.h:11-27)
+__global__ void concat_kernel(const int64_t* __restrict__ i1, const int64_t* __restrict__ j1, const double* __restrict__ v1,
+                              size_t n1, const int64_t* __restrict__ i2, const int64_t* __restrict__ j2,
+                              const double* __restrict__ v2, size_t n2, int64_t di, int64_t dj,
+                              int64_t* __restrict__ oi, int64_t* __restrict__ oj, double* __restrict__ ov) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n1) { oi[k] = i1[k]; oj[k] = j1[k]; ov[k] = v1[k]; }
+    else if (k < n1 + n2) { const size_t q = k - n1; oi[k] = i2[q] + di; oj[k] = j2[q] + dj; ov[k] = v2[q]; }
+}
+// dense[row, col] = value for every stored entry (duplicates were summed at assembly; SparseToDense.h:1-6)
+__global__ void csr_to_dense_kernel(const int32_t* __restrict__ entry_row, const int32_t* __restrict__ colind,
+                                    const double* __restrict__ values, size_t nnz, int64_t n, double* __restrict__ out) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nnz) out[(size_t)entry_row[e] * (size_t)n + (size_t)colind[e]] = values[e];
+}
+// per-input-triplet gradient of the dense form: grad_v[t] = grad_out[row_t, col_t]  (SparseToDense.h:8-12)
+__global__ void dense_grad_kernel(const int64_t* __restrict__ idx2, size_t T, int64_t m, int64_t n,
+                                  const double* __restrict__ grad_out, double* __restrict__ grad_v, int* __restrict__ err) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int64_t r = idx2[2 * t], c = idx2[2 * t + 1];
+    if (r < 0 || r >= m || c < 0 || c >= n) { atomicExch(err, 1); grad_v[t] = 0.0; return; }
+    grad_v[t] = grad_out[(size_t)r * (size_t)n + (size_t)c];
+}
+
 // number of products each stored entry of A generates = length of the matching row of B
 __global__ void spgemm_count_kernel(const int32_t* __restrict__ a_col, size_t a_nnz, const int32_t* __restrict__ b_rowptr,
                                     uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total) {
@@ -682,6 +707,69 @@ int ab_coo_scale(int64_t T, const int64_t* idx_, const double* vv_, const double
     AB_TRY(fetch_err(err.p, &herr));
     if (herr) return fail(AB_ERANGE, "coo_scale: index outside the diagonal of length %lld", (long long)nd);
     AB_TRY(out.commit());
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    return AB_OK;
+}
+
+// ---------------------------------------------------------------- vcat / hcat (sparse_concate)
+int ab_coo_concat(int64_t n1, const int64_t* ii1_, const int64_t* jj1_, const double* vv1_,
+                  int64_t n2, const int64_t* ii2_, const int64_t* jj2_, const double* vv2_,
+                  int64_t m1, int64_t ncol1, int hcat, int64_t* oii_, int64_t* ojj_, double* ovv_) {
+    AB_TRY(ensure_device());
+    if (n1 < 0 || n2 < 0) return fail(AB_EINVAL, "negative size");
+    if (n1 + n2 == 0) return AB_OK;
+    if ((n1 > 0 && (!ii1_ || !jj1_ || !vv1_)) || (n2 > 0 && (!ii2_ || !jj2_ || !vv2_)) || !oii_ || !ojj_ || !ovv_)
+        return fail(AB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(big_lock());
+    In<int64_t> i1, j1, i2, j2; In<double> v1, v2; Out<int64_t> oi, oj; Out<double> ov;
+    AB_TRY(i1.bind(ii1_, n1)); AB_TRY(j1.bind(jj1_, n1)); AB_TRY(v1.bind(vv1_, n1));
+    AB_TRY(i2.bind(ii2_, n2)); AB_TRY(j2.bind(jj2_, n2)); AB_TRY(v2.bind(vv2_, n2));
+    AB_TRY(oi.bind(oii_, n1 + n2)); AB_TRY(oj.bind(ojj_, n1 + n2)); AB_TRY(ov.bind(ovv_, n1 + n2));
+    concat_kernel<<<nblk(n1 + n2), 256, 0, stream()>>>(i1.d, j1.d, v1.d, (size_t)n1, i2.d, j2.d, v2.d, (size_t)n2,
+                                                       hcat ? 0 : m1, hcat ? ncol1 : 0, oi.d, oj.d, ov.d);
+    AB_LAUNCH_CHECK();
+    AB_TRY(oi.commit()); AB_TRY(oj.commit()); AB_TRY(ov.commit());
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    return AB_OK;
+}
+
+// ---------------------------------------------------------------- Array(A) (sparse_to_dense_ad)
+int ab_csr_to_dense(int64_t h, double* out_) {
+    AB_TRY(ensure_device());
+    Csr* c = csr_get(h);
+    if (!c) return AB_EHANDLE;
+    if (c->m * c->n == 0) return AB_OK;
+    if (!out_) return fail(AB_EINVAL, "out is null");
+    std::lock_guard<std::mutex> lk(big_lock());
+    AB_TRY(csr_ensure_entry_row(c));
+    Out<double> out;
+    AB_TRY(out.bind(out_, (size_t)(c->m * c->n)));
+    AB_CUDA(cudaMemsetAsync(out.d, 0, (size_t)(c->m * c->n) * sizeof(double), stream()));
+    if (c->nnz) {
+        csr_to_dense_kernel<<<nblk(c->nnz), 256, 0, stream()>>>(c->entry_row, c->colind, c->values, (size_t)c->nnz, c->n, out.d);
+        AB_LAUNCH_CHECK();
+    }
+    AB_TRY(out.commit());
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    return AB_OK;
+}
+int ab_dense_grad_values(int64_t T, const int64_t* idx2_, int64_t m, int64_t n, const double* grad_out_, double* grad_v_) {
+    AB_TRY(ensure_device());
+    if (T < 0 || m < 0 || n < 0) return fail(AB_EINVAL, "negative size");
+    if (T == 0) return AB_OK;
+    if (!idx2_ || !grad_out_ || !grad_v_) return fail(AB_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(big_lock());
+    In<int64_t> idx2; In<double> go; Out<double> gv;
+    AB_TRY(idx2.bind(idx2_, (size_t)T * 2)); AB_TRY(go.bind(grad_out_, (size_t)(m * n))); AB_TRY(gv.bind(grad_v_, (size_t)T));
+    DevBuf<int> err;
+    AB_TRY(err.alloc(1));
+    AB_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream()));
+    dense_grad_kernel<<<nblk(T), 256, 0, stream()>>>(idx2.d, (size_t)T, m, n, go.d, gv.d, err.p);
+    AB_LAUNCH_CHECK();
+    int herr = 0;
+    AB_TRY(fetch_err(err.p, &herr));
+    if (herr) return fail(AB_ERANGE, "sparse_to_dense_grad: index outside the %lld x %lld matrix", (long long)m, (long long)n);
+    AB_TRY(gv.commit());
     AB_CUDA(cudaStreamSynchronize(stream()));
     return AB_OK;
 }

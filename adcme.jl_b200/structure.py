@@ -412,6 +412,98 @@ def _diag_values(D):
     return out
 
 
+def sparse_concate_op(ii1, jj1, vv1, m1, n1, ii2, jj2, vv2, m2, n2, hcat_):
+    """SparseConcate(ii1,jj1,vv1,m1,n1,ii2,jj2,vv2,m2,n2,hcat) -> (ii,jj,vv)  (SparseConcate.cpp:19-34,
+    SparseConcate.h:11-27): the second operand's rows (vcat) or columns (hcat) are shifted, order kept."""
+    k1i, p1i = as_array(ii1, np.int64); k1j, p1j = as_array(jj1, np.int64); k1v, p1v = as_array(vv1, np.float64)
+    k2i, p2i = as_array(ii2, np.int64); k2j, p2j = as_array(jj2, np.int64); k2v, p2v = as_array(vv2, np.float64)
+    n = _n(k1v) + _n(k2v)
+    like = k1v if _is_torch(k1v) else k2v
+    oi, oj, ov = empty_like_kind(like, (n,), np.int64), empty_like_kind(like, (n,), np.int64), empty_like_kind(like, (n,), np.float64)
+    check(lib.ab_coo_concat(_n(k1v), p1i, p1j, p1v, _n(k2v), p2i, p2j, p2v, int(m1), int(n1), 1 if hcat_ else 0,
+                            ptr(oi), ptr(oj), ptr(ov)))
+    return oi, oj, ov
+
+
+def sparse_concate_grad(grad_vv, ii, jj, vv, ii1, jj1, vv1, m1, n1, ii2, jj2, vv2, m2, n2, hcat_):
+    """SparseConcateGrad: the gradient is the split of grad_vv (SparseConcate.h:60-68)."""
+    N1 = _n(ii1)
+    return None, None, grad_vv[:N1], None, None, None, None, grad_vv[N1:], None, None, None
+
+
+def _concat(A, B, hcat_: bool):
+    sp = _sparse()
+    A, B = _as_st(A), _as_st(B)
+    if hcat_ and A.m != B.m or not hcat_ and A.n != B.n:
+        raise ValueError(f"sparse_concate: shapes {A.shape} and {B.shape} do not fit")
+    ii1, jj1, vv1 = A.triplets()
+    ii2, jj2, vv2 = B.triplets()
+    if _req(vv1) or _req(vv2):                 # the split gradient is torch.cat's own
+        dI, dJ = (0, A.n) if hcat_ else (A.m, 0)
+        ii = _cat(ii1, (ii2 + dI), np.int64); jj = _cat(jj1, (jj2 + dJ), np.int64); vv = _cat(vv1, vv2, np.float64)
+    else:
+        ii, jj, vv = sparse_concate_op(ii1, jj1, vv1, A.m, A.n, ii2, jj2, vv2, B.m, B.n, hcat_)
+    return sp.SparseTensor(ii, jj, vv, A.m if hcat_ else A.m + B.m, A.n + B.n if hcat_ else A.n)
+
+
+def hcat(*args):
+    """[A B ...] (sparse.jl:247-249,258)."""
+    out = args[0]
+    for B in args[1:]:
+        out = _concat(out, B, True)
+    return out
+
+
+def vcat(*args):
+    """[A; B; ...] (sparse.jl:247-249,257)."""
+    out = args[0]
+    for B in args[1:]:
+        out = _concat(out, B, False)
+    return out
+
+
+def hvcat(rows, *values):
+    """[A B; C] (sparse.jl:259-268): `rows` gives the number of blocks in each block row."""
+    r, k = [], 0
+    for cnt in rows:
+        r.append(hcat(*values[k:k + cnt]))
+        k += cnt
+    return vcat(*r)
+
+
+def to_dense(A):
+    """Array(A) (sparse.jl:185-193 -> sparse_to_dense_ad): dense row-major matrix, duplicates summed."""
+    A = _as_st(A)
+    like = A.vv if (A.vv is not None and _is_torch(A.vv)) else np.empty(0)
+    out = empty_like_kind(like, (A.m, A.n), np.float64)
+    check(lib.ab_csr_to_dense(A.handle(), ptr(out)))
+    return out
+
+
+def sparse_to_dense_grad(grad_A, ij, m, n):
+    """SparseToDenseAdGrad: grad_vv[i] = grad_A[ij[i,0], ij[i,1]] (SparseToDense.h:8-18)."""
+    kg, pg = as_array(grad_A, np.float64)
+    ki, pi = as_array(ij, np.int64)
+    T = _n(ki) // 2
+    out = empty_like_kind(kg, (T,), np.float64)
+    check(lib.ab_dense_grad_values(T, pi, int(m), int(n), pg, ptr(out)))
+    return out
+
+
+def spsum(A, dims=None):
+    """sum(S; dims) (sparse.jl:606-612 -> tf.sparse.reduce_sum): total, or the column sums (dims=1) /
+    row sums (dims=2) as a vector — SpMV with a vector of ones."""
+    sp = _sparse()
+    A = _as_st(A)
+    if dims is None:
+        return float(np.asarray(sp.mul(A, np.ones(A.n))).sum())
+    if dims == 1:
+        return sp.rmul(np.ones(A.m), A)
+    if dims == 2:
+        return sp.mul(A, np.ones(A.n))
+    raise ValueError("dims must be 1, 2 or None")
+
+
 def spdiag(*args):
     """spdiag(n) identity, spdiag(o) diagonal matrix from a vector, spdiag(n, k1=>v1, ...) banded
     matrix from (offset, values) pairs (sparse.jl:544-561, 631-658)."""

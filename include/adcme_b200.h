@@ -232,6 +232,16 @@ int ab_csr_export_coo(int64_t h, int64_t* ii, int64_t* jj, double* vv, int base)
  * (idx = cols), deps/CustomOps/SparseMatMul/SparseMatMul.h:34-52 */
 int ab_coo_scale(int64_t T, const int64_t* idx, const double* vv, const double* d, int64_t nd,
                  int base, double* out);
+/* vcat / hcat (src/sparse.jl:227-262 `_sparse_concate`; deps/CustomOps/SparseConcate/SparseConcate.h:11-27):
+ * out = [T1; T2 shifted by m1 rows (vcat) or ncol1 columns (hcat)], input order kept */
+int ab_coo_concat(int64_t n1, const int64_t* ii1, const int64_t* jj1, const double* vv1,
+                  int64_t n2, const int64_t* ii2, const int64_t* jj2, const double* vv2,
+                  int64_t m1, int64_t ncol1, int hcat, int64_t* oii, int64_t* ojj, double* ovv /*[n1+n2]*/);
+/* Array(A) (src/sparse.jl:185-193; deps/CustomOps/SparseToDense/SparseToDense.h): row-major [m,n],
+ * duplicates summed (at assembly); grad_v[t] = grad_out[i_t, j_t] per input triplet (0-based idx2) */
+int ab_csr_to_dense(int64_t h, double* out /*[m*n]*/);
+int ab_dense_grad_values(int64_t T, const int64_t* idx2, int64_t m, int64_t n, const double* grad_out,
+                         double* grad_v /*[T]*/);
 /* C = alpha*A + beta*B on the union pattern (A + B: src/sparse.jl:203-218 -> tf.sparse.add) */
 int ab_csr_axpby(int64_t ha, double alpha, int64_t hb, double beta, int64_t* out_h);
 /* C = A*B (sparse_sparse_mat_mul, SparseMatMul.h:11-32; src/sparse.jl:579-595).  transpose_out != 0

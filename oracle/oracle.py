@@ -263,6 +263,23 @@ def sparse_scatter_update_grad(grad_out, oii, ojj, un, ii, jj):
     return govv, g[k0:k0 + un].copy()
 
 
+def sparse_concate(ii1, jj1, vv1, m1, n1, ii2, jj2, vv2, hcat):
+    """Forward (deps/CustomOps/SparseConcate/SparseConcate.h:11-27)."""
+    ii1, jj1, ii2, jj2 = _i64(ii1), _i64(jj1), _i64(ii2), _i64(jj2)
+    if hcat:
+        return np.concatenate([ii1, ii2]), np.concatenate([jj1, jj2 + n1]), np.concatenate([_f64(vv1), _f64(vv2)])
+    return np.concatenate([ii1, ii2 + m1]), np.concatenate([jj1, jj2]), np.concatenate([_f64(vv1), _f64(vv2)])
+
+
+def sparse_to_dense(ij, vv, m, n):
+    """forward (deps/CustomOps/SparseToDense/SparseToDense.h:1-6): A[i*n+j] += v in input order."""
+    ij, vv = _i64(ij).reshape(-1, 2), _f64(vv)
+    A = np.zeros(m * n)
+    for k in range(len(vv)):
+        A[ij[k, 0] * n + ij[k, 1]] += vv[k]
+    return A.reshape(m, n)
+
+
 def _csc_from_triplets(ii, jj, vv, m, n, base):
     """Eigen setFromTriplets into a column-major matrix = our CSR restatement with the roles of the
     two indices swapped: -> (colptr, rowind, values), rows sorted, duplicates summed in input order."""

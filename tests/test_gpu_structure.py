@@ -290,3 +290,46 @@ def test_dirichlet_pipeline_assemble_zero_rows_add_identity_solve(pkg, orc):
     u0 = spla.spsolve(K0.tocsc(), f)
     assert np.linalg.norm(u - u0) <= 1e-9 * np.linalg.norm(u0)
     assert np.allclose(u[bd - 1], f[bd - 1], rtol=1e-10)
+
+
+# ======================================================================== vcat / hcat / hvcat, Array, sum
+def test_concat_reference_tests(pkg, orc):
+    B1 = sp.random(10, 3, 0.3, random_state=31, format="csr")          # test/sparse.jl:56-61
+    B = pkg.SparseTensor(B1)
+    assert np.array_equal(pkg.vcat(B, B).toarray(), sp.vstack([B1, B1]).toarray())
+    assert np.array_equal(pkg.hcat(B, B).toarray(), sp.hstack([B1, B1]).toarray())
+    A = sp.random(10, 5, 0.3, random_state=32, format="csr")           # test/sparse.jl:260-267
+    Bm = sp.random(10, 5, 0.2, random_state=33, format="csr")
+    Cm = sp.random(5, 10, 0.4, random_state=34, format="csr")
+    D = pkg.hvcat((2, 1), pkg.SparseTensor(A), pkg.SparseTensor(Bm), pkg.SparseTensor(Cm))
+    assert np.array_equal(D.toarray(), sp.vstack([sp.hstack([A, Bm]), Cm]).toarray())
+    # op level: exact order and integers
+    rng = np.random.default_rng(233)
+    i1, j1, v1 = rand_coo(rng, 40, 30, 500, 0.2)
+    i2, j2, v2 = rand_coo(rng, 25, 30, 300, 0.2)
+    op = pkg.load_system_op("sparse_concate")
+    for hc, (a, b) in ((False, ((i1, j1, v1, 40, 30), (i2, j2, v2, 25, 30))),):
+        I, J, V = op(*a, *b, hc)
+        I0, J0, V0 = orc.sparse_concate(a[0], a[1], a[2], a[3], a[4], b[0], b[1], b[2], hc)
+        assert np.array_equal(I, I0) and np.array_equal(J, J0) and np.array_equal(V, V0)
+    with pytest.raises(ValueError):
+        pkg.hcat(pkg.SparseTensor(A), pkg.SparseTensor(Cm))
+
+
+def test_to_dense_and_sum(pkg, orc):
+    rng = np.random.default_rng(233)
+    ii, jj, vv = rand_coo(rng, 37, 53, 900, dup_frac=0.3)
+    A = pkg.SparseTensor(ii, jj, vv, 37, 53)
+    D = pkg.to_dense(A)
+    D0 = orc.sparse_to_dense(np.stack([ii - 1, jj - 1], 1), vv, 37, 53)
+    assert np.array_equal(D, D0)                                       # duplicates summed in input order
+    g = rng.standard_normal((37, 53))
+    gv = np.empty(len(vv))
+    ij = np.ascontiguousarray(np.stack([ii - 1, jj - 1], 1))
+    pkg.check(pkg.lib.ab_dense_grad_values(len(vv), ij.ctypes.data, 37, 53, g.ctypes.data, gv.ctypes.data))
+    assert np.array_equal(gv, g[ii - 1, jj - 1])                       # SparseToDense.h:8-18
+    s = sp.random(10, 20, 0.2, random_state=35, format="csr")          # test/sparse.jl:192-198
+    S = pkg.SparseTensor(s)
+    assert abs(pkg.spsum(S) - s.sum()) <= 1e-12 * abs(s).sum()
+    assert np.allclose(pkg.spsum(S, dims=1), np.asarray(s.sum(axis=0)).ravel(), rtol=1e-13, atol=1e-15)
+    assert np.allclose(pkg.spsum(S, dims=2), np.asarray(s.sum(axis=1)).ravel(), rtol=1e-13, atol=1e-15)
