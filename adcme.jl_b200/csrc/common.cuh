@@ -217,6 +217,21 @@ int launch_spmv_part(const Csr* c, const double* x, double* y, const double* dot
                      double* partials, uint32_t* ticket, const int* done_flag, const int32_t* tile_list,
                      int64_t nlist, int accumulate);
 int spmv_tile_rows(const Csr* c);
+// Distributed SpMV in ONE launch: the tile list holds the interior tiles first; before a CTA touches
+// list position >= n_before it waits (acquire) until every peer with recv_cnt > 0 has published `seq`
+// in flags[peer].  Only the row-pattern kernel implements it (spmv_supports_halo_wait()).
+struct HaloWait {
+    const uint32_t* flags;     // [world] sequence numbers published by the peers (this rank's memory)
+    const int*      recv_cnt;  // [world]
+    int             world;
+    uint32_t        seq;
+    unsigned        n_before;  // list positions below this need no halo
+    uint32_t*       err;       // set when a wait times out
+};
+bool spmv_supports_halo_wait(const Csr* c, const double* vals);
+int  launch_spmv_halo(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
+                      double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
+                      const int32_t* tile_list, int64_t nlist, const HaloWait& hw);
 // same with an explicit value array (c->values or the scaled copy c->svalues)
 int launch_spmv_vals(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
                      double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,

@@ -112,6 +112,7 @@ struct DistCsr {
     bool     xext_cuda_malloc = false;
     // interior / boundary tile lists of the SpMV tile kernel (null when the matrix is not tiled)
     int32_t* tiles_int = nullptr; int32_t* tiles_bnd = nullptr;
+    int32_t* tiles_all = nullptr;  // [n_int + n_bnd] interior tiles first: the one-launch SpMV (HaloWait)
     int64_t  n_int = 0, n_bnd = 0;
     // peer-memory path
     bool p2p = false;
@@ -128,7 +129,7 @@ struct DistCsr {
     uint32_t halo_seq = 0, red_seq = 0;
     ~DistCsr() {
         delete loc;
-        dev_free(send_idx); dev_free(sendbuf); dev_free(tiles_int); dev_free(tiles_bnd);
+        dev_free(send_idx); dev_free(sendbuf); dev_free(tiles_int); dev_free(tiles_bnd); dev_free(tiles_all);
         dev_free(d_peer_blk); dev_free(d_peer_x); dev_free(d_send_off); dev_free(d_send_cnt); dev_free(d_recv_cnt);
         for (int i = 0; i < nopened; ++i) cudaIpcCloseMemHandle(opened[i]);
         if (xext) { if (xext_cuda_malloc) cudaFree(xext); else dev_free(xext); }
@@ -262,8 +263,10 @@ __global__ void halo_wait_kernel(P2PBlock* blk, const int* __restrict__ recv_cnt
 }
 
 // All-reduce (sum) of two doubles over the box, one 32-thread CTA per rank.
+// s != nullptr: the CG scalar logic that follows the reduction (cg_fin_kernel) runs right here —
+// fin_which 0 = after the init kernel, 1 = after the update kernel — one launch fewer per iteration.
 __global__ void p2p_allreduce2_kernel(double* vals, P2PBlock* blk, P2PBlock* const* __restrict__ peer_blk, int world,
-                                      int me, uint32_t seq) {
+                                      int me, uint32_t seq, SolveScal* s, int fin_which, int parity, double tol) {
     const int t = threadIdx.x, par = seq & 1u;
     if (t < world) {
         P2PBlock* dst = peer_blk[t];
@@ -280,6 +283,10 @@ __global__ void p2p_allreduce2_kernel(double* vals, P2PBlock* blk, P2PBlock* con
         for (int p = 0; p < world; ++p) { s0 += r[2 * p]; s1 += r[2 * p + 1]; }   // rank order: same bits everywhere
         vals[0] = s0;
         vals[1] = s1;
+        if (s) {
+            if (fin_which == 0) cg_init_fin(s, tol, s0, s1);
+            else if (!s->done) cg_update_fin(s, parity, s0, s1, s->bad != 0);
+        }
     }
 }
 
@@ -320,11 +327,25 @@ static int allreduce2(DistCsr* d, double* p) {
     if (g_world == 1) return AB_OK;
     if (d->p2p) {
         ++d->red_seq;
-        p2p_allreduce2_kernel<<<1, 32, 0, stream()>>>(p, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq);
+        p2p_allreduce2_kernel<<<1, 32, 0, stream()>>>(p, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq, nullptr, 0, 0, 0.0);
         AB_LAUNCH_CHECK();
         return AB_OK;
     }
     AB_NCCL(g_nccl.AllReduce(p, p, 2, ncclDouble, ncclSum, g_comm, stream()));
+    return AB_OK;
+}
+// all-reduce of s->red followed by the CG scalar logic (which: 0 init, 1 update)
+static int allreduce2_fin(DistCsr* d, SolveScal* s, int which, int parity, double tol) {
+    if (g_world == 1) return AB_OK;
+    if (d->p2p) {
+        ++d->red_seq;
+        p2p_allreduce2_kernel<<<1, 32, 0, stream()>>>(s->red, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq, s, which, parity, tol);
+        AB_LAUNCH_CHECK();
+        return AB_OK;
+    }
+    AB_NCCL(g_nccl.AllReduce(s->red, s->red, 2, ncclDouble, ncclSum, g_comm, stream()));
+    cg_fin_kernel<<<1, 1, 0, stream()>>>(s, which, parity, tol);
+    AB_LAUNCH_CHECK();
     return AB_OK;
 }
 
@@ -336,6 +357,12 @@ static int dist_spmv_dev(DistCsr* d, const double* vals, double* y, const double
     if (!split) {
         AB_TRY(halo_end(d));
         return launch_spmv_vals(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, nullptr, 0, 0);
+    }
+    if (d->tiles_all && d->next > 0 && opt("dist_fused_wait", 1.0) != 0.0 && spmv_supports_halo_wait(c, vals)) {
+        // one launch: interior tiles, in-kernel acquire of the peers' halo flags, boundary tiles
+        HaloWait hw{d->blk->halo_flag, d->d_recv_cnt, g_world, d->halo_seq, (unsigned)d->n_int, &d->blk->err};
+        return launch_spmv_halo(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_all,
+                                d->n_int + d->n_bnd, hw);
     }
     if (d->n_int > 0)
         AB_TRY(launch_spmv_vals(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_int, d->n_int, 0));
@@ -414,11 +441,7 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
     if (scaled) cgs_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->sinv, x, r, p, n, tol, s, c->partials, c->ticket, raw);
     else cg_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->dinv, x, r, p, n, tol, s, c->partials, c->ticket, raw);
     AB_LAUNCH_CHECK();
-    if (raw) {
-        AB_TRY(allreduce2(d, s->red));
-        cg_fin_kernel<<<1, 1, 0, stream()>>>(s, 0, 0, tol);
-        AB_LAUNCH_CHECK();
-    }
+    if (raw) AB_TRY(allreduce2_fin(d, s, 0, 0, tol));
     int check = (int)opt("check_every", 0);
     if (check <= 0) check = 16;
     const int defer_x = opt("cg_defer_x", 1.0) != 0.0 ? 1 : 0;   // x += alpha p rides in K3 (cg_kernels.cuh)
@@ -433,11 +456,7 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
             if (scaled) cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, raw, defer_x);
             else cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, raw);
             AB_LAUNCH_CHECK();
-            if (raw) {
-                AB_TRY(allreduce2(d, s->red));
-                cg_fin_kernel<<<1, 1, 0, stream()>>>(s, 1, parity, tol);
-                AB_LAUNCH_CHECK();
-            }
+            if (raw) AB_TRY(allreduce2_fin(d, s, 1, parity, tol));
             if (scaled) cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, it, defer_x, s);
             else cg_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, c->dinv, p, n, parity, s);
             AB_LAUNCH_CHECK();
@@ -731,6 +750,9 @@ int ab_dist_csr_create(int64_t h_local, int64_t ilower, int64_t iupper, int64_t 
             AB_TRY(dev_alloc((void**)&d->tiles_int, (size_t)(d->n_int + 1) * sizeof(int32_t)));
             AB_TRY(dev_alloc((void**)&d->tiles_bnd, (size_t)(d->n_bnd + 1) * sizeof(int32_t)));
             tile_split_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, stream()>>>(tf.p, te.p, ntiles, d->tiles_int, d->tiles_bnd);
+            AB_TRY(dev_alloc((void**)&d->tiles_all, (size_t)(ntiles + 1) * sizeof(int32_t)));
+            if (d->n_int) AB_CUDA(cudaMemcpyAsync(d->tiles_all, d->tiles_int, (size_t)d->n_int * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream()));
+            if (d->n_bnd) AB_CUDA(cudaMemcpyAsync(d->tiles_all + d->n_int, d->tiles_bnd, (size_t)d->n_bnd * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream()));
             AB_LAUNCH_CHECK();
         }
         // ---- 7. peer mappings

@@ -525,61 +525,49 @@ constexpr int PAT_MAX_LEN = 255;
 
 // x[row + off] through ONE integer instruction for the address (IMAD.WIDE off*8 + xr); left to itself
 // the compiler re-associates to x + (row + off) and spends four (IADD3, LEA.HI.X.SX32, LEA, LEA.HI.X).
+// CG = true: ld.global.cg (L2 only) — used after an in-kernel halo wait, where this SM's L1 may hold
+// a stale copy of a line that straddles owned and halo entries.
+template <bool CG>
 __device__ __forceinline__ double rowpat_gather(const double* xr, int off) {
     const double* p;
     asm("mad.wide.s32 %0, %1, 8, %2;" : "=l"(p) : "r"(off), "l"(xr));
+    if (CG) {
+        double v;
+        asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+        return v;
+    }
     return __ldg(p);
 }
 // L consecutive pattern entries: L gathers, then L FMAs in stored order.  No predicates, no clamping.
-template <int L>
+template <int L, bool CG>
 __device__ __forceinline__ double rowpat_chunk(const int4* __restrict__ e, const double* xr, double acc) {
     double xv[L];
 #pragma unroll
-    for (int u = 0; u < L; ++u) xv[u] = rowpat_gather(xr, e[u].z);
+    for (int u = 0; u < L; ++u) xv[u] = rowpat_gather<CG>(xr, e[u].z);
 #pragma unroll
     for (int u = 0; u < L; ++u) acc = fma(*reinterpret_cast<const double*>(e + u), xv[u], acc);
     return acc;
 }
 
-// Tiles are visited in runs of `run` consecutive tiles per CTA, runs grid-strided: consecutive tiles
-// of a run reuse each other's x lines in this SM's L1 (row+n of one tile is the centre of a later one)
-// while all CTAs together still sweep one compact window of x that stays in L2 (measured: one
-// contiguous chunk per CTA tripled the DRAM traffic — every CTA then drags its own +-n^2 planes).
-// All gathers of a row (up to 8) are issued before the first FMA needs one: one memory latency per
-// row, not one per unrolled remainder; the next tile's pattern byte is fetched a tile ahead.
-// NOTE: no minBlocksPerSM (as for the tile kernels).  Measured at 512^3: __launch_bounds__(R, 8) —
-// same 32 registers — 1.23 ms vs 0.95 ms without; sizing the registers for 6 or 4 CTAs/SM (40 / 64
-// registers, ptxas then batches all 8 gathers) 1.08-1.15 ms; exact-length unrolled bodies behind a
-// switch 1.35 ms.  The kernel is issue/LSU co-bound, not latency-bound: fewer instructions win.
-template <int R, bool LIST>
-__global__ void __launch_bounds__(R)
-spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__ pat_ent, int npat_ent,
-                   const uint32_t* __restrict__ pat_info, const double* __restrict__ x, double* __restrict__ y,
-                   unsigned m, unsigned ntiles, unsigned run, const int32_t* __restrict__ tile_list, int accumulate,
-                   const double* __restrict__ dotvec, double* partials, uint32_t* ticket, double* dot_result,
-                   const int* __restrict__ done) {
-    extern __shared__ __align__(16) unsigned char rp_smem[];
-    int4* s_ent = reinterpret_cast<int4*>(rp_smem);                                  // [npat_ent]
-    uint32_t* s_info = reinterpret_cast<uint32_t*>(rp_smem + (size_t)npat_ent * 16);  // [256]
-    __shared__ double s_red[32];
-    if (done && *done) return;
+// Walks list positions [pos0, pos1) that belong to this CTA (runs of `run` positions, runs grid-strided).
+template <int R, bool LIST, bool CG>
+__device__ __forceinline__ void rowpat_walk(const uint8_t* __restrict__ rowcode, const int4* s_ent, const uint32_t* s_info,
+                                            const double* __restrict__ x, double* __restrict__ y, unsigned m,
+                                            unsigned pos0, unsigned pos1, unsigned run, const int32_t* __restrict__ tile_list,
+                                            const double* __restrict__ dotvec, double& dot, double& dot2) {
     const unsigned t = threadIdx.x;
-    for (int i = t; i < npat_ent; i += R) s_ent[i] = pat_ent[i];
-    for (int i = t; i < 256; i += R) s_info[i] = pat_info[i];
-    __syncthreads();
-    double dot = 0.0, dot2 = 0.0;
     const unsigned stride = gridDim.x * run;
-    unsigned ti = blockIdx.x * run, left = run;          // position in the tile sequence, tiles left in this run
+    unsigned ti = pos0 + blockIdx.x * run, left = run;   // position in the tile sequence, tiles left in this run
     unsigned row_nx = 0xffffffffu, code_nx = 0;
-    if (ti < ntiles) {
+    if (ti < pos1) {
         row_nx = (LIST ? (unsigned)tile_list[ti] : ti) * R + t;
         code_nx = row_nx < m ? rowcode[row_nx] : 0u;
     }
-    while (ti < ntiles) {
+    while (ti < pos1) {
         const unsigned row = row_nx, code = code_nx;
         // advance to the next tile of this CTA and fetch its pattern byte now
         if (--left == 0) { ti += stride - run + 1; left = run; } else ++ti;
-        if (ti < ntiles) {
+        if (ti < pos1) {
             row_nx = (LIST ? (unsigned)tile_list[ti] : ti) * R + t;
             code_nx = row_nx < m ? rowcode[row_nx] : 0u;
         }
@@ -590,15 +578,64 @@ spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__
             const double* xr = x + row;
             double acc = 0.0;
             int k = 0;
-            for (; k + 4 <= len; k += 4) acc = rowpat_chunk<4>(e + k, xr, acc);     // branches are warp-uniform
-            if (len & 2) { acc = rowpat_chunk<2>(e + k, xr, acc); k += 2; }         // wherever the warp's rows
-            if (len & 1) acc = rowpat_chunk<1>(e + k, xr, acc);                     // share a pattern
+            for (; k + 4 <= len; k += 4) acc = rowpat_chunk<4, CG>(e + k, xr, acc);     // branches are warp-uniform
+            if (len & 2) { acc = rowpat_chunk<2, CG>(e + k, xr, acc); k += 2; }         // wherever the warp's rows
+            if (len & 1) acc = rowpat_chunk<1, CG>(e + k, xr, acc);                     // share a pattern
             y[row] = acc;
             if (dotvec) {
                 dot  = fma(acc, dotvec[row], dot);
                 dot2 = fma(acc, acc, dot2);
             }
         }
+    }
+}
+
+// Tiles are visited in runs of `run` consecutive tiles per CTA, runs grid-strided: consecutive tiles
+// of a run reuse each other's x lines in this SM's L1 (row+n of one tile is the centre of a later one)
+// while all CTAs together still sweep one compact window of x that stays in L2 (measured: one
+// contiguous chunk per CTA tripled the DRAM traffic — every CTA then drags its own +-n^2 planes).
+// The next tile's pattern byte is fetched a tile ahead; a row's entries go through exact 4/2/1 chunks.
+// hw.flags != nullptr (distributed SpMV in one launch): list positions >= hw.n_before are boundary tiles;
+// the CTA first finishes its interior positions, then acquires the peers' halo flags, then walks the
+// boundary positions with L2-only gathers.
+// NOTE: no minBlocksPerSM (as for the tile kernels).  Measured at 512^3: __launch_bounds__(R, 8) —
+// same 32 registers — 1.23 ms vs 0.95 ms without; sizing the registers for 6 or 4 CTAs/SM (40 / 64
+// registers, ptxas then batches all 8 gathers) 1.08-1.15 ms; predicated 8-wide bodies 1.0 ms; this
+// body 0.75 ms.  The kernel is issue/L1 co-bound, not latency-bound: fewer instructions win.
+template <int R, bool LIST>
+__global__ void __launch_bounds__(R)
+spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__ pat_ent, int npat_ent,
+                   const uint32_t* __restrict__ pat_info, const double* __restrict__ x, double* __restrict__ y,
+                   unsigned m, unsigned ntiles, unsigned run, const int32_t* __restrict__ tile_list, int accumulate,
+                   const double* __restrict__ dotvec, double* partials, uint32_t* ticket, double* dot_result,
+                   const int* __restrict__ done, HaloWait hw) {
+    extern __shared__ __align__(16) unsigned char rp_smem[];
+    int4* s_ent = reinterpret_cast<int4*>(rp_smem);                                  // [npat_ent]
+    uint32_t* s_info = reinterpret_cast<uint32_t*>(rp_smem + (size_t)npat_ent * 16);  // [256]
+    __shared__ double s_red[32];
+    if (done && *done) return;
+    const unsigned t = threadIdx.x;
+    for (int i = t; i < npat_ent; i += R) s_ent[i] = pat_ent[i];
+    for (int i = t; i < 256; i += R) s_info[i] = pat_info[i];
+    __syncthreads();
+    double dot = 0.0, dot2 = 0.0;
+    if (LIST && hw.flags) {
+        const unsigned nb = min(hw.n_before, ntiles);
+        rowpat_walk<R, LIST, false>(rowcode, s_ent, s_info, x, y, m, 0u, nb, run, tile_list, dotvec, dot, dot2);
+        if (t < (unsigned)hw.world && hw.recv_cnt[t] > 0) {                            // acquire the halos
+            const long long t0 = clock64();
+            uint32_t v;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(hw.flags + t) : "memory");
+                if ((int32_t)(v - hw.seq) >= 0) break;
+                if (clock64() - t0 > (1ll << 32)) { atomicExch(hw.err, 1u); break; }
+                __nanosleep(20);
+            } while (true);
+        }
+        __syncthreads();
+        rowpat_walk<R, LIST, true>(rowcode, s_ent, s_info, x, y, m, nb, ntiles, run, tile_list, dotvec, dot, dot2);
+    } else {
+        rowpat_walk<R, LIST, false>(rowcode, s_ent, s_info, x, y, m, 0u, ntiles, run, tile_list, dotvec, dot, dot2);
     }
     AB_TILE_EPILOGUE(R)
 }
@@ -816,9 +853,11 @@ int spmv_tile_rows(const Csr* c) {
 template <int R, int U>
 static int launch_tile(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec, double* dot_result,
                        double* partials, uint32_t* ticket, const int* done_flag, int ctas_per_sm,
-                       const int32_t* tile_list, int64_t nlist, int accumulate) {
+                       const int32_t* tile_list, int64_t nlist, int accumulate, const HaloWait* hwp = nullptr) {
     unsigned ntiles = tile_list ? (unsigned)nlist : (unsigned)((c->m + R - 1) / R);
     if (ntiles == 0) return AB_OK;
+    HaloWait hw{};
+    if (hwp) hw = *hwp;
     unsigned cap = (unsigned)(sm_count() * ctas_per_sm);
     if (cap > (unsigned)MAX_REDUCE_GRID) cap = MAX_REDUCE_GRID;
     unsigned grid = ntiles < cap ? ntiles : cap;
@@ -844,11 +883,15 @@ static int launch_tile(const Csr* c, const double* vals, const double* x, double
         }                                                                                                                   \
         kern<<<grid, R, smem, stream()>>>(c->rowcode, (const int4*)c->pat_ent, c->npat_ent, c->pat_info, x, y,              \
                                           (unsigned)c->m, ntiles, run, tile_list, accumulate, dotvec, partials, ticket,     \
-                                          dot_result, done_flag);                                                           \
+                                          dot_result, done_flag, hw);                                                       \
     } while (0)
         if (tile_list) AB_ROWPAT(true); else AB_ROWPAT(false);
 #undef AB_ROWPAT
-    } else if (coded)
+        AB_LAUNCH_CHECK();
+        return AB_OK;
+    }
+    if (hwp) return fail(AB_EUNSUPPORTED, "in-kernel halo wait needs the row-pattern SpMV form");
+    if (coded)
         spmv_code_kernel<R, U><<<grid, R, 0, stream()>>>(c->rowptr, c->code8, (const CodeEnt*)c->codetab, x, y, c->m, ntiles,
                                                          tile_list, accumulate, dotvec, partials, ticket, dot_result, done_flag);
     else if (c->noff > 0 && opt("spmv_off8", 1.0) != 0.0)
@@ -864,9 +907,33 @@ static int launch_tile(const Csr* c, const double* vals, const double* x, double
 // tile_list != nullptr: only those tiles (requires spmv_tile_rows(c) != 0); accumulate: add the
 // fused dots onto dot_result instead of overwriting.
 // vals: the value array to multiply with (c->values, or the symmetrically scaled copy used by CG)
+static bool rowpat_ready(const Csr* c, const double* vals) {
+    return c->ncode > 0 && c->npat > 0 && c->code_src == vals && c->code_version == c->values_version &&
+           opt("spmv_code", 1.0) != 0.0 && opt("spmv_rowpat", 1.0) != 0.0 && spmv_tile_rows(c) != 0 &&
+           (int)opt("spmv_variant", -1) != 0;
+}
+bool spmv_supports_halo_wait(const Csr* c, const double* vals) { return rowpat_ready(c, vals); }
+
+static int launch_spmv_impl(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
+                            double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
+                            const int32_t* tile_list, int64_t nlist, int accumulate, const HaloWait* hwp);
+
+int launch_spmv_halo(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
+                     double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
+                     const int32_t* tile_list, int64_t nlist, const HaloWait& hw) {
+    if (!tile_list || !rowpat_ready(c, vals)) return fail(AB_EUNSUPPORTED, "in-kernel halo wait needs the row-pattern SpMV form");
+    return launch_spmv_impl(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, 0, &hw);
+}
+
 int launch_spmv_vals(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
                      double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
                      const int32_t* tile_list, int64_t nlist, int accumulate) {
+    return launch_spmv_impl(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, accumulate, nullptr);
+}
+
+static int launch_spmv_impl(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
+                            double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
+                            const int32_t* tile_list, int64_t nlist, int accumulate, const HaloWait* hwp) {
     if (c->m == 0) return AB_OK;
     // spmv_variant: -1 auto, 0 vector kernel, 1 tile kernel U=8, 2 tile kernel U=4
     int variant = (int)opt("spmv_variant", -1);
@@ -883,7 +950,7 @@ int launch_spmv_vals(const Csr* c, const double* vals, const double* x, double* 
             AB_TRY(csr_ensure_code(const_cast<Csr*>(c), vals));
             if (c->ncode > 0 && c->npat < 0) AB_TRY(csr_ensure_rowpat(const_cast<Csr*>(c)));
         }
-#define AB_T(RR, UU) launch_tile<RR, UU>(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, cps * (256 / RR), tile_list, nlist, accumulate)
+#define AB_T(RR, UU) launch_tile<RR, UU>(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, cps * (256 / RR), tile_list, nlist, accumulate, hwp)
         if (R == 256) return variant == 2 ? AB_T(256, 4) : AB_T(256, 8);
         if (R == 128) return AB_T(128, 8);
         return AB_T(64, 8);
