@@ -619,9 +619,10 @@ spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__
     for (int i = t; i < 256; i += R) s_info[i] = pat_info[i];
     __syncthreads();
     double dot = 0.0, dot2 = 0.0;
-    if (LIST && hw.flags) {
-        const unsigned nb = min(hw.n_before, ntiles);
-        rowpat_walk<R, LIST, false>(rowcode, s_ent, s_info, x, y, m, 0u, nb, run, tile_list, dotvec, dot, dot2);
+    // one interior walk for both modes (same code whether or not a halo wait follows)
+    const unsigned nb = (LIST && hw.flags) ? min(hw.n_before, ntiles) : ntiles;
+    rowpat_walk<R, LIST, false>(rowcode, s_ent, s_info, x, y, m, 0u, nb, run, tile_list, dotvec, dot, dot2);
+    if (LIST && nb < ntiles) {
         if (t < (unsigned)hw.world && hw.recv_cnt[t] > 0) {                            // acquire the halos
             const long long t0 = clock64();
             uint32_t v;
@@ -633,9 +634,8 @@ spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__
             } while (true);
         }
         __syncthreads();
-        rowpat_walk<R, LIST, true>(rowcode, s_ent, s_info, x, y, m, nb, ntiles, run, tile_list, dotvec, dot, dot2);
-    } else {
-        rowpat_walk<R, LIST, false>(rowcode, s_ent, s_info, x, y, m, 0u, ntiles, run, tile_list, dotvec, dot, dot2);
+        // boundary tiles one per CTA (run = 1): they are few, the tail must be as short as possible
+        rowpat_walk<R, LIST, true>(rowcode, s_ent, s_info, x, y, m, nb, ntiles, 1u, tile_list, dotvec, dot, dot2);
     }
     AB_TILE_EPILOGUE(R)
 }

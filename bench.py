@@ -223,6 +223,9 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
     n = args.grid
     N, nnz = n ** 3, poisson_nnz(n)
     pkg.mpi_init(rank, world, local_rank)
+    for kv in filter(None, os.environ.get("AB_OPTS", "").split(",")):       # A/B switches, e.g. AB_OPTS=dist_fused_wait=0
+        k_, v_ = kv.split("=")
+        pkg.check(lib.ab_set_option(k_.strip().encode(), float(v_)))
     A = pkg.mpi_SparseTensor.poisson3d(n, n, n, rank, world)
     nloc = A.nloc
     ones = torch.ones(nloc, dtype=torch.float64, device=dev)
