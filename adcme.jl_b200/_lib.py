@@ -37,6 +37,7 @@ SIGNATURES = {
     "ab_asm_destroy": (C.c_int, [_i32]),
     "ab_csr_from_coo": (C.c_int, [_i64, _ptr, _ptr, _ptr, _i64, _i64, C.c_int, _ptr]),
     "ab_csr_from_coo32": (C.c_int, [_i64, _ptr, _ptr, _ptr, _i64, _i64, C.c_int, _ptr]),
+    "ab_coo_reorder": (C.c_int, [_i64, _ptr, _ptr, _ptr, _i64, _i64, C.c_int, _ptr, _ptr, _ptr, _ptr]),
     "ab_csr_create": (C.c_int, [_i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "ab_csr_query": (C.c_int, [_i64, _ptr, _ptr, _ptr, _ptr]),
     "ab_csr_export": (C.c_int, [_i64, _ptr, _ptr, _ptr]),

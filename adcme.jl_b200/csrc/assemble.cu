@@ -883,6 +883,57 @@ int ab_csr_transpose(int64_t h, int64_t* out_h) {
     return AB_OK;
 }
 
+// ------------------------------------------------------------------ tf.sparse.reorder (SparseTensor ctor / find)
+__global__ void reorder_gather_kernel(const uint32_t* __restrict__ perm, size_t T, const int64_t* __restrict__ ii,
+                                      const int64_t* __restrict__ jj, const double* __restrict__ vv,
+                                      int64_t* __restrict__ oi, int64_t* __restrict__ oj, double* __restrict__ ov,
+                                      int64_t* __restrict__ operm) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= T) return;
+    const uint32_t t = perm[k];
+    if (oi) oi[k] = ii[t];
+    if (oj) oj[k] = jj[t];
+    if (ov) ov[k] = vv[t];
+    if (operm) operm[k] = (int64_t)t;
+}
+
+// Stable row-major sort of the triplets, duplicates KEPT (src/sparse.jl:62-76: tf.sparse.reorder in the
+// constructor; find() then hands (ii, jj, vv) in this order to every op).  Any output may be NULL;
+// perm[k] = input position of output k (0-based).
+int ab_coo_reorder(int64_t T, const int64_t* ii_, const int64_t* jj_, const double* vv_, int64_t m, int64_t n, int base,
+                   int64_t* oii_, int64_t* ojj_, double* ovv_, int64_t* perm_) {
+    AB_TRY(ensure_device());
+    if (T < 0 || m < 0 || n < 0) return fail(AB_EINVAL, "negative size");
+    if (T == 0) return AB_OK;
+    if (!ii_ || !jj_ || (ovv_ && !vv_)) return fail(AB_EINVAL, "null triplet array");
+    if (m >= INT32_MAX || n >= INT32_MAX) return fail(AB_EUNSUPPORTED, "matrix dimension exceeds int32 local index space");
+    if (T >= (int64_t)UINT32_MAX) return fail(AB_EUNSUPPORTED, "more than 2^32-1 triplets in one call");
+    std::lock_guard<std::mutex> lk(big_lock());
+    In<int64_t> ii, jj; In<double> vv;
+    AB_TRY(ii.bind(ii_, T)); AB_TRY(jj.bind(jj_, T)); AB_TRY(vv.bind(vv_, T));
+    Out<int64_t> oi, oj, op; Out<double> ov;
+    AB_TRY(oi.bind(oii_, T)); AB_TRY(oj.bind(ojj_, T)); AB_TRY(ov.bind(ovv_, T)); AB_TRY(op.bind(perm_, T));
+    const int colbits = bits_for(n > 0 ? n : 1), rowbits = bits_for(m > 0 ? m : 1);
+    DevBuf<uint64_t> k0, k1; DevBuf<uint32_t> p0, p1; DevBuf<int> err;
+    AB_TRY(k0.alloc(T)); AB_TRY(k1.alloc(T)); AB_TRY(p0.alloc(T)); AB_TRY(p1.alloc(T)); AB_TRY(err.alloc(1));
+    AB_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream()));
+    const unsigned nb = (unsigned)((T + 255) / 256);
+    make_keys_kernel<int64_t><<<nb, 256, 0, stream()>>>(ii.d, jj.d, (size_t)T, m, n, base, colbits, k0.p, err.p);
+    AB_LAUNCH_CHECK();
+    uint64_t* ks; uint32_t* ps;
+    AB_TRY(radix_sort_u64(k0.p, p0.p, k1.p, p1.p, (size_t)T, colbits + rowbits, &ks, &ps));
+    int herr = 0;
+    AB_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    if (herr) return fail(AB_ERANGE, "triplet index outside [%d,%lld]x[%d,%lld]", base, (long long)(m + base - 1), base,
+                          (long long)(n + base - 1));
+    reorder_gather_kernel<<<nb, 256, 0, stream()>>>(ps, (size_t)T, ii.d, jj.d, vv.d, oi.d, oj.d, ov.d, op.d);
+    AB_LAUNCH_CHECK();
+    AB_TRY(oi.commit()); AB_TRY(oj.commit()); AB_TRY(ov.commit()); AB_TRY(op.commit());
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    return AB_OK;
+}
+
 // ------------------------------------------------------------------ compress
 int ab_compress_count(int64_t N, const int64_t* idx2_, int64_t* nout) {
     AB_TRY(ensure_device());

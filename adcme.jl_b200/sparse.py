@@ -222,18 +222,22 @@ def find(s: SparseTensor):
     """(ii, jj, vv), 1-based; row-major sorted when options.sparse.auto_reorder (tf.sparse.reorder
     is a stable lexicographic sort, duplicates kept: sparse.jl:62-76,93-99)."""
     ii, jj, vv = s.triplets()
-    if options.sparse.auto_reorder:
-        i_np = np.asarray(ii.cpu() if _is_torch(ii) else ii)
-        j_np = np.asarray(jj.cpu() if _is_torch(jj) else jj)
-        p = np.lexsort((j_np, i_np))   # stable
-        if _is_torch(vv):
-            import torch
-
-            pt = torch.as_tensor(p, device=vv.device)
-            vv = vv[pt]
+    if options.sparse.auto_reorder and not s._pattern_only:      # a handle's triplets are already row-major
+        ki, pi = as_array(ii, np.int64)
+        kj, pj = as_array(jj, np.int64)
+        T = _numel(ki)
+        like = vv if _is_torch(vv) else (ki if _is_torch(ki) else np.empty(0))
+        oi, oj = empty_like_kind(like, (T,), np.int64), empty_like_kind(like, (T,), np.int64)
+        perm = empty_like_kind(like, (T,), np.int64)
+        if _is_torch(vv) and vv.requires_grad:                   # keep the autograd edge: permute on the AD side
+            check(lib.ab_coo_reorder(T, pi, pj, None, s.m, s.n, 1, ptr(oi), ptr(oj), None, ptr(perm)))
+            vv = vv[perm]
         else:
-            vv = np.asarray(vv)[p]
-        ii, jj = i_np[p], j_np[p]
+            kv, pv = as_array(vv, np.float64)
+            ov = empty_like_kind(like, (T,), np.float64)
+            check(lib.ab_coo_reorder(T, pi, pj, pv, s.m, s.n, 1, ptr(oi), ptr(oj), ptr(ov), ptr(perm)))
+            vv = ov
+        ii, jj = oi, oj
     return ii, jj, vv
 
 

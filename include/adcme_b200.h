@@ -86,6 +86,11 @@ int ab_csr_from_coo(int64_t T, const int64_t* ii, const int64_t* jj, const doubl
                     int64_t m, int64_t n, int base, int64_t* out_h);
 int ab_csr_from_coo32(int64_t T, const int32_t* ii, const int32_t* jj, const double* vv,
                       int64_t m, int64_t n, int base, int64_t* out_h);
+/* tf.sparse.reorder of the constructor (src/sparse.jl:62-76): stable row-major sort of the triplets,
+ * duplicates kept — the order find()/rows()/cols()/values() hand to every op.  Outputs may be NULL;
+ * perm[k] = input position of output k (so values with gradients can be permuted by the host AD). */
+int ab_coo_reorder(int64_t T, const int64_t* ii, const int64_t* jj, const double* vv, int64_t m, int64_t n,
+                   int base, int64_t* oii, int64_t* ojj, double* ovv, int64_t* perm);
 /* adopt an existing 0-based CSR (copied); T == nnz and the triplet map is the identity */
 int ab_csr_create(int64_t m, int64_t n, int64_t nnz, const int32_t* rowptr,
                   const int32_t* colind, const double* values, int64_t* out_h);

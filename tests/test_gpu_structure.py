@@ -333,3 +333,35 @@ def test_to_dense_and_sum(pkg, orc):
     assert abs(pkg.spsum(S) - s.sum()) <= 1e-12 * abs(s).sum()
     assert np.allclose(pkg.spsum(S, dims=1), np.asarray(s.sum(axis=0)).ravel(), rtol=1e-13, atol=1e-15)
     assert np.allclose(pkg.spsum(S, dims=2), np.asarray(s.sum(axis=1)).ravel(), rtol=1e-13, atol=1e-15)
+
+
+# ======================================================================== find / tf.sparse.reorder
+def test_find_is_stable_row_major_reorder(pkg):
+    import torch
+
+    rng = np.random.default_rng(233)
+    A = sp.random(10, 10, 0.3, random_state=41, format="coo")          # test/sparse.jl:269-292
+    p = rng.permutation(A.nnz)
+    S = pkg.SparseTensor(A.row[p] + 1, A.col[p] + 1, A.data[p], 10, 10)
+    i, j, v = pkg.find(S)
+    R = A.tocsr().tocoo()                                              # row-major
+    assert np.array_equal(i, R.row + 1) and np.array_equal(j, R.col + 1) and np.array_equal(v, R.data)
+    assert np.array_equal(pkg.rows(S), i) and np.array_equal(pkg.cols(S), j) and np.array_equal(pkg.values(S), v)
+    # duplicates are kept, in input order (stable) — tf.sparse.reorder does not merge
+    ii, jj, vv = rand_coo(rng, 50, 40, 3000, dup_frac=0.4)
+    i, j, v = pkg.find(pkg.SparseTensor(ii, jj, vv, 50, 40))
+    q = np.lexsort((np.arange(len(vv)), jj, ii))
+    assert np.array_equal(i, ii[q]) and np.array_equal(j, jj[q]) and np.array_equal(v, vv[q])
+    # device-resident values with gradient: the permutation stays on the autograd tape
+    vt = torch.tensor(vv, device="cuda", requires_grad=True)
+    _, _, v2 = pkg.find(pkg.SparseTensor(ii, jj, vt, 50, 40))
+    w = torch.arange(len(vv), dtype=torch.float64, device="cuda")
+    (v2 * w).sum().backward()
+    g = np.empty(len(vv)); g[q] = np.arange(len(vv), dtype=float)
+    assert np.array_equal(vt.grad.cpu().numpy(), g)
+    pkg.options.sparse.auto_reorder = False
+    try:
+        i3, _, _ = pkg.find(pkg.SparseTensor(ii, jj, vv, 50, 40))
+        assert np.array_equal(i3, ii)
+    finally:
+        pkg.reset_default_options()
