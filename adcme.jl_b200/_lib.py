@@ -74,6 +74,7 @@ SIGNATURES = {
     "ab_sparse_indexing_grad": (C.c_int, [_i64, _ptr, _i64, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ab_csr_export_coo": (C.c_int, [_i64, _ptr, _ptr, _ptr, C.c_int]),
     "ab_coo_scale": (C.c_int, [_i64, _ptr, _ptr, _ptr, _i64, C.c_int, _ptr]),
+    "ab_dense_to_coo": (C.c_int, [_i64, _i64, _ptr, _ptr]),
     "ab_coo_concat": (C.c_int, [_i64, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _i64, _i64, C.c_int, _ptr, _ptr, _ptr]),
     "ab_csr_to_dense": (C.c_int, [_i64, _ptr]),
     "ab_dense_grad_values": (C.c_int, [_i64, _ptr, _i64, _i64, _ptr, _ptr]),

@@ -345,6 +345,21 @@ __global__ void dense_grad_kernel(const int64_t* __restrict__ idx2, size_t T, in
     grad_v[t] = grad_out[(size_t)r * (size_t)n + (size_t)c];
 }
 
+// dense_to_sparse (src/sparse.jl:78-86: tf.where(o != 0) + gather_nd): row-major nonzeros
+__global__ void dense_flags_kernel(const double* __restrict__ a, size_t mn, uint32_t* __restrict__ keep) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < mn) keep[i] = (a[i] != 0.0) ? 1u : 0u;           // NaN != 0 is true, as in tf.not_equal
+}
+__global__ void dense_compact_kernel(const double* __restrict__ a, size_t mn, int64_t n, const uint32_t* __restrict__ excl,
+                                     int64_t* __restrict__ oi, int64_t* __restrict__ oj, double* __restrict__ ov) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= mn) return;
+    const double v = a[i];
+    if (!(v != 0.0)) return;
+    const uint32_t p = excl[i];
+    oi[p] = (int64_t)(i / (size_t)n) + 1; oj[p] = (int64_t)(i % (size_t)n) + 1; ov[p] = v;
+}
+
 // number of products each stored entry of A generates = length of the matching row of B
 __global__ void spgemm_count_kernel(const int32_t* __restrict__ a_col, size_t a_nnz, const int32_t* __restrict__ b_rowptr,
                                     uint32_t* __restrict__ cnt, unsigned long long* __restrict__ total) {
@@ -708,6 +723,36 @@ int ab_coo_scale(int64_t T, const int64_t* idx_, const double* vv_, const double
     if (herr) return fail(AB_ERANGE, "coo_scale: index outside the diagonal of length %lld", (long long)nd);
     AB_TRY(out.commit());
     AB_CUDA(cudaStreamSynchronize(stream()));
+    return AB_OK;
+}
+
+// ---------------------------------------------------------------- dense_to_sparse
+int ab_dense_to_coo(int64_t m, int64_t n, const double* a_, int64_t* out_th) {
+    AB_TRY(ensure_device());
+    if (!out_th) return fail(AB_EINVAL, "out_th is null");
+    if (m < 0 || n < 0) return fail(AB_EINVAL, "negative size");
+    const size_t mn = (size_t)m * (size_t)n;
+    if (mn > 0 && !a_) return fail(AB_EINVAL, "null matrix");
+    if (mn >= (size_t)UINT32_MAX) return fail(AB_EUNSUPPORTED, "more than 2^32-1 dense entries in one call");
+    std::lock_guard<std::mutex> lk(big_lock());
+    In<double> a;
+    AB_TRY(a.bind(a_, mn));
+    DevBuf<uint32_t> keep, total;
+    AB_TRY(keep.alloc(mn)); AB_TRY(total.alloc(1));
+    if (mn) { dense_flags_kernel<<<nblk(mn), 256, 0, stream()>>>(a.d, mn, keep.p); AB_LAUNCH_CHECK(); }
+    AB_TRY(scan_exclusive_u32(keep.p, keep.p, mn, total.p));
+    uint32_t nout = 0;
+    AB_TRY(fetch_u32(total.p, &nout));
+    Trip* t = new Trip();
+    auto body = [&]() -> int {
+        AB_TRY(trip_alloc(t, nout));
+        if (mn) { dense_compact_kernel<<<nblk(mn), 256, 0, stream()>>>(a.d, mn, n, keep.p, t->ii, t->jj, t->vv); AB_LAUNCH_CHECK(); }
+        AB_CUDA(cudaStreamSynchronize(stream()));
+        return AB_OK;
+    };
+    int rc = body();
+    if (rc != AB_OK) { delete t; return rc; }
+    *out_th = trip_put(t);
     return AB_OK;
 }
 

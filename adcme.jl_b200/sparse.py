@@ -49,6 +49,11 @@ class SparseTensor:
             coo = I.tocoo()
             m, n = coo.shape
             I, J, V = coo.row.astype(np.int64) + 1, coo.col.astype(np.int64) + 1, coo.data.astype(np.float64)
+        if J is None and V is None and len(tuple(getattr(I, "shape", ()))) == 2:   # SparseTensor(A::Array), sparse.jl:159-161
+            from . import structure
+
+            d = structure.dense_to_sparse(I)
+            I, J, V, m, n = d.ii, d.jj, d.vv, d.m, d.n
         if _numel(I) != _numel(J) or _numel(I) != _numel(V):
             raise ValueError("I, J, V must have the same length")
         self.ii, self.jj, self.vv = I, J, V

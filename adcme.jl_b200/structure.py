@@ -471,6 +471,19 @@ def hvcat(rows, *values):
     return vcat(*r)
 
 
+def dense_to_sparse(o):
+    """dense_to_sparse(o) (sparse.jl:78-86): SparseTensor of the nonzeros of a dense matrix."""
+    sp = _sparse()
+    if len(tuple(o.shape)) != 2:
+        raise ValueError("dense_to_sparse: a matrix is required")
+    m, n = int(o.shape[0]), int(o.shape[1])
+    ko, po = as_array(o, np.float64)
+    th = C.c_int64(0)
+    check(lib.ab_dense_to_coo(m, n, po, C.byref(th)))
+    ii, jj, vv = _fetch_trip(th.value, ko if _is_torch(ko) else np.empty(0))
+    return sp.SparseTensor(ii, jj, vv, m, n)
+
+
 def to_dense(A):
     """Array(A) (sparse.jl:185-193 -> sparse_to_dense_ad): dense row-major matrix, duplicates summed."""
     A = _as_st(A)

@@ -237,6 +237,9 @@ int ab_csr_export_coo(int64_t h, int64_t* ii, int64_t* jj, double* vv, int base)
  * (idx = cols), deps/CustomOps/SparseMatMul/SparseMatMul.h:34-52 */
 int ab_coo_scale(int64_t T, const int64_t* idx, const double* vv, const double* d, int64_t nd,
                  int base, double* out);
+/* dense_to_sparse (src/sparse.jl:78-86): the nonzeros (a != 0) of a row-major [m,n] matrix as 1-based
+ * triplets in row-major order -> triplet handle */
+int ab_dense_to_coo(int64_t m, int64_t n, const double* a, int64_t* out_th);
 /* vcat / hcat (src/sparse.jl:227-262 `_sparse_concate`; deps/CustomOps/SparseConcate/SparseConcate.h:11-27):
  * out = [T1; T2 shifted by m1 rows (vcat) or ncol1 columns (hcat)], input order kept */
 int ab_coo_concat(int64_t n1, const int64_t* ii1, const int64_t* jj1, const double* vv1,

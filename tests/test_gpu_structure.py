@@ -365,3 +365,15 @@ def test_find_is_stable_row_major_reorder(pkg):
         assert np.array_equal(i3, ii)
     finally:
         pkg.reset_default_options()
+
+
+def test_dense_to_sparse_reference_test(pkg):
+    A = sp.random(10, 20, 0.3, random_state=43, format="csr")          # test/sparse.jl:200-205
+    B = A.toarray()
+    S = pkg.dense_to_sparse(B)
+    assert np.array_equal(S.toarray(), B) and S.query()[2] == A.nnz
+    R = A.tocoo()
+    assert np.array_equal(S.ii, R.row + 1) and np.array_equal(S.jj, R.col + 1) and np.array_equal(S.vv, R.data)   # row-major
+    assert np.array_equal(pkg.SparseTensor(B).toarray(), B)            # SparseTensor(A::Array)
+    assert pkg.dense_to_sparse(np.zeros((3, 4))).query()[2] == 0
+    assert np.array_equal(pkg.to_dense(S), B)
