@@ -166,6 +166,10 @@ struct Csr {
     uint64_t values_version = 1;   // bumped whenever `values` change
     uint64_t scaled_version = 0;   // version svalues/sinv were built from (0 = never)
     bool     scaled_ok = false;    // false: a diagonal entry is missing / non-positive -> classic path
+    // numerical symmetry A == A' (bitwise), checked lazily per values_version (solver.cu): lets the
+    // legacy direct-solver strings try CG first and lets the adjoint solve skip the transpose
+    uint64_t sym_version = 0;
+    bool     is_sym = false;
     // cached transpose (lazy): handle id of A', and map tperm (A' entry -> A entry)
     int64_t   th    = 0;
     uint32_t* tperm = nullptr;

@@ -513,9 +513,76 @@ static int dense_lu_solve(Csr* c, const double* b, double* x) {
     return AB_OK;
 }
 
+// *bad = 1 unless every stored (r, c, v) has a stored (c, r, v) with the same bits (rows sorted by column)
+__global__ void symmetry_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                                const double* __restrict__ values, int64_t m, int* __restrict__ bad) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m || *(volatile int*)bad) return;
+    for (int j = rowptr[r]; j < rowptr[r + 1]; ++j) {
+        const int c = colind[j];
+        if (c == r) continue;
+        if (c >= m) { atomicExch(bad, 1); return; }
+        int lo = rowptr[c], hi = rowptr[c + 1] - 1, e = -1;
+        while (lo <= hi) {
+            const int mid = (lo + hi) >> 1, cm = colind[mid];
+            if (cm == r) { e = mid; break; }
+            if (cm < r) lo = mid + 1; else hi = mid - 1;
+        }
+        if (e < 0 || __double_as_longlong(values[e]) != __double_as_longlong(values[j])) { atomicExch(bad, 1); return; }
+    }
+}
+
+// A == A' bitwise?  Cached per values_version.
+static int csr_check_symmetric(Csr* c, bool* sym) {
+    if (c->sym_version != c->values_version) {
+        c->is_sym = false;
+        if (c->m == c->n && c->m > 0) {
+            DevBuf<int> bad;
+            AB_TRY(bad.alloc(1));
+            AB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), stream()));
+            symmetry_kernel<<<(unsigned)((c->m + 255) / 256), 256, 0, stream()>>>(c->rowptr, c->colind, c->values, c->m, bad.p);
+            AB_LAUNCH_CHECK();
+            int hb = 1;
+            AB_CUDA(cudaMemcpyAsync(&hb, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+            AB_CUDA(cudaStreamSynchronize(stream()));
+            c->is_sym = (hb == 0);
+        }
+        c->sym_version = c->values_version;
+    }
+    *sym = c->is_sym;
+    return AB_OK;
+}
+
+static int solve_dev_impl(Csr* c, Method meth, const double* b, double* x, double tol, int maxit, int* iters,
+                          double* relres);
+
 // Solve A x = b with device pointers.  Shared by forward and adjoint.
+// The legacy direct-solver strings (SparseLU / SparseQR / auto -> M_GENERAL) first try CG when the matrix
+// is numerically symmetric with a positive diagonal — the FEM/stencil systems this path exists for —
+// and fall back to BiCGSTAB (+ dense LU for tiny systems) when CG breaks down (symmetric indefinite) or
+// does not converge; solve_dev_impl vets every answer by the true residual, so a wrong guess costs time only.
 static int solve_dev(Csr* c, Method meth, const double* b, double* x, double tol, int maxit, int* iters,
                      double* relres) {
+    if (meth == M_GENERAL && c->m == c->n && c->m > 0 && opt("auto_cg", 1.0) != 0.0) {
+        bool sym = false;
+        AB_TRY(csr_check_symmetric(c, &sym));
+        if (sym) {
+            AB_TRY(csr_ensure_scaled(c));
+            if (c->scaled_ok) {
+                int it1 = 0; double rr1 = 0.0;
+                if (solve_dev_impl(c, M_CG, b, x, tol, maxit, &it1, &rr1) == AB_OK) {
+                    if (iters) *iters = it1;
+                    if (relres) *relres = rr1;
+                    return AB_OK;
+                }
+            }
+        }
+    }
+    return solve_dev_impl(c, meth, b, x, tol, maxit, iters, relres);
+}
+
+static int solve_dev_impl(Csr* c, Method meth, const double* b, double* x, double tol, int maxit, int* iters,
+                          double* relres) {
     if (c->m != c->n) return fail(AB_EINVAL, "sparse solve needs a square matrix (got %lld x %lld)", (long long)c->m, (long long)c->n);
     if (tol <= 0) tol = opt("tol", 1e-12);
     if (maxit <= 0) maxit = (int)opt("maxit", 0);
@@ -648,9 +715,14 @@ int ab_solve_grad(int64_t h, const char* method, const double* grad_u_, const do
     In<double> g, u;
     AB_TRY(g.bind(grad_u_, c->m));
     if (grad_vv_) AB_TRY(u.bind(u_, c->m));
-    // x = A^{-T} g.  CG asserts symmetry, so A itself is used; BiCGSTAB goes through the cached A'.
+    // x = A^{-T} g.  CG asserts symmetry, so A itself is used; so does a matrix that IS symmetric (bitwise
+    // check, cached); otherwise BiCGSTAB goes through the cached A'.
     Csr* ct = c;
-    if (meth != M_CG) AB_TRY(csr_ensure_transpose(c, &ct));
+    if (meth != M_CG) {
+        bool sym = false;
+        if (opt("auto_cg", 1.0) != 0.0) AB_TRY(csr_check_symmetric(c, &sym));
+        if (!sym) AB_TRY(csr_ensure_transpose(c, &ct));
+    }
     Out<double> gf;
     DevBuf<double> xtmp;
     double* x = nullptr;

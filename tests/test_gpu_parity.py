@@ -376,6 +376,38 @@ def test_cg_scaled_form_matches_classic_pcg(pkg, orc):
     assert np.allclose(u, [1.0, -0.5, 1.0 / 3.0], rtol=1e-12)
 
 
+def test_legacy_method_strings_try_cg_on_symmetric_matrices(pkg, orc):
+    """SparseLU / SparseQR / auto: CG first when A == A' bitwise with a positive diagonal, BiCGSTAB (+ dense
+    LU) otherwise or when CG breaks down — the answer is vetted by the true residual either way."""
+    rng = np.random.default_rng(233)
+    # symmetric INDEFINITE with a positive diagonal: CG must give up and the general path must answer
+    n = 60
+    B = sp.random(n, n, 0.1, random_state=5, format="csr")
+    S = (B + B.T + sp.identity(n) * 0.05).tocoo()
+    assert np.linalg.eigvalsh(S.toarray()).min() < 0 and S.diagonal().min() > 0
+    A = pkg.SparseTensor(S.row + 1, S.col + 1, S.data, n, n)
+    f = rng.uniform(size=n)
+    u = pkg.backslash(A, f, "SparseLU")
+    assert np.linalg.norm(S @ u - f) / np.linalg.norm(f) <= TOL_SOLVE
+    # SPD through the legacy strings: same answer as the explicit CG, and the adjoint needs no transpose
+    ii, jj, vv, N = spd_case(orc, 30)
+    P = pkg.SparseTensor(ii, jj, vv, N, N)
+    f = rng.uniform(size=N)
+    u1, u2 = pkg.backslash(P, f, "SparseLU"), pkg.backslash(P, f, "CG")
+    assert np.array_equal(u1, u2)
+    g = rng.uniform(size=N)
+    op = pkg.load_system_op("sparse_solver")
+    r1 = op.grad(g, u1, ii, jj, vv, f, "SparseLU")
+    r2 = op.grad(g, u1, ii, jj, vv, f, "SimplicialLLT")
+    assert np.array_equal(r1[2], r2[2]) and np.array_equal(r1[3], r2[3])
+    pkg.check(pkg.lib.ab_set_option(b"auto_cg", 0.0))          # the switch: plain BiCGSTAB again
+    try:
+        u3 = pkg.backslash(P, f, "SparseLU")
+    finally:
+        pkg.check(pkg.lib.ab_set_option(b"auto_cg", 1.0))
+    assert np.linalg.norm(u3 - u1) <= 1e-9 * np.linalg.norm(u1) and not np.array_equal(u3, u1)
+
+
 def test_solve_random_nonsymmetric_like_reference_test(pkg, orc):
     rng = np.random.default_rng(233)                                   # test/sparse.jl:71-78
     # (10, 0.1) is the reference's own case; the larger ones exercise BiCGSTAB on diagonally dominant
