@@ -224,6 +224,15 @@ int spmv_tile_rows(const Csr* c);
 // Distributed SpMV in ONE launch: the tile list holds the interior tiles first; before a CTA touches
 // list position >= n_before it waits (acquire) until every peer with recv_cnt > 0 has published `seq`
 // in flags[peer].  Only the row-pattern kernel implements it (spmv_supports_halo_wait()).
+constexpr int P2P_MAXW = 16;   // ranks on one NVSwitch box
+// Lives in cudaMalloc memory on each rank and is IPC-mapped by every peer (dist.cu).
+struct P2PBlock {
+    double   red[2][P2P_MAXW][2];     // all-reduce slots [parity][source rank][2 values]
+    uint32_t red_flag[2][P2P_MAXW];   // sequence number whose values sit in red[parity][source]
+    uint32_t halo_flag[P2P_MAXW];     // halo_flag[source] = sequence number of its last finished push
+    uint32_t err;                     // a spin loop timed out
+    uint32_t ticket;                  // last-CTA ticket of halo_push_kernel
+};
 struct HaloWait {
     const uint32_t* flags;     // [world] sequence numbers published by the peers (this rank's memory)
     const int*      recv_cnt;  // [world]
@@ -231,6 +240,11 @@ struct HaloWait {
     uint32_t        seq;
     unsigned        n_before;  // list positions below this need no halo
     uint32_t*       err;       // set when a wait times out
+    // optional: the kernel's last CTA pushes the two fused dot products straight into every peer's
+    // all-reduce slots (sequence red_seq) instead of leaving them for a separate all-reduce launch
+    P2PBlock* const* peer_blk; // [world] (nullptr: no push)
+    int              me;
+    uint32_t         red_seq;
 };
 bool spmv_supports_halo_wait(const Csr* c, const double* vals);
 int  launch_spmv_halo(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
@@ -339,6 +353,50 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
             "r"(smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// ---- peer-memory primitives (system-scope release/acquire over NVLink-mapped memory) -------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spins until *p has reached seq; gives up after ~2^32 clocks and reports through *err
+__device__ __forceinline__ void wait_seq(const uint32_t* p, uint32_t seq, uint32_t* err) {
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(p) - seq) < 0) {
+        if (clock64() - t0 > (1ll << 32)) { atomicExch(err, 1u); break; }
+        __nanosleep(20);
+    }
+}
+// one thread: deposit two partial sums in every rank's slot (own included) and publish `seq`
+__device__ __forceinline__ void p2p_push2(ab::P2PBlock* const* peer_blk, int world, int me, uint32_t seq, double v0, double v1) {
+    const int par = seq & 1u;
+    for (int p = 0; p < world; ++p) {
+        ab::P2PBlock* dst = peer_blk[p];
+        dst->red[par][me][0] = v0;
+        dst->red[par][me][1] = v1;
+    }
+    __threadfence_system();
+    for (int p = 0; p < world; ++p) st_release_sys(&peer_blk[p]->red_flag[par][me], seq);
+}
+// whole CTA: wait until every rank's contribution `seq` sits in MY block, sum in rank order (same bits
+// on every rank and in every CTA).  sh2 = 2 doubles of shared memory.
+__device__ __forceinline__ void p2p_wait_sum2(ab::P2PBlock* blk, int world, uint32_t seq, double* sh2, double& s0, double& s1) {
+    const int par = seq & 1u;
+    if ((int)threadIdx.x < world) wait_seq(&blk->red_flag[par][threadIdx.x], seq, &blk->err);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a0 = 0.0, a1 = 0.0;
+        const volatile double* r = &blk->red[par][0][0];
+        for (int p = 0; p < world; ++p) { a0 += r[2 * p]; a1 += r[2 * p + 1]; }
+        sh2[0] = a0; sh2[1] = a1;
+    }
+    __syncthreads();
+    s0 = sh2[0]; s1 = sh2[1];
 }
 
 __device__ __forceinline__ double2 ldg_stream_d2(const double2* p) {

@@ -88,16 +88,7 @@ static int nccl_load() {
                             g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "nccl error"); \
     } while (0)
 
-constexpr int MAXW = 16;   // ranks on one NVSwitch box
-
-// Lives in cudaMalloc memory on each rank and is IPC-mapped by every peer.
-struct P2PBlock {
-    double   red[2][MAXW][2];     // all-reduce slots [parity][source rank][2 values]
-    uint32_t red_flag[2][MAXW];   // sequence number whose values sit in red[parity][source]
-    uint32_t halo_flag[MAXW];     // halo_flag[source] = sequence number of its last finished push
-    uint32_t err;                 // a spin loop timed out
-    uint32_t ticket;              // last-CTA ticket of halo_push_kernel
-};
+constexpr int MAXW = P2P_MAXW;   // ranks on one NVSwitch box
 
 struct DistCsr {
     Csr* loc = nullptr;            // re-indexed local block: m = nloc, n = nloc + next
@@ -212,22 +203,9 @@ __global__ void pack_kernel(const int32_t* __restrict__ idx, const double* __res
     if (k < n) buf[k] = x[idx[k]];
 }
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// spins until *p has reached seq; gives up after ~2^31 clocks and reports through *err
-__device__ __forceinline__ void wait_seq(const uint32_t* p, uint32_t seq, uint32_t* err) {
-    const long long t0 = clock64();
-    while ((int32_t)(ld_acquire_sys(p) - seq) < 0) {
-        if (clock64() - t0 > (1ll << 32)) { atomicExch(err, 1u); break; }
-        __nanosleep(20);
-    }
-}
+using abd::st_release_sys;
+using abd::ld_acquire_sys;
+using abd::wait_seq;
 
 // Gathers this rank's boundary values and stores them into the consumers' halo tails over NVLink
 // (peer_x[p] is peer p's extended vector at the offset reserved for this rank); the last CTA then
@@ -287,6 +265,99 @@ __global__ void p2p_allreduce2_kernel(double* vals, P2PBlock* blk, P2PBlock* con
             if (fin_which == 0) cg_init_fin(s, tol, s0, s1);
             else if (!s->done) cg_update_fin(s, parity, s0, s1, s->bad != 0);
         }
+    }
+}
+
+// ---- CG vector kernels with the all-reduces folded in (peer-memory path, scaled form, x deferred) -----
+// K2': prologue = wait for every rank's <p,Ap> partial (pushed by the SpMV's last CTA), epilogue = the
+// last CTA pushes this rank's <r,r> partial.  Every CTA derives the same alpha from the same sums.
+static __global__ void __launch_bounds__(EW_THREADS)
+cgs_update_p2p_kernel(const double* __restrict__ Ap, double* __restrict__ r, size_t n, int parity, SolveScal* s,
+                      double* partials, uint32_t* ticket, P2PBlock* blk, P2PBlock* const* __restrict__ peer_blk, int world,
+                      int me, uint32_t seq_in, uint32_t seq_out) {
+    __shared__ double sh[32];
+    __shared__ double sh2[2];
+    if (s->done) return;
+    double pAp, yy;
+    abd::p2p_wait_sum2(blk, world, seq_in, sh2, pAp, yy);
+    const double rz = s->rz[parity];
+    const bool bad = !(pAp > 0.0) || !isfinite(pAp) || !isfinite(rz);
+    const double alpha = bad ? 0.0 : rz / pAp;
+    double a0 = 0.0;
+    const size_t n2 = n >> 1;
+    const double2* Ap2 = reinterpret_cast<const double2*>(Ap);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+        double2 av = Ap2[i], rv = r2[i];
+        rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+        r2[i] = rv;
+        a0 = fma(rv.x, rv.x, a0); a0 = fma(rv.y, rv.y, a0);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const size_t i = n - 1;
+        const double rv = fma(-alpha, Ap[i], r[i]);
+        r[i] = rv;
+        a0 = fma(rv, rv, a0);
+    }
+    double mine[1];
+    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
+    abd::grid_reduce<EW_THREADS, 1>(mine, partials, ticket, sh, [=](const double(&t)[1]) {
+        s->alpha = alpha;
+        s->bad = bad ? 1 : 0;
+        s->dots[0] = pAp; s->dots[1] = yy;
+        abd::p2p_push2(peer_blk, world, me, seq_out, t[0], t[0]);
+    });
+}
+
+// K3': prologue = wait for every rank's <r,r> partial; x += alpha p ; p = r + beta p ; the LAST CTA to
+// finish applies the CG scalar logic (cg_update_fin) — by then every CTA has read the old state.
+static __global__ void __launch_bounds__(EW_THREADS)
+cgs_direction_p2p_kernel(const double* __restrict__ r, double* __restrict__ p, double* __restrict__ x, size_t n, int parity,
+                         SolveScal* s, uint32_t* ticket, P2PBlock* blk, int world, uint32_t seq_in) {
+    __shared__ double sh2[2];
+    __shared__ bool s_last;
+    if (s->done) return;                       // K2' did not run either: nothing is owed
+    double rr, rr_dup;
+    abd::p2p_wait_sum2(blk, world, seq_in, sh2, rr, rr_dup);
+    const bool bad = s->bad != 0;
+    const double alpha = s->alpha, rz_old = s->rz[parity];
+    const bool stop = bad || !isfinite(rr) || (s->thr >= 0.0 && rr <= s->thr);   // what cg_update_fin will decide
+    const double beta = rr / rz_old;
+    const size_t n2 = n >> 1;
+    const double2* r2 = reinterpret_cast<const double2*>(r);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    double2* x2 = reinterpret_cast<double2*>(x);
+    if (!stop) {
+        for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+            double2 rv = r2[i], pv = p2[i], xv = x2[i];
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            pv.x = fma(beta, pv.x, rv.x);  pv.y = fma(beta, pv.y, rv.y);
+            x2[i] = xv;
+            p2[i] = pv;
+        }
+    } else {
+        for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+            double2 pv = p2[i], xv = x2[i];
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            x2[i] = xv;
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const size_t i = n - 1;
+        const double pv = p[i];
+        x[i] = fma(alpha, pv, x[i]);
+        if (!stop) p[i] = fma(beta, pv, r[i]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        *ticket = 0;
+        cg_update_fin(s, parity, rr, rr, bad);
     }
 }
 
@@ -350,8 +421,12 @@ static int allreduce2_fin(DistCsr* d, SolveScal* s, int which, int parity, doubl
 }
 
 // y = A_local [x_owned ; halo], halo exchange overlapped with the interior tiles when possible
-static int dist_spmv_dev(DistCsr* d, const double* vals, double* y, const double* dotvec, double* dots, const int* done) {
+// push_seq != 0: the SpMV's last CTA pushes the fused dots into the peers' all-reduce slots under that
+// sequence number (only honoured on the one-launch path; *pushed tells the caller whether it happened)
+static int dist_spmv_dev(DistCsr* d, const double* vals, double* y, const double* dotvec, double* dots, const int* done,
+                         uint32_t push_seq = 0, bool* pushed = nullptr) {
     Csr* c = d->loc;
+    if (pushed) *pushed = false;
     AB_TRY(halo_begin(d));
     const bool split = g_world > 1 && d->p2p && d->tiles_int && d->n_bnd > 0;
     if (!split) {
@@ -361,6 +436,10 @@ static int dist_spmv_dev(DistCsr* d, const double* vals, double* y, const double
     if (d->tiles_all && d->next > 0 && opt("dist_fused_wait", 1.0) != 0.0 && spmv_supports_halo_wait(c, vals)) {
         // one launch: interior tiles, in-kernel acquire of the peers' halo flags, boundary tiles
         HaloWait hw{d->blk->halo_flag, d->d_recv_cnt, g_world, d->halo_seq, (unsigned)d->n_int, &d->blk->err};
+        if (push_seq && dotvec) {
+            hw.peer_blk = d->d_peer_blk; hw.me = g_rank; hw.red_seq = push_seq;
+            if (pushed) *pushed = true;
+        }
         return launch_spmv_halo(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_all,
                                 d->n_int + d->n_bnd, hw);
     }
@@ -451,7 +530,20 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
         int chunk = maxit - it < check ? maxit - it : check;
         for (int k = 0; k < chunk; ++k, ++it) {
             const int parity = it & 1;
-            AB_TRY(dist_spmv_dev(d, vals, Ap, p, s->dots, &s->done));
+            // fully fused iteration (peer-memory path, scaled form, row-pattern SpMV): 4 launches — halo push,
+            // SpMV (+ halo wait + push of <p,Ap>), K2' (wait, r update, push of <r,r>), K3' (wait, x/p, scalars)
+            const bool fuse = raw && scaled && defer_x && d->p2p && opt("dist_fused_reduce", 1.0) != 0.0;
+            bool pushed = false;
+            AB_TRY(dist_spmv_dev(d, vals, Ap, p, s->dots, &s->done, fuse ? d->red_seq + 1 : 0, &pushed));
+            if (pushed) {
+                const uint32_t seq1 = ++d->red_seq, seq2 = ++d->red_seq;
+                cgs_update_p2p_kernel<<<g, EW_THREADS, 0, stream()>>>(Ap, r, n, parity, s, c->partials, c->ticket, d->blk,
+                                                                      d->d_peer_blk, g_world, g_rank, seq1, seq2);
+                AB_LAUNCH_CHECK();
+                cgs_direction_p2p_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, s, c->ticket, d->blk, g_world, seq2);
+                AB_LAUNCH_CHECK();
+                continue;
+            }
             if (raw) AB_TRY(allreduce2(d, s->dots));
             if (scaled) cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, raw, defer_x);
             else cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, raw);

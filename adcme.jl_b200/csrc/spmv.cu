@@ -637,6 +637,24 @@ spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__
         // boundary tiles one per CTA (run = 1): they are few, the tail must be as short as possible
         rowpat_walk<R, LIST, true>(rowcode, s_ent, s_info, x, y, m, nb, ntiles, 1u, tile_list, dotvec, dot, dot2);
     }
+    if (LIST && hw.peer_blk) {
+        // distributed CG: the last CTA hands this rank's two partial sums straight to every peer's
+        // all-reduce slots; the consumer kernel (K2) waits for all of them in its prologue
+        if (dotvec) {
+            double mine[2];
+            mine[0] = abd::block_sum<R>(dot, s_red);
+            mine[1] = abd::block_sum<R>(dot2, s_red);
+            P2PBlock* const* pb = hw.peer_blk;
+            const int world = hw.world, me = hw.me;
+            const uint32_t rseq = hw.red_seq;
+            abd::grid_reduce<R, 2>(mine, partials, ticket, s_red, [=](const double(&tot)[2]) {
+                dot_result[0] = tot[0];
+                dot_result[1] = tot[1];
+                abd::p2p_push2(pb, world, me, rseq, tot[0], tot[1]);
+            });
+        }
+        return;
+    }
     AB_TILE_EPILOGUE(R)
 }
 
