@@ -532,7 +532,10 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
             const int parity = it & 1;
             // fully fused iteration (peer-memory path, scaled form, row-pattern SpMV): 4 launches — halo push,
             // SpMV (+ halo wait + push of <p,Ap>), K2' (wait, r update, push of <r,r>), K3' (wait, x/p, scalars)
-            const bool fuse = raw && scaled && defer_x && d->p2p && opt("dist_fused_reduce", 1.0) != 0.0;
+            // Measured at 512^3 (same box A/B): N=2 902 vs 880 it/s with the reductions folded in, N=8 2855 vs
+            // 2994 — with eight ranks the 1184 CTAs of K2'/K3' all polling the same eight flag words slow the
+            // arrival of the remote stores more than the two saved launches return.  Default: on for <= 2 ranks.
+            const bool fuse = raw && scaled && defer_x && d->p2p && opt("dist_fused_reduce", g_world <= 2 ? 1.0 : 0.0) != 0.0;
             bool pushed = false;
             AB_TRY(dist_spmv_dev(d, vals, Ap, p, s->dots, &s->done, fuse ? d->red_seq + 1 : 0, &pushed));
             if (pushed) {
