@@ -66,3 +66,54 @@ def test_gloo_world2_plumbing():
     assert lo0 == 0 and lo1 == hi0 + 1 and hi1 == 16 ** 3 - 1
     assert mx0 == mx1 == 20.0
     assert tot0 == tot1 == 16 ** 3
+
+
+# ---------------------------------------------------------------------------------------------
+# host mirror logic that needs no device: Julia-style index arguments, spdiag / spzero triplets,
+# Jacobian-handle reuse decision, option defaults (src/sparse.jl:303-314,540-575,631-658; options.jl)
+def test_julia_style_index_arguments(pkg):
+    import importlib
+
+    st = importlib.import_module(pkg.__name__ + ".structure")
+    il = st._index_list
+    assert il(slice(None), 5)[0].tolist() == [1, 2, 3, 4, 5] and il(None, 3)[0].tolist() == [1, 2, 3]
+    assert il(slice(2, 3), 10)[0].tolist() == [2, 3]                  # 2:3 is inclusive, 1-based
+    assert il(slice(1, 9, 4), 10)[0].tolist() == [1, 5, 9]            # 1:4:9
+    assert il(7, 10) == (pytest.approx(np.array([7])), True)          # integer index squeezes the dimension
+    assert il(np.array([False, True, True]), 3)[0].tolist() == [2, 3]  # findall(mask)
+    assert il([4, 1], 5)[0].tolist() == [4, 1] and il(range(2, 5), 9)[0].tolist() == [2, 3, 4]
+
+
+def test_spdiag_spzero_triplets_without_device(pkg):
+    A = pkg.spdiag(4)
+    assert (A.m, A.n) == (4, 4) and np.asarray(A.ii).tolist() == [1, 2, 3, 4] and np.asarray(A.vv).tolist() == [1.0] * 4
+    D = pkg.spdiag(np.array([3.0, 5.0]))
+    assert D._diag and np.asarray(D.jj).tolist() == [1, 2]
+    B = pkg.spdiag(5, (0, np.arange(5.0)), (-2, np.ones(3)), (1, 2 * np.ones(4)))     # sparse.jl:631-658
+    dense = np.zeros((5, 5))
+    np.add.at(dense, (np.asarray(B.ii) - 1, np.asarray(B.jj) - 1), np.asarray(B.vv))
+    assert np.array_equal(dense, np.diag(np.arange(5.0)) + np.diag(np.ones(3), -2) + np.diag(2 * np.ones(4), 1))
+    with pytest.raises(ValueError):
+        pkg.spdiag(5, (0, np.ones(4)))
+    Z = pkg.spzero(3, 7)
+    assert Z.shape == (3, 7) and len(Z.vv) == 0
+    with pytest.raises(ValueError):
+        pkg.hcat(pkg.spzero(3, 2), pkg.spzero(4, 2))                  # shape check happens before any device call
+    with pytest.raises(ValueError):
+        pkg.spzero(3, 3) + pkg.spzero(3, 4)
+
+
+def test_newton_options_and_jacobian_reuse_decision(pkg):
+    import importlib
+
+    op = importlib.import_module(pkg.__name__ + ".optim")
+    pkg.reset_default_options()
+    nr = pkg.options.newton_raphson                                    # options.jl:20-44
+    assert (nr.max_iter, nr.rtol, nr.tol, nr.LM, nr.linesearch) == (100, 1e-12, 1e-12, 0.0, False)
+    ls = nr.linesearch_options
+    assert (ls.c1, ls.rho_hi, ls.rho_lo, ls.iterations, ls.alpha_initial) == (1e-4, 0.5, 0.1, 1000, 1.0)
+    i, j = np.array([1, 2]), np.array([1, 2])
+    assert op._same_indices(i, i) and op._same_indices(i, i.copy()) and not op._same_indices(i, np.array([1, 3]))
+    assert not op._same_indices(i, np.array([1, 2, 3])) and not op._same_indices(i, None)
+    with pytest.raises(ValueError):
+        pkg.newton_raphson(lambda th, u: (u, None), np.ones((2, 2)))  # "Initial guess must be a vector"
