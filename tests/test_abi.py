@@ -80,3 +80,69 @@ def test_op_registry_mirrors_reference_names(pkg):
         pkg.load_system_op("sinkhorn_knopp")
     assert pkg.options.sparse.solver == "SparseLU" and pkg.options.sparse.auto_reorder is True
     assert pkg.options.mpi.solver == "BoomerAMG"
+
+
+# ---------------------------------------------------------------------------------------------
+# The three descriptions of the boundary must agree argument by argument: the header prototypes,
+# the ctypes table the tests bind with, and the ccall signatures of the Julia shim a maintainer adds.
+def _header_prototypes():
+    txt = open(os.path.join(REPO, "include", "adcme_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\b(int64_t|int|double|const char\*)\s+(ab_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        args = " ".join(args.split())
+        kinds = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    kinds.append("str" if re.match(r"const char\s*\*", a) else "ptr")
+                elif re.match(r"(u?int64_t)\b", a):
+                    kinds.append("i64")
+                elif re.match(r"(u?int32_t)\b", a):
+                    kinds.append("i32")
+                elif re.match(r"double\b", a):
+                    kinds.append("dbl")
+                elif re.match(r"(unsigned\s+)?int\b", a):
+                    kinds.append("int")
+                else:
+                    raise AssertionError(f"unclassified parameter '{a}' of {name}")
+        protos[name] = (ret, kinds)
+    return protos
+
+
+def test_ctypes_table_matches_header_prototypes(pkg):
+    protos = _header_prototypes()
+    assert set(protos) == set(pkg.SIGNATURES)
+    cmap = {C.c_int64: "i64", C.c_int32: "i32", C.c_int: "int", C.c_double: "dbl", C.c_void_p: "ptr", C.c_char_p: "str"}
+    rmap = {"int": C.c_int, "int64_t": C.c_int64, "double": C.c_double, "const char*": C.c_char_p}
+    for name, (ret, kinds) in protos.items():
+        res, args = pkg.SIGNATURES[name]
+        assert res is rmap[ret], name
+        got = [cmap[a] for a in args]
+        # int32_t and int are both 4-byte signed here; ctypes declares either
+        norm = lambda ks: ["int" if k == "i32" else k for k in ks]          # noqa: E731
+        assert norm(got) == norm(kinds), f"{name}: ctypes {got} vs header {kinds}"
+
+
+def test_julia_shim_ccalls_match_header_prototypes():
+    protos = _header_prototypes()
+    src = open(os.path.join(REPO, "julia", "ADCMEB200.jl")).read()
+    calls = re.findall(r"ccall\(\(:(ab_[a-z0-9_]+),\s*LIB\),\s*([A-Za-z0-9_{}]+),\s*\(([^)]*)\)", src)
+    assert len(calls) >= 20
+    jl = {"Int64": "i64", "Int32": "int", "Cint": "int", "Cdouble": "dbl", "Cstring": "str"}
+    rj = {"Cint": "int", "Int64": "int64_t", "Cdouble": "double", "Cstring": "const char*"}
+    seen = set()
+    for name, ret, args in calls:
+        assert name in protos, f"{name} is not declared in the header"
+        seen.add(name)
+        hret, kinds = protos[name]
+        assert rj[ret] == hret, f"{name}: Julia returns {ret}, header {hret}"
+        toks = [t.strip() for t in args.split(",") if t.strip()]
+        got = ["ptr" if t.startswith(("Ptr{", "Ref{")) else jl[t] for t in toks]
+        norm = lambda ks: ["int" if k == "i32" else k for k in ks]          # noqa: E731
+        assert got == norm(kinds), f"{name}: Julia {got} vs header {kinds}"
+    # the shim covers the hot path and the widened rows
+    for must in ("ab_csr_from_coo", "ab_spmm", "ab_solve", "ab_solve_grad", "ab_asm_copy", "ab_compress", "ab_factorize",
+                 "ab_zero_out_row", "ab_scatter_update", "ab_sparse_indexing", "ab_spgemm", "ab_csr_axpby", "ab_newton_step"):
+        assert must in seen, must
