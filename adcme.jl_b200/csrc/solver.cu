@@ -645,6 +645,8 @@ static int solve_dev_impl(Csr* c, Method meth, const double* b, double* x, doubl
         AB_TRY(dense_lu_solve(c, b, x));
         AB_TRY(true_relres(c, b, x, &tr2));
         if (relres) *relres = tr2;
+        if (!isfinite(tr2))   // NaN / Inf in the matrix or the right-hand side: an error, never a silent NaN
+            return fail(AB_EBREAKDOWN, "Sparse solver failed: non-finite values in the matrix or right-hand side");
         return AB_OK;
     }
     if (fin.breakdown)
