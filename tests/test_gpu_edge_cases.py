@@ -125,5 +125,6 @@ def test_handle_misuse_and_shape_errors(pkg):
     with pytest.raises(ValueError):
         A @ np.ones(2)
     hc = C.c_int64(0)
-    rc = pkg.lib.ab_csr_axpby(A.handle(), 1.0, pkg.SparseTensor(np.array([1]), np.array([1]), np.array([1.0]), 3, 3).handle(), 1.0, C.byref(hc))
+    B = pkg.SparseTensor(np.array([1]), np.array([1]), np.array([1.0]), 3, 3)       # keep alive: its finaliser frees the handle
+    rc = pkg.lib.ab_csr_axpby(A.handle(), 1.0, B.handle(), 1.0, C.byref(hc))
     assert rc == -1 and b"does not match" in pkg.lib.ab_last_error()
