@@ -15,7 +15,7 @@ from .sparse import (                                           # noqa: F401
     compress_indices, factorize, find, rows, cols, values, mul, rmul, solve,
 )
 from .structure import (                                        # noqa: F401
-    zero_out_row, scatter_update, scatter_add, getindex, add, matmul, spdiag, spzero, hcat, vcat, hvcat, to_dense, dense_to_sparse, spsum,
+    zero_out_row, scatter_update, scatter_add, getindex, add, matmul, spdiag, spzero, hcat, vcat, hvcat, to_dense, dense_to_sparse, spsum, trisolve,
 )
 from .optim import NRResult, backtracking, newton_raphson, newton_raphson_with_grad   # noqa: F401
 from .extra import (                                            # noqa: F401

@@ -80,6 +80,8 @@ SIGNATURES = {
     "ab_dense_grad_values": (C.c_int, [_i64, _ptr, _i64, _i64, _ptr, _ptr]),
     "ab_csr_axpby": (C.c_int, [_i64, _dbl, _i64, _dbl, _ptr]),
     "ab_spgemm": (C.c_int, [_i64, _i64, C.c_int, _ptr]),
+    "ab_tri_solve": (C.c_int, [_i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "ab_tri_solve_grad": (C.c_int, [_i64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "ab_newton_step": (C.c_int, [_i64, _str, _ptr, _ptr, _dbl, _ptr, _ptr, _ptr, _dbl, C.c_int, _ptr]),
     "ab_vec_axpby": (C.c_int, [_i64, _dbl, _ptr, _dbl, _ptr, _ptr]),
     "ab_vec_dot": (C.c_int, [_i64, _ptr, _ptr, _ptr]),

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libadcme_b200.so")
-SOURCES = ["handles.cu", "assemble.cu", "spmv.cu", "spmm.cu", "solver.cu", "stencil.cu", "structure.cu", "newton.cu", "dist.cu"]
+SOURCES = ["handles.cu", "assemble.cu", "spmv.cu", "spmm.cu", "solver.cu", "stencil.cu", "structure.cu", "newton.cu", "trisolve.cu", "dist.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

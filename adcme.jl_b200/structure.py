@@ -517,6 +517,55 @@ def spsum(A, dims=None):
     raise ValueError("dims must be 1, 2 or None")
 
 
+def tri_solve_op(a, b, c, d):
+    """TriSolve(a, b, c, d) -> x   (TriSolve.cpp:14-19, TriSolve.h:1-20)."""
+    ka, pa = as_array(a, np.float64); kb, pb = as_array(b, np.float64)
+    kc, pc = as_array(c, np.float64); kd, pd = as_array(d, np.float64)
+    n = _n(kb)
+    x = empty_like_kind(kd, (n,), np.float64)
+    check(lib.ab_tri_solve(n, pa, pb, pc, pd, ptr(x)))
+    return x
+
+
+def tri_solve_grad(grad_x, x, a, b, c, d):
+    """TriSolveGrad(grad_x, x, a, b, c, d) -> (grad_a, grad_b, grad_c, grad_d)   (TriSolve.cpp:35-45, .h:22-37)."""
+    kg, pg = as_array(grad_x, np.float64); kx, px = as_array(x, np.float64)
+    ka, pa = as_array(a, np.float64); kb, pb = as_array(b, np.float64); kc, pc = as_array(c, np.float64)
+    n = _n(kb)
+    ga, gc = empty_like_kind(kg, (max(n - 1, 0),), np.float64), empty_like_kind(kg, (max(n - 1, 0),), np.float64)
+    gb, gd = empty_like_kind(kg, (n,), np.float64), empty_like_kind(kg, (n,), np.float64)
+    check(lib.ab_tri_solve_grad(n, pg, px, pa, pb, pc, ptr(ga), ptr(gb), ptr(gc), ptr(gd)))
+    return ga, gb, gc, gd
+
+
+def trisolve(a, b, c, d):
+    """trisolve(a, b, c, d) (sparse.jl:731-739): solve the tridiagonal system with sub-diagonal a, diagonal b,
+    super-diagonal c and right-hand side d."""
+    n = _n(b)
+    if not (_n(d) == n and _n(a) == n - 1 and _n(c) == n - 1):
+        raise ValueError("trisolve: need length(b) == length(d) == length(a)+1 == length(c)+1")
+    if any(_req(t) for t in (a, b, c, d)):
+        import torch
+
+        dev = next(t.device for t in (a, b, c, d) if _is_torch(t))
+        ts = [t if _is_torch(t) else torch.as_tensor(np.asarray(t, np.float64), device=dev) for t in (a, b, c, d)]
+
+        class TriSolveFn(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, a_, b_, c_, d_):
+                x = tri_solve_op(a_.detach(), b_.detach(), c_.detach(), d_.detach())
+                ctx.save_for_backward(x, a_, b_, c_)
+                return x
+
+            @staticmethod
+            def backward(ctx, gx):
+                x, a_, b_, c_ = ctx.saved_tensors
+                return tri_solve_grad(gx.contiguous(), x, a_.detach(), b_.detach(), c_.detach(), None)
+
+        return TriSolveFn.apply(*ts)
+    return tri_solve_op(a, b, c, d)
+
+
 def spdiag(*args):
     """spdiag(n) identity, spdiag(o) diagonal matrix from a vector, spdiag(n, k1=>v1, ...) banded
     matrix from (offset, values) pairs (sparse.jl:544-561, 631-658)."""

@@ -257,6 +257,15 @@ int ab_csr_axpby(int64_t ha, double alpha, int64_t hb, double beta, int64_t* out
  * Each C(i,j) is summed in k-ascending order (Eigen's column-major product order). */
 int ab_spgemm(int64_t ha, int64_t hb, int transpose_out, int64_t* out_h);
 
+/* ---- trisolve (src/sparse.jl:731-739; deps/CustomOps/TriSolve/TriSolve.h:1-37) — csrc/trisolve.cu -----
+ * a[n-1] sub-diagonal (a[i-1] multiplies x[i-1] in row i), b[n] diagonal, c[n-1] super-diagonal, d[n] rhs.
+ * Device form: parallel cyclic reduction (ceil(log2 n) streaming sweeps).  A zero pivot / non-finite
+ * result returns AB_EBREAKDOWN.  Gradient: grad_d = solve of the transposed system with grad_x;
+ * grad_a[i-1] = -grad_d[i] x[i-1], grad_b[i] = -grad_d[i] x[i], grad_c[i] = -grad_d[i] x[i+1]. */
+int ab_tri_solve(int64_t n, const double* a, const double* b, const double* c, const double* d, double* x);
+int ab_tri_solve_grad(int64_t n, const double* grad_x, const double* x, const double* a, const double* b,
+                      const double* c, double* grad_a, double* grad_b, double* grad_c, double* grad_d);
+
 /* ---- Newton-Raphson inner loop on the device — csrc/newton.cu ----------
  * src/optim.jl:462-592 (newton_raphson), :364-426 (backtracking).  The residual/Jacobian callback
  * stays in the host language; the linear solve, the update u - step*delta, ||r|| and the

@@ -280,6 +280,38 @@ def sparse_to_dense(ij, vv, m, n):
     return A.reshape(m, n)
 
 
+def tri_solve(a, b, c, d):
+    """TriSolve_forward (deps/CustomOps/TriSolve/TriSolve.h:1-20): the Thomas algorithm, line by line."""
+    a, b, c, d = _f64(a), _f64(b), _f64(c), _f64(d)
+    n = len(b)
+    B, D = b.copy(), d.copy()
+    for i in range(1, n):
+        w = a[i - 1] / B[i - 1]
+        B[i] = B[i] - w * c[i - 1]
+        D[i] = D[i] - w * D[i - 1]
+    X = np.zeros(n)
+    if n:
+        X[n - 1] = D[n - 1] / B[n - 1]
+    for i in range(n - 2, -1, -1):
+        X[i] = (D[i] - c[i] * X[i + 1]) / B[i]
+    return X
+
+
+def tri_solve_grad(grad_x, x, a, b, c):
+    """TriSolve_backward (TriSolve.h:22-37) -> (grad_a, grad_b, grad_c, grad_d)."""
+    x = _f64(x)
+    n = len(x)
+    gd = tri_solve(c, b, a, grad_x)
+    ga, gb, gc = np.zeros(max(n - 1, 0)), np.zeros(n), np.zeros(max(n - 1, 0))
+    for i in range(n):
+        if i > 0:
+            ga[i - 1] = -gd[i] * x[i - 1]
+        gb[i] = -gd[i] * x[i]
+        if i < n - 1:
+            gc[i] = -gd[i] * x[i + 1]
+    return ga, gb, gc, gd
+
+
 def _csc_from_triplets(ii, jj, vv, m, n, base):
     """Eigen setFromTriplets into a column-major matrix = our CSR restatement with the roles of the
     two indices swapped: -> (colptr, rowind, values), rows sorted, duplicates summed in input order."""

@@ -377,3 +377,42 @@ def test_dense_to_sparse_reference_test(pkg):
     assert np.array_equal(pkg.SparseTensor(B).toarray(), B)            # SparseTensor(A::Array)
     assert pkg.dense_to_sparse(np.zeros((3, 4))).query()[2] == 0
     assert np.array_equal(pkg.to_dense(S), B)
+
+
+# ======================================================================== trisolve
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 1000, 4097, 300000])
+def test_trisolve_matches_oracle(pkg, orc, n):
+    rng = np.random.default_rng(233)
+    a, c = rng.uniform(size=max(n - 1, 0)), rng.uniform(size=max(n - 1, 0))
+    b, d = rng.uniform(size=n) + 10, rng.uniform(size=n)
+    op = pkg.load_system_op("tri_solve")
+    x = op(a, b, c, d)
+    x0 = orc.tri_solve(a, b, c, d)
+    assert np.max(np.abs(x - x0)) <= 1e-10 * np.max(np.abs(x0))       # cyclic reduction vs Thomas: rounding only
+    g = rng.standard_normal(n)
+    ga, gb, gc, gd = op.grad(g, x, a, b, c, d)
+    ga0, gb0, gc0, gd0 = orc.tri_solve_grad(g, x0, a, b, c)
+    for u, v in ((ga, ga0), (gb, gb0), (gc, gc0), (gd, gd0)):
+        assert u.shape == v.shape and (v.size == 0 or np.max(np.abs(u - v)) <= 1e-10 * np.max(np.abs(v)))
+
+
+def test_trisolve_reference_test_autograd_and_errors(pkg):
+    import torch
+
+    rng = np.random.default_rng(233)
+    n = 10                                                             # test/sparse.jl:352-364
+    a, b, c, d = rng.uniform(size=n - 1), rng.uniform(size=n) + 10, rng.uniform(size=n - 1), rng.uniform(size=n)
+    A = np.diag(b) + np.diag(a, -1) + np.diag(c, 1)
+    u = pkg.trisolve(a, b, c, d)
+    assert np.linalg.norm(u - np.linalg.solve(A, d)) < 1e-12
+    bt = torch.tensor(b, device="cuda", requires_grad=True)
+    dt = torch.tensor(d, device="cuda", requires_grad=True)
+    x = pkg.trisolve(a, bt, c, dt)
+    x.sum().backward()
+    lam = np.linalg.solve(A.T, np.ones(n))
+    assert np.allclose(dt.grad.cpu().numpy(), lam, rtol=1e-10) and np.allclose(bt.grad.cpu().numpy(), -lam * u, rtol=1e-10)
+    with pytest.raises(ValueError):
+        pkg.trisolve(a, b, c[:-1], d)
+    with pytest.raises(pkg.ADCMEError) as e:
+        pkg.trisolve(np.zeros(2), np.zeros(3), np.zeros(2), np.ones(3))       # singular: zero pivot
+    assert e.value.code == -6

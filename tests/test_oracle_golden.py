@@ -260,3 +260,22 @@ def test_newton_oracle_golden(orc, golden):
     assert np.allclose(y, 2.0, rtol=1e-12)
     gth = orc.newton_adjoint_grad(-sp.identity(5), sp.diags(3 * y ** 2), np.ones(5))
     assert np.allclose(gth, r["expect_grad_each"], rtol=1e-12)
+
+
+def test_trisolve_oracle_vs_dense_and_fd(orc):
+    rng = np.random.default_rng(233)                          # test/sparse.jl:352-364
+    n = 10
+    a, c, b, d = rng.uniform(size=n - 1), rng.uniform(size=n - 1), rng.uniform(size=n) + 10, rng.uniform(size=n)
+    A = np.diag(b) + np.diag(a, -1) + np.diag(c, 1)
+    x = orc.tri_solve(a, b, c, d)
+    assert np.linalg.norm(x - np.linalg.solve(A, d)) < 1e-13
+    g = rng.standard_normal(n)                                # loss = <g, x>
+    ga, gb, gc, gd = orc.tri_solve_grad(g, x, a, b, c)
+    assert np.allclose(gd, np.linalg.solve(A.T, g), rtol=1e-12)
+    eps = 1e-6
+    for arr, grad, k in ((a, ga, 3), (b, gb, 4), (c, gc, 5), (d, gd, 6)):
+        p = arr.copy(); p[k] += eps
+        args = {id(a): a, id(b): b, id(c): c, id(d): d}
+        args[id(arr)] = p
+        fd = (g @ orc.tri_solve(args[id(a)], args[id(b)], args[id(c)], args[id(d)]) - g @ x) / eps
+        assert abs(fd - grad[k]) <= 1e-5 * max(1.0, abs(grad[k]))
