@@ -11,7 +11,7 @@ module ADCMEB200
 using SparseArrays
 export B200SparseTensor, b200_spmm, b200_solve, b200_solve_grad, B200Assembler, b200_accumulate!,
        b200_assemble, b200_compress, b200_factorize, b200_fsolve, b200_zero_out_row, b200_scatter_update,
-       b200_getindex, b200_spgemm, b200_add, b200_newton_step
+       b200_getindex, b200_spgemm, b200_add, b200_trisolve, b200_newton_step
 
 const LIB = get(ENV, "ADCME_B200_LIB", joinpath(@__DIR__, "..", "adcme.jl_b200", "libadcme_b200.so"))
 
@@ -197,6 +197,14 @@ function b200_add(a::B200SparseTensor, b::B200SparseTensor, alpha::Real=1.0, bet
     h = Ref{Int64}(0)
     chk(ccall((:ab_csr_axpby, LIB), Cint, (Int64, Cdouble, Int64, Cdouble, Ref{Int64}), a.h, alpha, b.h, beta, h))
     h[]
+end
+
+"trisolve(a, b, c, d) — src/sparse.jl:731-739."
+function b200_trisolve(a::Vector{Float64}, b::Vector{Float64}, c::Vector{Float64}, d::Vector{Float64})
+    x = similar(d)
+    chk(ccall((:ab_tri_solve, LIB), Cint, (Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+              length(b), a, b, c, d, x))
+    x
 end
 
 # ---- Newton-Raphson inner loop (SURVEY §8f N3) — csrc/newton.cu; src/optim.jl:509-539 --------------
