@@ -129,6 +129,7 @@ _OPS = {
     "zero_out_row": (_st.zero_out_row_op, _st.zero_out_row_grad),
     "sparse_scatter_update": (_st.sparse_scatter_update_op, _st.sparse_scatter_update_grad),
     "sparse_indexing": (_st.sparse_indexing_op, _st.sparse_indexing_grad),
+    "sparse_least_square": (_st.sparse_least_square_op, _st.sparse_least_square_grad),
     "tri_solve": (_st.tri_solve_op, _st.tri_solve_grad),
     "sparse_concate": (_st.sparse_concate_op, _st.sparse_concate_grad),
     "sparse_sparse_mat_mul": (_st.sparse_sparse_mat_mul_op, None),

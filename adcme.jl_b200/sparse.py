@@ -375,8 +375,10 @@ def _resolve_method(method: str) -> str:
 
 
 def _solve_raw(A: SparseTensor, f, method: str):
-    if A.m != A.n:
-        raise NotImplementedError("non-square `\\` (sparse_least_square) is outside the hot path (SURVEY §2b)")
+    if A.m != A.n:                       # sparse.jl:418-431: non-square `\` is the least-squares solve (batched over rows of f)
+        from . import structure
+
+        return structure.least_square_raw(A, f)
     if len(_shape(f)) != 1:
         raise ValueError("sparse_solver: f must be rank 1 (SparseSolver.cpp:38)")
     if int(_shape(f)[0]) != A.m:
@@ -392,6 +394,12 @@ def backslash(A, f, method: str = "auto"):
     if isinstance(A, tuple):
         return solve(A, f)
     method = _resolve_method(method)
+    if A.m != A.n and _needs_grad(A.vv, f):
+        from . import structure
+
+        if A._h is not None and _is_torch(A.vv):
+            A._refresh_values(A.vv)
+        return structure.least_square_autograd(A, f)
     if _needs_grad(A.vv, f):
         import torch
 

@@ -517,6 +517,127 @@ def spsum(A, dims=None):
     raise ValueError("dims must be 1, 2 or None")
 
 
+# ---------------------------------------------------------------------- least squares  A \ f,  A tall
+def _normal_equations(A):
+    """(handle of A' , SparseTensor of M = A'A) on the device: ab_csr_transpose + ab_spgemm."""
+    sp = _sparse()
+    ht = C.c_int64(0)
+    check(lib.ab_csr_transpose(A.handle(), C.byref(ht)))
+    At = sp.SparseTensor.from_handle(ht.value)
+    hm = C.c_int64(0)
+    check(lib.ab_spgemm(At.handle(), A.handle(), 0, C.byref(hm)))
+    return At, sp.SparseTensor.from_handle(hm.value)
+
+
+def _axpby(a, x, b, y):
+    kx, px = as_array(x, np.float64); ky, py = as_array(y, np.float64)
+    out = empty_like_kind(kx, (_n(kx),), np.float64)
+    check(lib.ab_vec_axpby(_n(kx), float(a), px, float(b), py, ptr(out)))
+    return out
+
+
+def least_square_raw(A, f):
+    """u = argmin ||A u - f||_2 for every row of f (SparseLeastSquare.h:10-32; the reference factors A with
+    SparseQR).  Here: normal equations M = A'A (SpGEMM on the device), rhs = A'f, Jacobi-PCG on the SPD M —
+    A must have full column rank, as SparseQR's solution being unique requires."""
+    sp = _sparse()
+    At, M = _normal_equations(A)
+    vec = len(tuple(f.shape)) == 1
+    rows = [f] if vec else [f[i] for i in range(int(f.shape[0]))]
+    outs = []
+    for fi in rows:
+        if int(fi.shape[0]) != A.m:
+            raise ValueError("dimension mismatch")
+        rhs = sp._spmm_raw(At, fi if not _is_torch(fi) else fi.contiguous(), False)
+        outs.append(sp._solve_raw(M, rhs, "CG"))
+    if vec:
+        return outs[0]
+    if _is_torch(outs[0]):
+        import torch
+
+        return torch.stack(outs, dim=0)
+    return np.stack(outs, axis=0)
+
+
+def least_square_grad(A, grad_u, u, f):
+    """SparseLeastSquare backward (SparseLeastSquare.h:34-83), one batch row: x = (A'A)^-1 g ; grad_f = A x ;
+    grad_vv[k] = (f - A u)[i_k] x[j_k] - u[j_k] (A x)[i_k]  — two per-triplet outer-product gathers."""
+    sp = _sparse()
+    At, M = _normal_equations(A)
+    x = sp._solve_raw(M, grad_u, "CG")
+    gf = sp._spmm_raw(A, x, False)
+    t = sp._spmm_raw(A, u, False)
+    resid = _axpby(1.0, f, -1.0, t)
+    T = A.query()[3]
+    kx, px = as_array(x, np.float64); ku, pu = as_array(u, np.float64)
+    kr, pr = as_array(resid, np.float64); kg, pg = as_array(gf, np.float64)
+    g1 = empty_like_kind(kx, (T,), np.float64); g2 = empty_like_kind(kx, (T,), np.float64)
+    check(lib.ab_spmm_grad_values(A.handle(), pr, px, 1, ptr(g1)))        # (f - A u)[i_k] * x[j_k]
+    check(lib.ab_spmm_grad_values(A.handle(), pg, pu, 1, ptr(g2)))        # (A x)[i_k] * u[j_k]
+    return _axpby(1.0, g1, -1.0, g2), gf
+
+
+def least_square_autograd(A, f):
+    """Differentiable least-squares `\\` (gradients for the values and the right-hand side)."""
+    import torch
+
+    dev = A.vv.device if _is_torch(A.vv) else f.device
+    vv = A.vv if _is_torch(A.vv) else torch.as_tensor(np.asarray(A.vv, np.float64), device=dev)
+    if not _is_torch(f):
+        f = torch.as_tensor(np.asarray(f, np.float64), device=dev)
+
+    class LeastSquareFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, vv_, f_):
+            u = least_square_raw(A, f_.detach())
+            ctx.save_for_backward(u, f_)
+            return u
+
+        @staticmethod
+        def backward(ctx, gu):
+            u, f_ = ctx.saved_tensors
+            gu = gu.contiguous()
+            if f_.dim() == 1:
+                gvv, gf = least_square_grad(A, gu, u, f_.detach())
+                return gvv, gf
+            gvv, gfs = None, []
+            for l in range(f_.shape[0]):
+                g1, gf = least_square_grad(A, gu[l].contiguous(), u[l].contiguous(), f_[l].detach().contiguous())
+                gvv = g1 if gvv is None else gvv + g1
+                gfs.append(gf)
+            return gvv, torch.stack(gfs, 0)
+
+    return LeastSquareFn.apply(vv, f)
+
+
+def sparse_least_square_op(ii, jj, vv, ff, n):
+    """SparseLeastSquare(ii, jj, vv, ff, n) -> u ; ff is [nbatch, m] (SparseLeastSquare.cpp:11-18)."""
+    sp = _sparse()
+    m = int(ff.shape[-1])
+    A = sp.SparseTensor(ii, jj, vv, m, int(n))
+    return least_square_raw(A, ff)
+
+
+def sparse_least_square_grad(grad_u, u, ii, jj, vv, ff, n):
+    """SparseLeastSquareGrad -> (grad_ii, grad_jj, grad_vv, grad_ff, grad_n); batch rows accumulate into grad_vv."""
+    sp = _sparse()
+    m = int(ff.shape[-1])
+    A = sp.SparseTensor(ii, jj, vv, m, int(n))
+    if len(tuple(ff.shape)) == 1:
+        gvv, gf = least_square_grad(A, grad_u, u, ff)
+        return None, None, gvv, gf, None
+    gvv, gfs = None, []
+    for l in range(int(ff.shape[0])):
+        g1, gf = least_square_grad(A, grad_u[l], u[l], ff[l])
+        gvv = g1 if gvv is None else _axpby(1.0, gvv, 1.0, g1)
+        gfs.append(gf)
+    if _is_torch(gfs[0]):
+        import torch
+
+        return None, None, gvv, torch.stack(gfs, 0), None
+    return None, None, gvv, np.stack(gfs, 0), None
+
+
 def tri_solve_op(a, b, c, d):
     """TriSolve(a, b, c, d) -> x   (TriSolve.cpp:14-19, TriSolve.h:1-20)."""
     ka, pa = as_array(a, np.float64); kb, pb = as_array(b, np.float64)

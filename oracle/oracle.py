@@ -280,6 +280,38 @@ def sparse_to_dense(ij, vv, m, n):
     return A.reshape(m, n)
 
 
+def sparse_least_square(ii, jj, vv, ff, m, n):
+    """forward (deps/CustomOps/SparseLeastSquare/SparseLeastSquare.h:10-32): u = argmin ||A u - f|| per batch
+    row (the reference factors A with SparseQR; a dense QR-based lstsq gives the same minimiser)."""
+    A = np.zeros((m, n))
+    np.add.at(A, (_i64(ii) - 1, _i64(jj) - 1), _f64(vv))              # setFromTriplets sums duplicates
+    F = _f64(ff).reshape(-1, m)
+    U = np.stack([np.linalg.lstsq(A, F[l], rcond=None)[0] for l in range(F.shape[0])])
+    return U[0] if np.ndim(ff) == 1 else U
+
+
+def sparse_least_square_grad(grad_u, u, ii, jj, vv, ff, m, n):
+    """backward (SparseLeastSquare.h:34-83), the loops as written: M = A'A, x = M^-1 g, grad_f = A x,
+    grad_vv[k] += -t[i_k] x[j_k] + f[i_k] x[j_k] - u[j_k] * sum_r At(r, i_k) x[r]   (t = A u)."""
+    ii, jj = _i64(ii) - 1, _i64(jj) - 1
+    A = np.zeros((m, n))
+    np.add.at(A, (ii, jj), _f64(vv))
+    M = A.T @ A
+    G, Uu, F = _f64(grad_u).reshape(-1, n), _f64(u).reshape(-1, n), _f64(ff).reshape(-1, m)
+    gvv, gfs = np.zeros(len(ii)), []
+    for l in range(G.shape[0]):
+        t = A @ Uu[l]
+        x = np.linalg.solve(M, G[l])
+        gf = A @ x
+        gfs.append(gf)
+        for k in range(len(ii)):
+            gvv[k] += -t[ii[k]] * x[jj[k]]
+            gvv[k] += F[l][ii[k]] * x[jj[k]]
+            gvv[k] += -Uu[l][jj[k]] * float(A[ii[k], :] @ x)          # InnerIterator over column i_k of At
+    gfs = np.stack(gfs)
+    return gvv, (gfs[0] if np.ndim(ff) == 1 else gfs)
+
+
 def tri_solve(a, b, c, d):
     """TriSolve_forward (deps/CustomOps/TriSolve/TriSolve.h:1-20): the Thomas algorithm, line by line."""
     a, b, c, d = _f64(a), _f64(b), _f64(c), _f64(d)

@@ -416,3 +416,35 @@ def test_trisolve_reference_test_autograd_and_errors(pkg):
     with pytest.raises(pkg.ADCMEError) as e:
         pkg.trisolve(np.zeros(2), np.zeros(3), np.zeros(2), np.ones(3))       # singular: zero pivot
     assert e.value.code == -6
+
+
+# ======================================================================== least squares  A \ f,  A tall
+def test_least_square_golden_parity_and_autograd(pkg, orc, golden):
+    import torch
+
+    g = golden["least_squares_adjacent"]                               # test/sparse.jl:131-139
+    A = pkg.SparseTensor(np.array(g["ii"]), np.array(g["jj"]), np.array(g["vv"], float), g["m"], g["n"])
+    o = pkg.backslash(A, np.array(g["ff"], float))
+    assert np.linalg.norm(o - np.array(g["expect"])) < g["tol"]
+    rng = np.random.default_rng(233)
+    m, n, T = 300, 40, 2500
+    ii, jj, vv = rng.integers(1, m + 1, T), rng.integers(1, n + 1, T), rng.standard_normal(T)
+    ii[:n], jj[:n] = np.arange(1, n + 1), np.arange(1, n + 1)
+    vv[:n] += 8.0
+    F = rng.standard_normal((3, m))
+    op = pkg.load_system_op("sparse_least_square")
+    U = op(ii, jj, vv, F, n)                                           # batched: one solve per row of F
+    U0 = orc.sparse_least_square(ii, jj, vv, F, m, n)
+    assert U.shape == (3, n) and np.max(np.abs(U - U0)) <= 1e-9 * np.max(np.abs(U0))
+    Gu = rng.standard_normal((3, n))
+    r = op.grad(Gu, U0, ii, jj, vv, F, n)
+    gvv0, gf0 = orc.sparse_least_square_grad(Gu, U0, ii, jj, vv, F, m, n)
+    assert np.max(np.abs(r[2] - gvv0)) <= 1e-8 * np.max(np.abs(gvv0)) and np.max(np.abs(r[3] - gf0)) <= 1e-8 * np.max(np.abs(gf0))
+    vt = torch.tensor(vv, device="cuda", requires_grad=True)
+    ft = torch.tensor(F[0], device="cuda", requires_grad=True)
+    u = pkg.backslash(pkg.SparseTensor(ii, jj, vt, m, n), ft)
+    w = torch.tensor(Gu[0], device="cuda")
+    (u * w).sum().backward()
+    g1, gf1 = orc.sparse_least_square_grad(Gu[0], U0[0], ii, jj, vv, F[0], m, n)
+    assert np.max(np.abs(vt.grad.cpu().numpy() - g1)) <= 1e-8 * np.max(np.abs(g1))
+    assert np.max(np.abs(ft.grad.cpu().numpy() - gf1)) <= 1e-8 * np.max(np.abs(gf1))

@@ -279,3 +279,24 @@ def test_trisolve_oracle_vs_dense_and_fd(orc):
         args[id(arr)] = p
         fd = (g @ orc.tri_solve(args[id(a)], args[id(b)], args[id(c)], args[id(d)]) - g @ x) / eps
         assert abs(fd - grad[k]) <= 1e-5 * max(1.0, abs(grad[k]))
+
+
+def test_least_square_oracle_golden_and_fd(orc, golden):
+    g = golden["least_squares_adjacent"]                      # test/sparse.jl:131-139
+    u = orc.sparse_least_square(g["ii"], g["jj"], g["vv"], g["ff"], g["m"], g["n"])
+    assert np.linalg.norm(u - np.array(g["expect"])) < g["tol"]
+    rng = np.random.default_rng(233)
+    m, n, T = 9, 4, 30
+    ii, jj, vv = rng.integers(1, m + 1, T), rng.integers(1, n + 1, T), rng.standard_normal(T)
+    ii[:n], jj[:n] = np.arange(1, n + 1), np.arange(1, n + 1)          # full column rank
+    vv[:n] += 5.0
+    f, w = rng.standard_normal(m), rng.standard_normal(n)
+    u = orc.sparse_least_square(ii, jj, vv, f, m, n)
+    gvv, gf = orc.sparse_least_square_grad(w, u, ii, jj, vv, f, m, n)  # loss = <w, u>
+    eps = 1e-6
+    for k in (0, 7, 19):
+        v2 = vv.copy(); v2[k] += eps
+        fd = (w @ orc.sparse_least_square(ii, jj, v2, f, m, n) - w @ u) / eps
+        assert abs(fd - gvv[k]) <= 2e-5 * max(1.0, abs(gvv[k]))
+    f2 = f.copy(); f2[3] += eps
+    assert abs((w @ orc.sparse_least_square(ii, jj, vv, f2, m, n) - w @ u) / eps - gf[3]) <= 2e-5
