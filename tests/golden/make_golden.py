@@ -34,6 +34,13 @@ def main():
     n = g["newton_cuberoot_adjoint"]
     th = np.array(n["theta"])
     assert np.allclose(np.cbrt(th), n["expect_x"]) and np.allclose(th ** (-2 / 3) / 3, n["expect_grad"])
+    ls = g["least_squares_adjacent"]                               # test/sparse.jl:131-139
+    A = sp.coo_matrix((ls["vv"], (np.array(ls["ii"]) - 1, np.array(ls["jj"]) - 1)), shape=(ls["m"], ls["n"])).toarray()
+    assert np.allclose(np.linalg.lstsq(A, np.array(ls["ff"], float), rcond=None)[0], ls["expect"], atol=ls["tol"])
+    gi = g["get_index_bool_mask"]                                  # test/sparse.jl:316-321
+    M = np.diag(gi["diag"])
+    sel = np.flatnonzero(gi["idof"])
+    assert M[np.ix_(sel, sel)].tolist() == gi["expect_dense"]
     print("golden vectors consistent")
 
 
