@@ -95,6 +95,7 @@ SIGNATURES = {
     "ab_dist_csr_create": (C.c_int, [_i64, _i64, _i64, _i64, _ptr]),
     "ab_dist_spmv": (C.c_int, [_i64, _ptr, _ptr]),
     "ab_dist_solve": (C.c_int, [_i64, _str, _ptr, _ptr, _dbl, C.c_int, _ptr, _ptr]),
+    "ab_dist_solve_grad": (C.c_int, [_i64, _ptr, _ptr, _ptr, _ptr, _dbl, C.c_int, _ptr, _ptr]),
     "ab_dist_cg_fixed": (C.c_int, [_i64, _ptr, _ptr, C.c_int, _ptr]),
     "ab_dist_destroy": (C.c_int, [_i64]),
     "ab_timer_reset": (C.c_int, []),

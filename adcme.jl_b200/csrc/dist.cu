@@ -361,6 +361,16 @@ cgs_direction_p2p_kernel(const double* __restrict__ r, double* __restrict__ p, d
     }
 }
 
+// adjoint gradient of the distributed solve, per stored entry of the local block:
+// g[e] = -x[row_e] * u_ext[col_e]   (SparseSolver.h:60-68 restricted to the rows this rank owns; col_e is
+// the re-indexed column, so halo columns read the halo tail filled by the exchange)
+static __global__ void dist_grad_vals_kernel(const int32_t* __restrict__ entry_row, const int32_t* __restrict__ colind,
+                                             const double* __restrict__ x, const double* __restrict__ uext, size_t nnz,
+                                             double* __restrict__ g) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < nnz) g[e] = -x[entry_row[e]] * uext[colind[e]];
+}
+
 static int halo_begin(DistCsr* d) {
     if (g_world == 1) return AB_OK;
     if (d->p2p) {
@@ -943,6 +953,52 @@ int ab_dist_solve(int64_t dh, const char* method, const double* f, double* u, do
     if (tol <= 0) tol = opt("tol", 1e-10);   // Hypre tolerance in the reference: 1e-10 (MPITensor.h:66,91)
     if (maxit <= 0) maxit = (int)opt("maxit", 100000);
     return dist_solve_common(dh, f, u, tol, maxit, iters, relres);
+}
+
+// Adjoint of the distributed solve (replaces the backward of mpi_SparseTensor `\`, src/mpi.jl:493-508 with
+// mpiops.jl:65-83): x = A^{-T} grad_u = A^{-1} grad_u (CG asserts symmetry), grad_f = x (local rows),
+// grad_vals[e] = -x[row_e] * u[col_e] for every stored entry e of this rank's rows, in the order of the local
+// CSR the handle was created from; u at off-rank columns comes from one halo exchange.  Collective.
+int ab_dist_solve_grad(int64_t dh, const double* grad_u_, const double* u_, double* grad_vals_, double* grad_f_, double tol,
+                       int maxit, int* iters, double* relres) {
+    AB_TRY(ensure_device());
+    DistCsr* d = dist_get(dh);
+    if (!d) return AB_EHANDLE;
+    if (d->nloc && (!grad_u_ || (grad_vals_ && !u_))) return fail(AB_EINVAL, "null vector");
+    if (tol <= 0) tol = opt("tol", 1e-10);
+    if (maxit <= 0) maxit = (int)opt("maxit", 100000);
+    DevBuf<double> xbuf;
+    {
+        std::lock_guard<std::mutex> lk(big_lock());
+        AB_TRY(xbuf.alloc((size_t)d->nloc + 2));
+    }
+    AB_TRY(dist_solve_common(dh, grad_u_, xbuf.p, tol, maxit, iters, relres));      // device output: no staging
+    std::lock_guard<std::mutex> lk(big_lock());
+    Csr* c = d->loc;
+    if (grad_f_ && d->nloc) AB_CUDA(cudaMemcpyAsync(grad_f_, xbuf.p, (size_t)d->nloc * sizeof(double), cudaMemcpyDefault, stream()));
+    if (grad_vals_) {
+        AB_TRY(csr_ensure_work(c, 4));
+        AB_TRY(csr_ensure_entry_row(c));
+        if (d->nloc) AB_CUDA(cudaMemcpyAsync(d->xext, u_, (size_t)d->nloc * sizeof(double), cudaMemcpyDefault, stream()));
+        AB_TRY(halo_begin(d));
+        AB_TRY(halo_end(d));
+        Out<double> gv;
+        AB_TRY(gv.bind(grad_vals_, (size_t)c->nnz));
+        if (c->nnz) {
+            dist_grad_vals_kernel<<<(unsigned)((c->nnz + 255) / 256), 256, 0, stream()>>>(c->entry_row, c->colind, xbuf.p, d->xext,
+                                                                                         (size_t)c->nnz, gv.d);
+            AB_LAUNCH_CHECK();
+        }
+        AB_TRY(gv.commit());
+        if (g_world > 1 && d->p2p) {
+            // box-wide rendezvous: nobody may overwrite a halo tail that a slower rank is still reading
+            SolveScal* s = (SolveScal*)c->scal;
+            AB_TRY(allreduce2(d, s->red));
+            AB_TRY(check_p2p_err(d));
+        }
+    }
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    return AB_OK;
 }
 
 int ab_dist_cg_fixed(int64_t dh, const double* f, double* u, int iters, double* relres) {

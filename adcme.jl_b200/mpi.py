@@ -109,6 +109,17 @@ class mpi_SparseTensor:
         check(lib.ab_dist_solve(self._dh, solver.encode(), pb, ptr(u), tol, maxit, C.byref(it), C.byref(rr)))
         return u, it.value, rr.value
 
+    def solve_grad(self, grad_u_local, u_local, tol: float = 0.0, maxit: int = 0):
+        """Backward of `mpi_SparseTensor \\ b`: (grad of the local CSR values, per stored entry of this rank's
+        rows; grad_b_local).  Collective — every rank calls it."""
+        kg, pg = as_array(grad_u_local, np.float64)
+        ku, pu = as_array(u_local, np.float64)
+        nnz = self.local.query()[2]
+        gv = empty_like_kind(kg, (nnz,), np.float64)
+        gf = empty_like_kind(kg, (self.nloc,), np.float64)
+        check(lib.ab_dist_solve_grad(self._dh, pg, pu, ptr(gv), ptr(gf), tol, maxit, None, None))
+        return gv, gf
+
     def cg_fixed(self, b_local, iters: int):
         kb, pb = as_array(b_local, np.float64)
         u = empty_like_kind(kb, (self.nloc,), np.float64)

@@ -293,6 +293,12 @@ int ab_dist_solve(int64_t dh, const char* method, const double* f_local, double*
                   double tol, int maxit, int* iters, double* relres);
 int ab_dist_cg_fixed(int64_t dh, const double* f_local, double* u_local, int iters,
                      double* relres);
+/* adjoint of the distributed solve (collective): x = A^{-1} grad_u (CG: A symmetric), grad_f = x on the
+ * local rows, grad_vals[e] = -x[row_e]*u[col_e] for every stored entry e of this rank's rows in the order
+ * of the local CSR handle (u at off-rank columns arrives by one halo exchange).  Either output may be NULL. */
+int ab_dist_solve_grad(int64_t dh, const double* grad_u_local, const double* u_local,
+                       double* grad_vals_local /*[nnz_local]*/, double* grad_f_local /*[nloc]*/,
+                       double tol, int maxit, int* iters, double* relres);
 int ab_dist_destroy(int64_t dh);
 
 /* ---- timers (reference: MPITensor_Solve_Timer_*, MPITensor.cpp:15-21) -- */

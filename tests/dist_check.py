@@ -80,9 +80,18 @@ def main():
     ug, itg, rrg = D.solve(fg[glo:ghi + 1], tol=1e-12)
     u0 = spla.spsolve(G.tocsc(), fg)
     e5 = float(np.max(np.abs(ug - u0[glo:ghi + 1])) / np.max(np.abs(u0)))
-    ok4 = e4 <= 1e-13 and e5 <= 1e-9 and rrg <= 1e-12
+    # adjoint: x = G^-1 g (G symmetric), grad_f = x, grad_vals[e] = -x[row_e] u[col_e] over this rank's CSR entries
+    gg = rng.uniform(-1, 1, M)
+    gvals, gfl = D.solve_grad(gg[glo:ghi + 1], u0[glo:ghi + 1], tol=1e-13)
+    x0 = spla.spsolve(G.tocsc(), gg)
+    Gl = G[glo:ghi + 1].tocsr(); Gl.sort_indices()
+    rows_g = np.repeat(np.arange(glo, ghi + 1), np.diff(Gl.indptr))
+    gv0 = -x0[rows_g] * u0[Gl.indices]
+    e6 = float(np.max(np.abs(gfl - x0[glo:ghi + 1])) / np.max(np.abs(x0)))
+    e7 = float(np.max(np.abs(gvals - gv0)) / np.max(np.abs(gv0)))
+    ok4 = e4 <= 1e-13 and e5 <= 1e-9 and rrg <= 1e-12 and e6 <= 1e-9 and e7 <= 1e-9
     print(f"rank {rank}/{world}: general matrix rows [{glo},{ghi}] spmv_err {e4:.2e} solve iters {itg} relres {rrg:.2e} "
-          f"err vs direct {e5:.2e} {'OK' if ok4 else 'FAIL'}", flush=True)
+          f"err vs direct {e5:.2e} adjoint grad_f err {e6:.2e} grad_vals err {e7:.2e} {'OK' if ok4 else 'FAIL'}", flush=True)
     ok = ok and ok4
     D.close()
     t = torch.tensor([0 if ok else 1], device=dev)

@@ -773,6 +773,15 @@ def test_dist_path_world1_equals_single_gpu(pkg):
     r = C.c_double(0)
     pkg.check(pkg.lib.ab_cg_fixed(D.local.handle(), b.data_ptr(), u2.data_ptr(), 30, C.byref(r)))
     assert torch.equal(u1, u2)
+    # adjoint of the distributed solve == the single-GPU adjoint (per stored entry: the handle came from CSR)
+    g = torch.rand(N, dtype=torch.float64, device="cuda")
+    gv, gf = D.solve_grad(g, u, tol=1e-12)
+    gv1 = torch.empty(D.local.query()[2], dtype=torch.float64, device="cuda")
+    gf1 = torch.empty_like(g)
+    pkg.check(pkg.lib.ab_solve_grad(D.local.handle(), b"CG", g.data_ptr(), u.data_ptr(), gv1.data_ptr(), gf1.data_ptr(),
+                                    1e-12, 0, None, None))
+    assert float((gf - gf1).abs().max() / gf1.abs().max()) <= 1e-9
+    assert float((gv - gv1).abs().max() / gv1.abs().max()) <= 1e-9
     D.close()
 
 
