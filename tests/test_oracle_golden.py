@@ -300,3 +300,38 @@ def test_least_square_oracle_golden_and_fd(orc, golden):
         assert abs(fd - gvv[k]) <= 2e-5 * max(1.0, abs(gvv[k]))
     f2 = f.copy(); f2[3] += eps
     assert abs((w @ orc.sparse_least_square(ii, jj, vv, f2, m, n) - w @ u) / eps - gf[3]) <= 2e-5
+
+
+# ======================================================================== randomized oracle pinning (hypothesis)
+def test_oracle_assembly_and_compress_randomized(orc):
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 12), st.integers(1, 12), st.lists(st.tuples(st.integers(0, 11), st.integers(0, 11),
+                                                                     st.floats(-4, 4, allow_nan=False, width=32)), max_size=80))
+    def check(m, n, trips):
+        trips = [(i % m, j % n, float(v)) for i, j, v in trips]
+        ii = np.array([t[0] for t in trips], np.int64) + 1
+        jj = np.array([t[1] for t in trips], np.int64) + 1
+        vv = np.array([t[2] for t in trips], float)
+        rp, ci, va, slot = orc.coo_to_csr(ii, jj, vv, m, n, base=1)
+        D = np.zeros((m, n))
+        for i, j, v in trips:                      # input-order accumulation, like setFromTriplets
+            D[i, j] += v
+        R = np.zeros((m, n))
+        for r in range(m):
+            cols = ci[rp[r]:rp[r + 1]]
+            assert np.all(np.diff(cols) > 0)       # sorted, merged
+            R[r, cols] = va[rp[r]:rp[r + 1]]
+        assert np.array_equal(R, D)
+        for t, (i, j, _) in enumerate(trips):      # slot maps every triplet to its stored entry
+            e = slot[t]
+            assert ci[e] == j and rp[i] <= e < rp[i + 1]
+        # compress on the row-major sorted stream
+        order = np.lexsort((np.arange(len(trips)), jj, ii)) if trips else np.zeros(0, int)
+        idx2 = np.stack([ii[order] - 1, jj[order] - 1], 1) if trips else np.zeros((0, 2), np.int64)
+        oi, ov = orc.compress(idx2, vv[order] if trips else vv)
+        assert len(ov) == len(va) and (len(ov) == 0 or np.allclose(ov, va, rtol=1e-15, atol=1e-15))
+        assert all((ci[rp[r]:rp[r + 1]] == oi[oi[:, 0] == r, 1]).all() for r in range(m)) if len(ov) else True
+
+    check()
