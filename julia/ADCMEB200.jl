@@ -11,7 +11,9 @@ module ADCMEB200
 using SparseArrays
 export B200SparseTensor, b200_spmm, b200_solve, b200_solve_grad, B200Assembler, b200_accumulate!,
        b200_assemble, b200_compress, b200_factorize, b200_fsolve, b200_zero_out_row, b200_scatter_update,
-       b200_getindex, b200_spgemm, b200_add, b200_trisolve, b200_newton_step
+       b200_getindex, b200_spgemm, b200_add, b200_trisolve, b200_newton_step, b200_find, b200_dense_to_sparse,
+       b200_to_dense, b200_concat, b200_transpose, b200_poisson2d, b200_poisson3d, b200_dist_unique_id, b200_dist_init,
+       b200_dist_create, b200_dist_solve, b200_dist_solve_grad, b200_dist_spmv, b200_dist_destroy, b200_dist_finalize
 
 const LIB = get(ENV, "ADCME_B200_LIB", joinpath(@__DIR__, "..", "adcme.jl_b200", "libadcme_b200.so"))
 
@@ -216,5 +218,149 @@ function b200_newton_step(J::B200SparseTensor, r::Vector{Float64}, u::Vector{Flo
               J.h, method, r, u, step, unew, delta, rn, 0.0, 0, C_NULL))
     unew, delta, rn[]
 end
+
+# ---- gradients of the structural ops (the `...Grad` companions load_op_and_grad pairs with the forward) --
+"ZeroOutRowGrad: grad_vv from grad_ovv (ZeroOutRow.h:50-57)."
+function b200_zero_out_row_grad(indices::Array{Int64,2}, bd::Vector{Int64}, grad_ovv::Vector{Float64})
+    idx = permutedims(indices); N = size(indices, 1); g = Vector{Float64}(undef, N)
+    chk(ccall((:ab_zero_out_row_grad, LIB), Cint, (Int64, Ptr{Int64}, Ptr{Int64}, Int64, Ptr{Cdouble}, Int64, Ptr{Cdouble}),
+              N, idx, bd, length(bd), grad_ovv, length(grad_ovv), g))
+    g
+end
+"SparseScatterUpdateGrad: (grad_vv1, grad_vv2) from grad_nvv (SparseScatterUpdate.h:39-60)."
+function b200_scatter_update_grad(oii, ojj, un::Integer, m, n, ii::Vector{Int64}, jj::Vector{Int64}, grad_out::Vector{Float64})
+    g1, g2 = Vector{Float64}(undef, length(oii)), Vector{Float64}(undef, un)
+    chk(ccall((:ab_scatter_update_grad, LIB), Cint,
+              (Int64, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ptr{Cdouble}, Int64,
+               Ptr{Cdouble}, Ptr{Cdouble}),
+              length(oii), oii, ojj, un, m, n, ii, length(ii), jj, length(jj), grad_out, length(grad_out), g1, g2))
+    g1, g2
+end
+"SparseIndexingGrad: grad_vv1 (per input triplet of A) from grad_vv2 (SparseIndexing.h:66-83)."
+function b200_getindex_grad(s::B200SparseTensor, ii::Vector{Int64}, jj::Vector{Int64}, ii2::Vector{Int64}, jj2::Vector{Int64},
+                            grad_vv2::Vector{Float64})
+    g = Vector{Float64}(undef, s.T)
+    chk(ccall((:ab_sparse_indexing_grad, LIB), Cint,
+              (Int64, Ptr{Int64}, Int64, Ptr{Int64}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}, Int64, Ptr{Cdouble}),
+              s.h, ii, length(ii), jj, length(jj), ii2, jj2, grad_vv2, length(grad_vv2), g))
+    g
+end
+"SparseCompressGrad (SparseCompress.h:45-54)."
+function b200_compress_grad(indices::Array{Int64,2}, grad_nv::Vector{Float64})
+    idx = permutedims(indices); N = size(indices, 1); g = Vector{Float64}(undef, N)
+    chk(ccall((:ab_compress_grad, LIB), Cint, (Int64, Ptr{Int64}, Ptr{Cdouble}, Ptr{Cdouble}), N, idx, grad_nv, g))
+    g
+end
+"TriSolveGrad -> (grad_a, grad_b, grad_c, grad_d) (TriSolve.h:22-37)."
+function b200_trisolve_grad(grad_x::Vector{Float64}, x::Vector{Float64}, a::Vector{Float64}, b::Vector{Float64}, c::Vector{Float64})
+    n = length(b)
+    ga, gb, gc, gd = Vector{Float64}(undef, n - 1), Vector{Float64}(undef, n), Vector{Float64}(undef, n - 1), Vector{Float64}(undef, n)
+    chk(ccall((:ab_tri_solve_grad, LIB), Cint,
+              (Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+              n, grad_x, x, a, b, c, ga, gb, gc, gd))
+    ga, gb, gc, gd
+end
+"SolveGrad of the factorize/solve pair -> (grad_rhs, grad_vv) (Solve.h:15-33)."
+function b200_fsolve_grad(id::Int64, grad_out::Vector{Float64}, out::Vector{Float64}, ii::Vector{Int64}, jj::Vector{Int64})
+    d = length(out); grhs, gvv = Vector{Float64}(undef, d), Vector{Float64}(undef, length(ii))
+    chk(ccall((:ab_factorized_solve_grad, LIB), Cint,
+              (Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}, Ptr{Int64}, Int64, Int64, Ptr{Cdouble}, Ptr{Cdouble}),
+              id, grad_out, out, ii, jj, length(ii), d, grhs, gvv))
+    grhs, gvv
+end
+
+# ---- find / format glue ----------------------------------------------------------------------------
+"find(s): row-major (stable) reorder of the triplets, duplicates kept (src/sparse.jl:62-76, 93-99)."
+function b200_find(ii::Vector{Int64}, jj::Vector{Int64}, vv::Vector{Float64}, m::Integer, n::Integer)
+    T = length(vv); oi, oj, ov, perm = similar(ii), similar(jj), similar(vv), Vector{Int64}(undef, T)
+    chk(ccall((:ab_coo_reorder, LIB), Cint,
+              (Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}, Int64, Int64, Cint, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}, Ptr{Int64}),
+              T, ii, jj, vv, m, n, 1, oi, oj, ov, perm))
+    oi, oj, ov
+end
+"dense_to_sparse(o) (src/sparse.jl:78-86): o is handed over row-major."
+function b200_dense_to_sparse(o::Matrix{Float64})
+    m, n = size(o); th = Ref{Int64}(0)
+    chk(ccall((:ab_dense_to_coo, LIB), Cint, (Int64, Int64, Ptr{Cdouble}, Ref{Int64}), m, n, permutedims(o), th))
+    fetch_trip(th[])
+end
+"Array(s) (src/sparse.jl:185-193)."
+function b200_to_dense(s::B200SparseTensor)
+    out = Matrix{Float64}(undef, s.n, s.m)                  # row-major [m,n] == column-major [n,m]
+    chk(ccall((:ab_csr_to_dense, LIB), Cint, (Int64, Ptr{Cdouble}), s.h, out))
+    permutedims(out)
+end
+"[A; B] / [A B] (src/sparse.jl:227-262)."
+function b200_concat(ii1, jj1, vv1, m1::Integer, n1::Integer, ii2, jj2, vv2, hcat_::Bool)
+    N = length(vv1) + length(vv2); oi, oj, ov = Vector{Int64}(undef, N), Vector{Int64}(undef, N), Vector{Float64}(undef, N)
+    chk(ccall((:ab_coo_concat, LIB), Cint,
+              (Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}, Int64, Int64, Cint,
+               Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}),
+              length(vv1), ii1, jj1, vv1, length(vv2), ii2, jj2, vv2, m1, n1, hcat_ ? 1 : 0, oi, oj, ov))
+    oi, oj, ov
+end
+"A' as a new device handle (src/sparse.jl:220-225)."
+function b200_transpose(s::B200SparseTensor)
+    h = Ref{Int64}(0)
+    chk(ccall((:ab_csr_transpose, LIB), Cint, (Int64, Ref{Int64}), s.h, h))
+    h[]
+end
+set_option(key::String, value::Real) = chk(ccall((:ab_set_option, LIB), Cint, (Cstring, Cdouble), key, value))
+
+# ---- stencil generators (N1) — docs/src/assets/Codes/MPI/ccode/GetPoissonMatrix.h:15-72 ---------------
+function b200_poisson2d(n::Integer, kext::Matrix{Float64}; sign::Integer=-1)
+    h = Ref{Int64}(0)
+    chk(ccall((:ab_poisson2d_csr, LIB), Cint, (Int64, Ptr{Cdouble}, Cint, Ref{Int64}), n, permutedims(kext), sign, h))
+    h[]
+end
+b200_poisson2d_update!(h::Int64, n::Integer, kext::Matrix{Float64}; sign::Integer=-1) =
+    chk(ccall((:ab_poisson2d_update, LIB), Cint, (Int64, Int64, Ptr{Cdouble}, Cint), h, n, permutedims(kext), sign))
+function b200_poisson2d_grad(n::Integer, xgrad::Vector{Float64}, uext::Matrix{Float64}; sign::Integer=-1)
+    g = Vector{Float64}(undef, (n + 2)^2)
+    chk(ccall((:ab_poisson2d_grad, LIB), Cint, (Int64, Ptr{Cdouble}, Ptr{Cdouble}, Cint, Ptr{Cdouble}), n, xgrad, permutedims(uext), sign, g))
+    g
+end
+function b200_poisson3d(nx::Integer, ny::Integer, nz::Integer, row_lo::Integer=0, row_hi::Integer=nx * ny * nz)
+    h = Ref{Int64}(0)
+    chk(ccall((:ab_poisson3d_csr, LIB), Cint, (Int64, Int64, Int64, Int64, Int64, Ref{Int64}), nx, ny, nz, row_lo, row_hi, h))
+    h[]
+end
+
+# ---- mpi_SparseTensor \ b and its backward (src/mpi.jl:420-508) — one Julia process per GPU -------------
+"Rank 0 creates the 128-byte id, the host broadcasts it with its own transport (MPI.Bcast!), every rank joins."
+function b200_dist_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    chk(ccall((:ab_dist_unique_id, LIB), Cint, (Ptr{UInt8},), id))
+    id
+end
+b200_dist_init(rank::Integer, world::Integer, id::Vector{UInt8}) =
+    chk(ccall((:ab_dist_init, LIB), Cint, (Cint, Cint, Ptr{UInt8}), rank, world, id))
+b200_dist_finalize() = chk(ccall((:ab_dist_finalize, LIB), Cint, ()))
+"Local row block [ilower, iupper] (Hypre IJ layout, inclusive) of an N x N matrix; h_local holds GLOBAL column ids."
+function b200_dist_create(h_local::Int64, ilower::Integer, iupper::Integer, N::Integer)
+    dh = Ref{Int64}(0)
+    chk(ccall((:ab_dist_csr_create, LIB), Cint, (Int64, Int64, Int64, Int64, Ref{Int64}), h_local, ilower, iupper, N, dh))
+    dh[]
+end
+function b200_dist_solve(dh::Int64, f_local::Vector{Float64}; solver::String="BoomerAMG", tol::Real=0.0, maxit::Integer=0)
+    u = similar(f_local); it = Ref{Cint}(0); rr = Ref{Cdouble}(0.0)
+    chk(ccall((:ab_dist_solve, LIB), Cint, (Int64, Cstring, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Ref{Cint}, Ref{Cdouble}),
+              dh, solver, f_local, u, tol, maxit, it, rr))
+    u
+end
+"Backward of the distributed solve: (grad of this rank's stored CSR values, grad_f_local).  Collective."
+function b200_dist_solve_grad(dh::Int64, nnz_local::Integer, grad_u_local::Vector{Float64}, u_local::Vector{Float64})
+    gv, gf = Vector{Float64}(undef, nnz_local), similar(u_local)
+    chk(ccall((:ab_dist_solve_grad, LIB), Cint,
+              (Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Ptr{Cint}, Ptr{Cdouble}),
+              dh, grad_u_local, u_local, gv, gf, 0.0, 0, C_NULL, C_NULL))
+    gv, gf
+end
+function b200_dist_spmv(dh::Int64, x_local::Vector{Float64})
+    y = similar(x_local)
+    chk(ccall((:ab_dist_spmv, LIB), Cint, (Int64, Ptr{Cdouble}, Ptr{Cdouble}), dh, x_local, y))
+    y
+end
+b200_dist_destroy(dh::Int64) = chk(ccall((:ab_dist_destroy, LIB), Cint, (Int64,), dh))
 
 end # module
