@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 #include <vector>
 #include "../../include/adcme_b200.h"
@@ -145,10 +146,17 @@ struct Csr {
     // row-pattern form on top of the pattern codes (lazy, spmv.cu): when the rows' code sequences
     // come from at most 256 distinct patterns (a 3-D 7-point stencil has 27), rowcode[r] names the
     // pattern and pat_ent / pat_info hold the patterns: 1 byte per ROW instead of per entry, no rowptr.
-    uint8_t*  rowcode  = nullptr;  // [m]
+    uint8_t*  rowcode  = nullptr;  // [m + 1024] (zero padded: 16-byte bulk copies may over-read)
     void*     pat_ent  = nullptr;  // [npat_ent] x {double value; int32 offset; int32 pad}, patterns back to back
     uint32_t* pat_info = nullptr;  // [256] start | len << 16
     int       npat = -1, npat_ent = 0;   // npat: -1 not attempted, 0 unavailable
+    // x-window form of the row patterns (lazy, spmv.cu: spmv_rowwin_kernel): a 1024-row tile needs x only
+    // inside a few index intervals (one per cluster of stencil offsets); the TMA unit stages those intervals
+    // in shared memory and the pattern entries address the stage directly.  rw_ok: -1 not attempted, 0 n/a.
+    void*     rw_plan  = nullptr;  // host RowWinPlan (spmv.cu)
+    void*     rw_ent   = nullptr;  // [npat_ent] x {double value; int32 stage index rel. to the local row; int32 pad}
+    uint8_t*  rw_tmask = nullptr;  // [ceil(m/1024)] bit i: interval i is referenced by a row of the tile
+    int       rw_ok = -1;
     // triplet bookkeeping (null when the handle was created from CSR: identity map)
     uint32_t* perm     = nullptr; // [T]  sorted position -> input triplet
     uint32_t* segstart = nullptr; // [nnz+1] first sorted position of each stored entry
@@ -249,7 +257,10 @@ struct HaloWait {
 bool spmv_supports_halo_wait(const Csr* c, const double* vals);
 int  launch_spmv_halo(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
                       double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
-                      const int32_t* tile_list, int64_t nlist, const HaloWait& hw);
+                      const int32_t* tile_list, int64_t nlist, const HaloWait& hw, int list_rows);
+// rows per tile that launch_spmv_halo expects in its tile list for this matrix / operand (0: unsupported)
+int  spmv_halo_tile_rows(const Csr* c, const double* vals, const double* x);
+constexpr int SPMV_WINDOW_TILE_ROWS = 1024;   // tile size of the x-window SpMV kernel (spmv.cu RW_R)
 // same with an explicit value array (c->values or the scaled copy c->svalues)
 int launch_spmv_vals(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
                      double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,

@@ -105,6 +105,9 @@ struct DistCsr {
     int32_t* tiles_int = nullptr; int32_t* tiles_bnd = nullptr;
     int32_t* tiles_all = nullptr;  // [n_int + n_bnd] interior tiles first: the one-launch SpMV (HaloWait)
     int64_t  n_int = 0, n_bnd = 0;
+    // the same split for the 1024-row tiles of the x-window kernel (one-launch SpMV only)
+    int32_t* wtiles_all = nullptr;
+    int64_t  wn_int = 0, wn_bnd = 0;
     // peer-memory path
     bool p2p = false;
     P2PBlock* blk = nullptr;                 // mine
@@ -120,7 +123,7 @@ struct DistCsr {
     uint32_t halo_seq = 0, red_seq = 0;
     ~DistCsr() {
         delete loc;
-        dev_free(send_idx); dev_free(sendbuf); dev_free(tiles_int); dev_free(tiles_bnd); dev_free(tiles_all);
+        dev_free(send_idx); dev_free(sendbuf); dev_free(tiles_int); dev_free(tiles_bnd); dev_free(tiles_all); dev_free(wtiles_all);
         dev_free(d_peer_blk); dev_free(d_peer_x); dev_free(d_send_off); dev_free(d_send_cnt); dev_free(d_recv_cnt);
         for (int i = 0; i < nopened; ++i) cudaIpcCloseMemHandle(opened[i]);
         if (xext) { if (xext_cuda_malloc) cudaFree(xext); else dev_free(xext); }
@@ -445,13 +448,20 @@ static int dist_spmv_dev(DistCsr* d, const double* vals, double* y, const double
     }
     if (d->tiles_all && d->next > 0 && opt("dist_fused_wait", 1.0) != 0.0 && spmv_supports_halo_wait(c, vals)) {
         // one launch: interior tiles, in-kernel acquire of the peers' halo flags, boundary tiles
-        HaloWait hw{d->blk->halo_flag, d->d_recv_cnt, g_world, d->halo_seq, (unsigned)d->n_int, &d->blk->err};
+        const int lrows = spmv_halo_tile_rows(c, vals, d->xext);
+        const bool win = lrows == SPMV_WINDOW_TILE_ROWS && d->wtiles_all;
+        HaloWait hw{d->blk->halo_flag, d->d_recv_cnt, g_world, d->halo_seq, (unsigned)(win ? d->wn_int : d->n_int), &d->blk->err};
         if (push_seq && dotvec) {
             hw.peer_blk = d->d_peer_blk; hw.me = g_rank; hw.red_seq = push_seq;
             if (pushed) *pushed = true;
         }
-        return launch_spmv_halo(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_all,
-                                d->n_int + d->n_bnd, hw);
+        if (win)
+            return launch_spmv_halo(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->wtiles_all,
+                                    d->wn_int + d->wn_bnd, hw, lrows);
+        if (lrows == spmv_tile_rows(c))
+            return launch_spmv_halo(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_all,
+                                    d->n_int + d->n_bnd, hw, lrows);
+        if (pushed) *pushed = false;
     }
     if (d->n_int > 0)
         AB_TRY(launch_spmv_vals(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, d->tiles_int, d->n_int, 0));
@@ -859,6 +869,24 @@ int ab_dist_csr_create(int64_t h_local, int64_t ilower, int64_t iupper, int64_t 
             if (d->n_int) AB_CUDA(cudaMemcpyAsync(d->tiles_all, d->tiles_int, (size_t)d->n_int * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream()));
             if (d->n_bnd) AB_CUDA(cudaMemcpyAsync(d->tiles_all + d->n_int, d->tiles_bnd, (size_t)d->n_bnd * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream()));
             AB_LAUNCH_CHECK();
+            // the same split over 1024-row tiles (x-window SpMV kernel)
+            const int RW = SPMV_WINDOW_TILE_ROWS;
+            const int64_t wnt = (nloc + RW - 1) / RW;
+            DevBuf<uint32_t> wf, we;
+            DevBuf<int32_t> wi, wb;
+            AB_TRY(wf.alloc(wnt)); AB_TRY(we.alloc(wnt)); AB_TRY(wi.alloc(wnt + 1)); AB_TRY(wb.alloc(wnt + 1));
+            tile_halo_flag_kernel<<<(unsigned)wnt, 128, 0, stream()>>>(c->rowptr, c->colind, nloc, RW, nloc, wf.p);
+            AB_LAUNCH_CHECK();
+            AB_TRY(scan_exclusive_u32(wf.p, we.p, (size_t)wnt, tot.p));
+            AB_CUDA(cudaMemcpyAsync(&nb_, tot.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream()));
+            AB_CUDA(cudaStreamSynchronize(stream()));
+            d->wn_bnd = nb_; d->wn_int = wnt - nb_;
+            tile_split_kernel<<<(unsigned)((wnt + 255) / 256), 256, 0, stream()>>>(wf.p, we.p, wnt, wi.p, wb.p);
+            AB_LAUNCH_CHECK();
+            AB_TRY(dev_alloc((void**)&d->wtiles_all, (size_t)(wnt + 1) * sizeof(int32_t)));
+            if (d->wn_int) AB_CUDA(cudaMemcpyAsync(d->wtiles_all, wi.p, (size_t)d->wn_int * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream()));
+            if (d->wn_bnd) AB_CUDA(cudaMemcpyAsync(d->wtiles_all + d->wn_int, wb.p, (size_t)d->wn_bnd * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream()));
+            AB_CUDA(cudaStreamSynchronize(stream()));
         }
         // ---- 7. peer mappings
         if (want_p2p) AB_TRY(setup_p2p(d, d->dst_off));

@@ -522,6 +522,7 @@ static int csr_ensure_code(Csr* c, const double* vals) {
 // ---- row-pattern form ---------------------------------------------------------------------------
 constexpr int PAT_MAX_ENT = 2048;   // total {value, offset} entries over all patterns (32 KB of shared memory)
 constexpr int PAT_MAX_LEN = 255;
+constexpr int RW_PAD = 1024;        // rowcode padding: the window kernel's 16-byte bulk copies may over-read
 
 // x[row + off] through ONE integer instruction for the address (IMAD.WIDE off*8 + xr); left to itself
 // the compiler re-associates to x + (row + off) and spends four (IADD3, LEA.HI.X.SX32, LEA, LEA.HI.X).
@@ -742,10 +743,13 @@ rowpat_assign_kernel(const int32_t* __restrict__ rowptr, const uint8_t* __restri
     }
 }
 
+static int csr_build_rowwin(Csr* c, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat);
+
 // npat > 0 afterwards: rowcode/pat_ent/pat_info encode the matrix the pattern codes encode
 static int csr_ensure_rowpat(Csr* c) {
     if (c->npat >= 0 && c->ncode > 0) return AB_OK;     // csr_ensure_code resets npat when it rebuilds
     c->npat = 0;
+    c->rw_ok = 0;
     if (c->ncode <= 0 || c->m == 0) return AB_OK;
     DevBuf<unsigned long long> gtab; DevBuf<int> grep, gcount;
     AB_TRY(gtab.alloc(VAL_HASH)); AB_TRY(grep.alloc(VAL_HASH)); AB_TRY(gcount.alloc(1));
@@ -794,7 +798,10 @@ static int csr_ensure_rowpat(Csr* c) {
     if (!c->pat_info) AB_TRY(dev_alloc((void**)&c->pat_info, 256 * sizeof(uint32_t)));
     dev_free(c->pat_ent); c->pat_ent = nullptr;
     AB_TRY(dev_alloc(&c->pat_ent, (size_t)(nent > 0 ? nent : 1) * sizeof(CodeEnt)));
-    if (!c->rowcode) AB_TRY(dev_alloc((void**)&c->rowcode, (size_t)c->m));
+    if (!c->rowcode) {
+        AB_TRY(dev_alloc((void**)&c->rowcode, (size_t)c->m + RW_PAD));
+        AB_CUDA(cudaMemsetAsync(c->rowcode + c->m, 0, RW_PAD, stream()));
+    }
     AB_CUDA(cudaMemcpyAsync(dphash.p, phash.data(), 256 * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream()));
     AB_CUDA(cudaMemcpyAsync(c->pat_info, pinfo.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream()));
     if (nent) {
@@ -810,6 +817,296 @@ static int csr_ensure_rowpat(Csr* c) {
     AB_CUDA(cudaStreamSynchronize(stream()));
     if (hbad) return AB_OK;                               // a hash collision: keep the per-entry codes
     c->npat = cnt; c->npat_ent = nent;
+    return csr_build_rowwin(c, pent, pinfo, cnt);
+}
+
+// ---- x-window form of the row patterns -----------------------------------------------------------
+// spmv_rowpat_kernel is bound by the L1/LSU data pipe, not by HBM (ncu, 512^3: l1tex data-pipe wavefronts
+// 80 % busy, 137 warp-instructions per 32 rows, DRAM 37 %): every row gathers its x operands through L1
+// (7 x LDG.64) and re-reads its {value, offset} list from shared memory (7 x LDS.128).  This form removes
+// both.  The distinct (col - row) offsets of the matrix are clustered into a few INTERVALS; for a tile of
+// 1024 consecutive rows the operands x[row + o] of all rows lie inside [r0 + lo_i, r0 + lo_i + len_i) —
+// e.g. 7-point stencil on an n^3 grid: [-n^2, -n^2+1024), [-n-2, n+1026), [n^2, n^2+1024).  One elected
+// thread asks the TMA unit (cp.async.bulk, mbarrier completion) to stream those intervals plus the tile's
+// 1024 pattern bytes into shared memory (L2 -> smem, no L1 tags, no LSU address work), and every pattern
+// entry addresses the stage directly: x[row + o] = stage[local_row + soff].  The DOMINANT pattern (the
+// interior stencil: 98.8 % of the rows at 512^3) travels in the kernel parameters, so its values and stage
+// offsets are constant-bank operands: a row is K x (LDS.64 + DFMA) with no table lookups; all other rows
+// walk their pattern out of shared memory as before.  Thread t owns local rows t, t+256, t+512, t+768
+// (conflict-free LDS.64, coalesced y stores).  Summation order inside a row is the stored order, so y is
+// bit-identical to every other SpMV form.  HBM traffic per row is unchanged (1 + 8 + 8 bytes); the L2 -> SM
+// traffic is 8 * (sum of interval lengths) / 1024 bytes per row (33 at 512^3: the +-1, +-n neighbours share
+// one interval).
+constexpr int RW_R = 1024;           // rows per tile
+constexpr int RW_T = 256;            // threads per CTA
+constexpr int RW_J = RW_R / RW_T;    // rows per thread
+constexpr int RW_MAXI = 8;           // intervals
+constexpr int RW_MAXK = 8;           // entries of the dominant pattern carried in the kernel parameters
+constexpr int RW_NOCENTER = INT32_MIN;
+constexpr size_t RW_SMEM_MAX = 74 * 1024;   // 3 CTAs per SM at least
+
+struct RowWinPlan {
+    int ni;                 // number of intervals
+    int wtot;               // doubles staged per tile (sum of len[])
+    int dom;                // id of the dominant pattern (-1: none)
+    int dk;                 // its number of entries
+    int center;             // stage offset of x[row] relative to the local row (RW_NOCENTER: offset 0 is in no interval)
+    int pad_;
+    int lo[RW_MAXI];        // first x index of the interval relative to the tile's first row (even)
+    int len[RW_MAXI];       // doubles (even)
+    int sbase[RW_MAXI];     // where the interval starts in the stage (doubles, even)
+    int dsoff[RW_MAXK];     // dominant pattern: stage offset relative to the local row
+    double dval[RW_MAXK];   // dominant pattern: values
+};
+
+// x indices [a, b) of interval i that exist for the tile starting at row r0 (a, b even: 16-byte bulk copies);
+// *tail >= 0 names one last element the bulk copy cannot take (odd vector length) — it is copied by hand
+__device__ __forceinline__ bool rowwin_range(const RowWinPlan& P, int i, unsigned r0, long long xlen, long long& a, long long& b,
+                                             long long& tail) {
+    a = (long long)r0 + P.lo[i];
+    b = a + P.len[i];
+    tail = -1;
+    if (a < 0) a = 0;
+    if (b > xlen) { b = xlen; if (b & 1) { b -= 1; tail = b; } }
+    return b > a || tail >= a;
+}
+
+// K: entries of the dominant pattern handled from the kernel parameters (0: every row walks its pattern);
+// CK: position of the diagonal inside the dominant pattern (-1: unknown) — <y,x> then reuses the operand.
+template <int K, int CK, bool LIST>
+__global__ void __launch_bounds__(RW_T)
+spmv_rowwin_kernel(const __grid_constant__ RowWinPlan P, const uint8_t* __restrict__ rowcode, const int4* __restrict__ ent,
+                   int nent, const uint32_t* __restrict__ pinfo, const uint8_t* __restrict__ tmask,
+                   const double* __restrict__ x, long long xlen, double* __restrict__ y, unsigned m, unsigned ntiles,
+                   const int32_t* __restrict__ tile_list, int accumulate, const double* __restrict__ dotvec,
+                   int dot_in_window, double* partials, uint32_t* ticket, double* dot_result,
+                   const int* __restrict__ done, HaloWait hw) {
+    extern __shared__ __align__(128) unsigned char rw_smem[];
+    double*   s_x    = reinterpret_cast<double*>(rw_smem);                              // [P.wtot]
+    int4*     s_ent  = reinterpret_cast<int4*>(rw_smem + (size_t)P.wtot * 8);           // [nent]
+    uint32_t* s_info = reinterpret_cast<uint32_t*>(s_ent + nent);                       // [256]
+    uint8_t*  s_code = reinterpret_cast<uint8_t*>(s_info + 256);                        // [RW_R]
+    __shared__ alignas(8) uint64_t bar;
+    __shared__ double s_red[32];
+    if (done && *done) return;
+    const unsigned t = threadIdx.x;
+    for (int i = t; i < nent; i += RW_T) s_ent[i] = ent[i];
+    for (int i = t; i < 256; i += RW_T) s_info[i] = pinfo[i];
+    if (t == 0) {
+        abd::mbar_init(&bar, 1);
+        abd::mbar_fence_init();
+    }
+    __syncthreads();
+    double dot = 0.0, dot2 = 0.0;
+    unsigned phase = 0;
+    const double* xt = s_x + t;
+
+    auto do_tile = [&](unsigned tile) {
+        const unsigned r0 = tile * (unsigned)RW_R;
+        const unsigned nr = min((unsigned)RW_R, m - r0);
+        if (t == 0) {
+            const unsigned live = tmask[tile];
+            unsigned bytes = (nr + 15u) & ~15u;
+            long long a, b, tail;
+            for (int i = 0; i < P.ni; ++i)
+                if (((live >> i) & 1u) && rowwin_range(P, i, r0, xlen, a, b, tail)) {
+                    bytes += (unsigned)(b - a) * 8u;
+                    if (tail >= 0) s_x[P.sbase[i] + (tail - ((long long)r0 + P.lo[i]))] = x[tail];   // ordered by the arrive below
+                }
+            abd::mbar_expect_tx(&bar, bytes);
+            abd::bulk_g2s(s_code, rowcode + r0, (nr + 15u) & ~15u, &bar);
+            for (int i = 0; i < P.ni; ++i)
+                if (((live >> i) & 1u) && rowwin_range(P, i, r0, xlen, a, b, tail) && b > a)
+                    abd::bulk_g2s(s_x + P.sbase[i] + (a - ((long long)r0 + P.lo[i])), x + a, (unsigned)(b - a) * 8u, &bar);
+        }
+        abd::mbar_wait(&bar, phase);
+        phase ^= 1u;
+#pragma unroll
+        for (int j = 0; j < RW_J; ++j) {
+            const unsigned tl = t + (unsigned)j * RW_T;
+            if (tl < nr) {
+                const unsigned code = s_code[tl];
+                const double* xb = xt + j * RW_T;
+                double acc = 0.0, xc = 0.0;
+                bool have_xc = false;
+                if (K > 0 && code == (unsigned)P.dom) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const double xk = xb[P.dsoff[k]];
+                        if (k == CK) xc = xk;
+                        acc = fma(P.dval[k], xk, acc);
+                    }
+                    have_xc = CK >= 0;
+                } else {
+                    const uint32_t info = s_info[code];
+                    const int4* e = s_ent + (info & 0xffffu);
+                    const int len = (int)(info >> 16);
+                    int k = 0;
+                    for (; k + 2 <= len; k += 2) {
+                        const int4 q0 = e[k], q1 = e[k + 1];
+                        const double x0 = xb[q0.z], x1 = xb[q1.z];
+                        acc = fma(__hiloint2double(q0.y, q0.x), x0, acc);
+                        acc = fma(__hiloint2double(q1.y, q1.x), x1, acc);
+                    }
+                    if (k < len) {
+                        const int4 q0 = e[k];
+                        acc = fma(__hiloint2double(q0.y, q0.x), xb[q0.z], acc);
+                    }
+                }
+                y[r0 + tl] = acc;
+                if (dotvec) {
+                    const double w = have_xc ? xc : (dot_in_window ? xb[P.center] : dotvec[r0 + tl]);
+                    dot  = fma(acc, w, dot);
+                    dot2 = fma(acc, acc, dot2);
+                }
+            }
+        }
+        __syncthreads();   // the stage is rewritten by the next tile
+    };
+
+    const unsigned nb = (LIST && hw.flags) ? min(hw.n_before, ntiles) : ntiles;
+    for (unsigned ti = blockIdx.x; ti < nb; ti += gridDim.x) do_tile(LIST ? (unsigned)tile_list[ti] : ti);
+    if (LIST && nb < ntiles) {
+        if (t < (unsigned)hw.world && hw.recv_cnt[t] > 0) abd::wait_seq(hw.flags + t, hw.seq, hw.err);   // acquire the halos
+        __syncthreads();
+        // the halo tails were written by peers through the generic proxy; the bulk copies read through the async proxy
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (unsigned ti = nb + blockIdx.x; ti < ntiles; ti += gridDim.x) do_tile((unsigned)tile_list[ti]);
+    }
+    if (LIST && hw.peer_blk) {
+        if (dotvec) {
+            double mine[2];
+            mine[0] = abd::block_sum<RW_T>(dot, s_red);
+            mine[1] = abd::block_sum<RW_T>(dot2, s_red);
+            P2PBlock* const* pb = hw.peer_blk;
+            const int world = hw.world, me = hw.me;
+            const uint32_t rseq = hw.red_seq;
+            abd::grid_reduce<RW_T, 2>(mine, partials, ticket, s_red, [=](const double(&tot)[2]) {
+                dot_result[0] = tot[0];
+                dot_result[1] = tot[1];
+                abd::p2p_push2(pb, world, me, rseq, tot[0], tot[1]);
+            });
+        }
+        return;
+    }
+    AB_TILE_EPILOGUE(RW_T)
+}
+
+// rows per pattern (dominant pattern = argmax)
+__global__ void __launch_bounds__(256)
+rowcode_hist_kernel(const uint8_t* __restrict__ rowcode, int64_t m, unsigned long long* __restrict__ hist) {
+    __shared__ unsigned sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < m; r += (int64_t)gridDim.x * 256) atomicAdd(&sh[rowcode[r]], 1u);
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+// tmask[tile] = OR over the tile's rows of the interval mask of their pattern
+__global__ void __launch_bounds__(256)
+rowwin_tmask_kernel(const uint8_t* __restrict__ rowcode, int64_t m, const uint32_t* __restrict__ patmask, uint8_t* __restrict__ tmask) {
+    __shared__ uint32_t s_pm[256];
+    __shared__ unsigned s_or;
+    s_pm[threadIdx.x] = patmask[threadIdx.x];
+    if (threadIdx.x == 0) s_or = 0;
+    __syncthreads();
+    const int64_t r0 = (int64_t)blockIdx.x * RW_R;
+    unsigned mine = 0;
+    for (int j = 0; j < RW_J; ++j) {
+        const int64_t r = r0 + threadIdx.x + j * 256;
+        if (r < m) mine |= s_pm[rowcode[r]];
+    }
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicOr(&s_or, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) tmask[blockIdx.x] = (uint8_t)s_or;
+}
+
+// rw_ok = 1 afterwards when the window form is available for the matrix the row patterns encode.
+// pent / pinfo: the host copies of the pattern tables csr_ensure_rowpat has just built.
+static int csr_build_rowwin(Csr* c, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat) {
+    c->rw_ok = 0;
+    if (c->m < 1 || pent.empty()) return AB_OK;
+    // ---- intervals: cluster the distinct offsets
+    std::vector<int> offs;
+    for (const CodeEnt& e : pent) offs.push_back(e.off);
+    std::sort(offs.begin(), offs.end());
+    offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+    RowWinPlan P;
+    memset(&P, 0, sizeof(P));
+    P.dom = -1; P.center = RW_NOCENTER;
+    std::vector<long long> ilo, ihi;
+    for (int o : offs) {
+        const long long lo = (long long)o & ~1ll, hi = ((long long)o + RW_R + 1) & ~1ll;   // even bounds: 16-byte bulk copies
+        if (!ilo.empty() && lo <= ihi.back()) { if (hi > ihi.back()) ihi.back() = hi; }
+        else { ilo.push_back(lo); ihi.push_back(hi); }
+    }
+    if ((int)ilo.size() > RW_MAXI) return AB_OK;
+    long long w = 0;
+    P.ni = (int)ilo.size();
+    for (int i = 0; i < P.ni; ++i) {
+        if (ilo[i] < INT32_MIN / 2 || ihi[i] > INT32_MAX / 2) return AB_OK;
+        P.lo[i] = (int)ilo[i]; P.len[i] = (int)(ihi[i] - ilo[i]); P.sbase[i] = (int)w;
+        w += P.len[i];
+    }
+    const size_t smem = (size_t)w * 8 + pent.size() * 16 + 1024 + RW_R;
+    if (smem > RW_SMEM_MAX) return AB_OK;
+    P.wtot = (int)w;
+    auto stage_off = [&](int o, int* iv) {
+        for (int i = 0; i < P.ni; ++i)
+            if (o >= P.lo[i] && o + RW_R <= P.lo[i] + P.len[i]) { if (iv) *iv = i; return P.sbase[i] + (o - P.lo[i]); }
+        return (int)RW_NOCENTER;
+    };
+    P.center = stage_off(0, nullptr);
+    // ---- entries with stage offsets, interval mask per pattern
+    std::vector<CodeEnt> went(pent);
+    std::vector<uint32_t> patmask(256, 0);
+    for (int p = 0; p < npat; ++p) {
+        const int st = (int)(pinfo[p] & 0xffffu), len = (int)(pinfo[p] >> 16);
+        for (int k = 0; k < len; ++k) {
+            int iv = 0;
+            const int so = stage_off(pent[st + k].off, &iv);
+            if (so == RW_NOCENTER) return AB_OK;   // cannot happen: every offset opened an interval
+            went[st + k].off = so;
+            patmask[p] |= 1u << iv;
+        }
+    }
+    for (int p = npat; p < 256; ++p) patmask[p] = patmask[npat - 1];
+    // ---- dominant pattern
+    DevBuf<unsigned long long> dh;
+    AB_TRY(dh.alloc(256));
+    AB_CUDA(cudaMemsetAsync(dh.p, 0, 256 * sizeof(unsigned long long), stream()));
+    {
+        int64_t nblk = (c->m + 255) / 256, cap = (int64_t)sm_count() * 8;
+        rowcode_hist_kernel<<<(unsigned)(nblk < cap ? nblk : cap), 256, 0, stream()>>>(c->rowcode, c->m, dh.p);
+        AB_LAUNCH_CHECK();
+    }
+    unsigned long long hh[256];
+    AB_CUDA(cudaMemcpyAsync(hh, dh.p, sizeof(hh), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    int dom = 0;
+    for (int p = 1; p < npat; ++p) if (hh[p] > hh[dom]) dom = p;
+    const int dlen = (int)(pinfo[dom] >> 16), dst = (int)(pinfo[dom] & 0xffffu);
+    if (dlen >= 1 && dlen <= RW_MAXK) {
+        P.dom = dom; P.dk = dlen;
+        for (int k = 0; k < dlen; ++k) { P.dsoff[k] = went[dst + k].off; P.dval[k] = went[dst + k].v; }
+    }
+    // ---- device tables
+    const int64_t ntile = (c->m + RW_R - 1) / RW_R;
+    DevBuf<uint32_t> dpm;
+    AB_TRY(dpm.alloc(256));
+    dev_free(c->rw_ent); c->rw_ent = nullptr;
+    AB_TRY(dev_alloc(&c->rw_ent, went.size() * sizeof(CodeEnt)));
+    if (!c->rw_tmask) AB_TRY(dev_alloc((void**)&c->rw_tmask, (size_t)ntile));
+    AB_CUDA(cudaMemcpyAsync(c->rw_ent, went.data(), went.size() * sizeof(CodeEnt), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemcpyAsync(dpm.p, patmask.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream()));
+    rowwin_tmask_kernel<<<(unsigned)ntile, 256, 0, stream()>>>(c->rowcode, c->m, dpm.p, c->rw_tmask);
+    AB_LAUNCH_CHECK();
+    AB_CUDA(cudaStreamSynchronize(stream()));   // host tables must outlive the copies
+    if (!c->rw_plan) c->rw_plan = malloc(sizeof(RowWinPlan));
+    if (!c->rw_plan) return fail(AB_ECUDA, "out of host memory");
+    memcpy(c->rw_plan, &P, sizeof(P));
+    c->rw_ok = 1;
     return AB_OK;
 }
 
@@ -850,6 +1147,61 @@ spmv_vector_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict
             dot_result[1] = tot[1];
         });
     }
+}
+
+static bool rowwin_ready(const Csr* c, const double* vals, const double* x) {
+    return c->rw_ok == 1 && c->rw_plan && c->ncode > 0 && c->npat > 0 && c->code_src == vals &&
+           c->code_version == c->values_version && ((uintptr_t)x & 15) == 0 && opt("spmv_code", 1.0) != 0.0 &&
+           opt("spmv_rowpat", 1.0) != 0.0 && opt("spmv_rowwin", 1.0) != 0.0 && (int)opt("spmv_variant", -1) != 0;
+}
+
+// tile_list (when given) holds RW_R-row tiles
+static int launch_rowwin(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result, double* partials,
+                         uint32_t* ticket, const int* done_flag, const int32_t* tile_list, int64_t nlist, int accumulate,
+                         const HaloWait* hwp) {
+    const RowWinPlan& P = *reinterpret_cast<const RowWinPlan*>(c->rw_plan);
+    const unsigned ntiles = tile_list ? (unsigned)nlist : (unsigned)((c->m + RW_R - 1) / RW_R);
+    if (ntiles == 0) return AB_OK;
+    HaloWait hw{};
+    if (hwp) hw = *hwp;
+    const size_t smem = (size_t)P.wtot * 8 + (size_t)c->npat_ent * 16 + 1024 + RW_R;
+    int cps = (int)((227 * 1024) / (smem + 1280));
+    const int cps_opt = (int)opt("spmv_rowwin_ctas", 0.0);
+    if (cps_opt > 0 && cps_opt < cps) cps = cps_opt;
+    if (cps > 8) cps = 8;
+    if (cps < 1) cps = 1;
+    unsigned cap = (unsigned)(sm_count() * cps);
+    if (cap > (unsigned)MAX_REDUCE_GRID) cap = MAX_REDUCE_GRID;
+    const unsigned grid = ntiles < cap ? ntiles : cap;
+    const int dot_in_window = (dotvec == x && P.center != RW_NOCENTER) ? 1 : 0;
+    int ck = -1;
+    for (int k = 0; k < P.dk; ++k) if (P.dom >= 0 && P.dsoff[k] == P.center) ck = k;
+    if (!dot_in_window) ck = -1;
+    const bool fast = P.dom >= 0 && opt("spmv_rowwin_dom", 1.0) != 0.0;
+#define AB_RW(KK, CC, LISTV)                                                                                                  \
+    do {                                                                                                                      \
+        auto kern = spmv_rowwin_kernel<KK, CC, LISTV>;                                                                        \
+        static size_t smem_set = 0;                                                                                           \
+        if (smem > smem_set) {                                                                                                \
+            AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RW_SMEM_MAX));               \
+            AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));                         \
+            smem_set = RW_SMEM_MAX;                                                                                           \
+        }                                                                                                                     \
+        kern<<<grid, RW_T, smem, stream()>>>(P, c->rowcode, (const int4*)c->rw_ent, c->npat_ent, c->pat_info, c->rw_tmask, x, \
+                                             (long long)c->n, y, (unsigned)c->m, ntiles, tile_list, accumulate, dotvec,       \
+                                             dot_in_window, partials, ticket, dot_result, done_flag, hw);                     \
+    } while (0)
+#define AB_RW2(KK, CC) do { if (tile_list) AB_RW(KK, CC, true); else AB_RW(KK, CC, false); } while (0)
+    if (fast && P.dk == 7 && ck == 3) AB_RW2(7, 3);
+    else if (fast && P.dk == 7) AB_RW2(7, -1);
+    else if (fast && P.dk == 5 && ck == 2) AB_RW2(5, 2);
+    else if (fast && P.dk == 5) AB_RW2(5, -1);
+    else if (fast && P.dk == 3 && ck == 1) AB_RW2(3, 1);
+    else AB_RW2(0, -1);
+#undef AB_RW2
+#undef AB_RW
+    AB_LAUNCH_CHECK();
+    return AB_OK;
 }
 
 static int pick_vector_lanes(const Csr* c) {
@@ -931,27 +1283,34 @@ static bool rowpat_ready(const Csr* c, const double* vals) {
            (int)opt("spmv_variant", -1) != 0;
 }
 bool spmv_supports_halo_wait(const Csr* c, const double* vals) { return rowpat_ready(c, vals); }
+// rows per tile the one-launch halo SpMV expects in its tile list: RW_R when the x-window kernel will run
+int spmv_halo_tile_rows(const Csr* c, const double* vals, const double* x) {
+    if (!rowpat_ready(c, vals)) return 0;
+    return rowwin_ready(c, vals, x) ? RW_R : spmv_tile_rows(c);
+}
 
 static int launch_spmv_impl(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
                             double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
-                            const int32_t* tile_list, int64_t nlist, int accumulate, const HaloWait* hwp);
+                            const int32_t* tile_list, int64_t nlist, int accumulate, const HaloWait* hwp, int list_rows);
 
 int launch_spmv_halo(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
                      double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
-                     const int32_t* tile_list, int64_t nlist, const HaloWait& hw) {
+                     const int32_t* tile_list, int64_t nlist, const HaloWait& hw, int list_rows) {
     if (!tile_list || !rowpat_ready(c, vals)) return fail(AB_EUNSUPPORTED, "in-kernel halo wait needs the row-pattern SpMV form");
-    return launch_spmv_impl(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, 0, &hw);
+    if (list_rows != spmv_halo_tile_rows(c, vals, x)) return fail(AB_EINVAL, "tile list built for %d-row tiles, kernel uses %d", list_rows, spmv_halo_tile_rows(c, vals, x));
+    return launch_spmv_impl(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, 0, &hw, list_rows);
 }
 
 int launch_spmv_vals(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
                      double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
                      const int32_t* tile_list, int64_t nlist, int accumulate) {
-    return launch_spmv_impl(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, accumulate, nullptr);
+    return launch_spmv_impl(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, accumulate, nullptr, 0);
 }
 
+// list_rows: rows per tile the tile list was built for (0: the tile kernels' own spmv_tile_rows)
 static int launch_spmv_impl(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
                             double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
-                            const int32_t* tile_list, int64_t nlist, int accumulate, const HaloWait* hwp) {
+                            const int32_t* tile_list, int64_t nlist, int accumulate, const HaloWait* hwp, int list_rows) {
     if (c->m == 0) return AB_OK;
     // spmv_variant: -1 auto, 0 vector kernel, 1 tile kernel U=8, 2 tile kernel U=4
     int variant = (int)opt("spmv_variant", -1);
@@ -968,6 +1327,9 @@ static int launch_spmv_impl(const Csr* c, const double* vals, const double* x, d
             AB_TRY(csr_ensure_code(const_cast<Csr*>(c), vals));
             if (c->ncode > 0 && c->npat < 0) AB_TRY(csr_ensure_rowpat(const_cast<Csr*>(c)));
         }
+        if (rowwin_ready(c, vals, x) && (!tile_list || list_rows == RW_R))
+            return launch_rowwin(c, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, accumulate, hwp);
+        if (tile_list && list_rows == RW_R) return fail(AB_EINVAL, "tile list built for the x-window kernel, which is not available");
 #define AB_T(RR, UU) launch_tile<RR, UU>(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, cps * (256 / RR), tile_list, nlist, accumulate, hwp)
         if (R == 256) return variant == 2 ? AB_T(256, 4) : AB_T(256, 8);
         if (R == 128) return AB_T(128, 8);
@@ -1015,6 +1377,7 @@ extern "C" int ab_csr_get_info(int64_t h, const char* key, double* value) {
     if (!strcmp(key, "noff")) *value = c->noff;
     else if (!strcmp(key, "npat")) *value = (c->code_version == c->values_version && c->ncode > 0) ? c->npat : -1;
     else if (!strcmp(key, "ncode")) *value = (c->code_version == c->values_version) ? c->ncode : -1;
+    else if (!strcmp(key, "rowwin")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0) ? c->rw_ok : -1;
     else if (!strcmp(key, "tile_rows")) *value = ab::spmv_tile_rows(c);
     else if (!strcmp(key, "max_row_nnz")) *value = c->max_row_nnz;
     else if (!strcmp(key, "scaled")) *value = (c->scaled_version == c->values_version && c->scaled_ok) ? 1 : 0;

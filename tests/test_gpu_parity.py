@@ -670,18 +670,21 @@ def test_pattern_code_spmv_is_lossless(pkg):
     run-to-run deterministic."""
     import torch
 
-    forms = (("rowpat", 1.0, 1.0, 1.0), ("code", 0.0, 1.0, 1.0), ("off8", 0.0, 0.0, 1.0), ("plain", 0.0, 0.0, 0.0))
+    forms = (("rowwin", 1.0, 1.0, 1.0, 1.0), ("rowpat", 1.0, 1.0, 1.0, 0.0), ("code", 0.0, 1.0, 1.0, 0.0),
+             ("off8", 0.0, 0.0, 1.0, 0.0), ("plain", 0.0, 0.0, 0.0, 0.0))
 
-    def with_form(rowpat, code, off8, fn):
+    def with_form(rowpat, code, off8, rowwin, fn):
         pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", rowpat))
         pkg.check(pkg.lib.ab_set_option(b"spmv_code", code))
         pkg.check(pkg.lib.ab_set_option(b"spmv_off8", off8))
+        pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin", rowwin))
         try:
             return fn()
         finally:
             pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", 1.0))
             pkg.check(pkg.lib.ab_set_option(b"spmv_code", 1.0))
             pkg.check(pkg.lib.ab_set_option(b"spmv_off8", 1.0))
+            pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin", 1.0))
 
     for n in (48, 67):                         # 67: tiles straddle planes, odd sizes
         N = n ** 3
@@ -703,17 +706,26 @@ def test_pattern_code_spmv_is_lossless(pkg):
             pkg.check(pkg.lib.ab_cg_fixed(A.handle(), f.data_ptr(), u.data_ptr(), 40, C.byref(rr)))
             return u
 
-        ys = {name: with_form(a, b, c, spmv) for name, a, b, c in forms}
-        for name in ("rowpat", "code", "off8"):
+        ys = {name: with_form(a, b, c, d, spmv) for name, a, b, c, d in forms}
+        pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin_dom", 0.0))                # every row walks its pattern out of the stage
+        try:
+            ys["rowwin_generic"] = with_form(1.0, 1.0, 1.0, 1.0, spmv)
+        finally:
+            pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin_dom", 1.0))
+        assert torch.equal(ys["rowwin_generic"], ys["plain"])
+        for name in ("rowwin", "rowpat", "code", "off8"):
             assert torch.equal(ys[name], ys["plain"]), name                      # lossless: same bits
         S = A.to_scipy()
         dinv = 1.0 / np.sqrt(S.diagonal())
         y0 = dinv * (S @ (dinv * x.cpu().numpy()))
         assert np.max(np.abs(ys["plain"].cpu().numpy() - y0)) <= 1e-13 * np.max(np.abs(y0))
-        us = {name: with_form(a, b, c, cg) for name, a, b, c in forms}
-        for name in ("rowpat", "code", "off8"):
+        us = {name: with_form(a, b, c, d, cg) for name, a, b, c, d in forms}
+        for name in ("rowwin", "rowpat", "code", "off8"):
             assert float((us[name] - us["plain"]).abs().max() / us["plain"].abs().max()) <= 1e-11, name
-        assert torch.equal(with_form(1.0, 1.0, 1.0, cg), us["rowpat"])          # deterministic run to run
+        assert torch.equal(with_form(1.0, 1.0, 1.0, 0.0, cg), us["rowpat"])     # deterministic run to run
+        assert torch.equal(with_form(1.0, 1.0, 1.0, 1.0, cg), us["rowwin"])
+        pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"rowwin", C.byref(C.c_double(0))))
+        pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin", 0.0))               # the cg_defer_x checks below compare with us["rowpat"]
         # the x update riding in K3 (10 vector passes) is the same arithmetic, only moved
         pkg.check(pkg.lib.ab_set_option(b"cg_defer_x", 0.0))
         try:
@@ -728,7 +740,10 @@ def test_pattern_code_spmv_is_lossless(pkg):
             assert sols[0][1] == sols[1][1] and torch.equal(sols[0][0], sols[1][0])
         finally:
             pkg.check(pkg.lib.ab_set_option(b"cg_defer_x", 1.0))
+            pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin", 1.0))
         info = C.c_double(0)
+        pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"rowwin", C.byref(info)))
+        assert info.value == 1                 # the x-window form was built for the stencil
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"npat", C.byref(info)))
         assert info.value == 27                # interior + face / edge / corner variants of the 7-point stencil
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"ncode", C.byref(info)))
@@ -753,6 +768,85 @@ def test_pattern_code_spmv_is_lossless(pkg):
     pkg.check(pkg.lib.ab_poisson2d_update(h2.value, n, (3.0 * np.ones((n + 2, n + 2))).ctypes.data, -1))
     u3 = pkg.backslash(B, f, "CG")
     assert np.linalg.norm(3.0 * u3 - u1) / np.linalg.norm(u1) <= 1e-9
+
+
+def test_window_spmv_matrix_classes(pkg):
+    """The x-window SpMV (1024-row tiles staged by the TMA unit) against the plain int32 kernel, bit for bit, on
+    matrix classes that exercise each of its paths: dominant patterns of 3 / 5 / 7 entries carried in the kernel
+    parameters (1-D, 2-D, 3-D stencils), a 9-entry dominant pattern (every row walks its pattern out of the
+    stage), odd vector lengths (the element the 16-byte bulk copy cannot take), windows clamped at both ends of
+    the vector, a partial last tile, and a banded matrix with a few hundred row patterns."""
+    import torch
+
+    rng = np.random.default_rng(233)
+
+    def stencil(shape, offsets_vals):
+        N = int(np.prod(shape))
+        idx = np.arange(N).reshape(shape)
+        rows, cols, vals = [np.arange(N)], [np.arange(N)], [np.full(N, 4.0 + len(shape))]
+        for d, v in offsets_vals:
+            src = [slice(None)] * len(shape)
+            dst = [slice(None)] * len(shape)
+            ok = True
+            for ax, dd in enumerate(d):
+                if dd > 0: src[ax], dst[ax] = slice(0, shape[ax] - dd), slice(dd, None)
+                elif dd < 0: src[ax], dst[ax] = slice(-dd, None), slice(0, shape[ax] + dd)
+                ok = ok and abs(dd) < shape[ax]
+            if not ok: continue
+            r, c_ = idx[tuple(src)].ravel(), idx[tuple(dst)].ravel()
+            rows.append(r); cols.append(c_); vals.append(np.full(r.size, v))
+        return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(N, N))
+
+    cases = {
+        "1d_3pt": stencil((5001,), [((1,), -1.0), ((-1,), -1.0)]),
+        "2d_5pt": stencil((97, 131), [((0, 1), -1.0), ((0, -1), -1.0), ((1, 0), -1.0), ((-1, 0), -1.0)]),
+        "3d_7pt_aniso": stencil((21, 33, 40), [((0, 0, 1), -1.0), ((0, 0, -1), -1.0), ((0, 1, 0), -0.5), ((0, -1, 0), -0.5),
+                                                ((1, 0, 0), -0.25), ((-1, 0, 0), -0.25)]),
+        "2d_9pt": stencil((64, 80), [((a, b), -0.5) for a in (-1, 0, 1) for b in (-1, 0, 1) if (a, b) != (0, 0)]),
+        "tiny": stencil((7,), [((1,), -1.0), ((-1,), -1.0)]),
+    }
+    # banded SPD matrix with a handful of distinct values but hundreds of row patterns
+    N = 6000
+    B = sp.lil_matrix((N, N))
+    for off in (1, 3, 17, 64):
+        mask = rng.uniform(size=N - off) < 0.5
+        v = np.where(mask, rng.choice([-0.25, -0.5], N - off), 0.0)
+        B.setdiag(v, off); B.setdiag(v, -off)
+    B.setdiag(np.full(N, 4.0))
+    B = B.tocsr(); B.eliminate_zeros()
+    cases["banded_many_patterns"] = B
+    info = C.c_double(0)
+    used = 0
+    for name, S in cases.items():
+        S = S.tocsr(); S.sort_indices()
+        N = S.shape[0]
+        A = pkg.SparseTensor(S)
+        x = torch.randn(N, dtype=torch.float64, device="cuda")
+        out = {}
+        for use in (0.0, 1.0):
+            pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin", use))
+            pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", use))
+            pkg.check(pkg.lib.ab_set_option(b"spmv_code", use))
+            pkg.check(pkg.lib.ab_set_option(b"spmv_off8", use))
+            try:
+                y = torch.empty_like(x)
+                pkg.check(pkg.lib.ab_spmv_solver_form(A.handle(), x.data_ptr(), y.data_ptr()))
+                out[use] = y
+            finally:
+                for k in (b"spmv_rowwin", b"spmv_rowpat", b"spmv_code", b"spmv_off8"):
+                    pkg.check(pkg.lib.ab_set_option(k, 1.0))
+        assert torch.equal(out[0.0], out[1.0]), name
+        dinv = 1.0 / np.sqrt(S.diagonal())
+        y0 = dinv * (S @ (dinv * x.cpu().numpy()))
+        assert np.max(np.abs(out[1.0].cpu().numpy() - y0)) <= 1e-13 * np.max(np.abs(y0)), name
+        pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"rowwin", C.byref(info)))
+        used += int(info.value == 1)
+        # a full solve through the window form agrees with scipy
+        f = rng.uniform(size=N)
+        u = pkg.backslash(A, f, "CG")
+        assert np.linalg.norm(S @ u - f) / np.linalg.norm(f) <= TOL_SOLVE, name
+        A.close()
+    assert used >= 4, used
 
 
 def test_dist_path_world1_equals_single_gpu(pkg):
