@@ -86,6 +86,7 @@ SIGNATURES = {
     "ab_vec_axpby": (C.c_int, [_i64, _dbl, _ptr, _dbl, _ptr, _ptr]),
     "ab_vec_dot": (C.c_int, [_i64, _ptr, _ptr, _ptr]),
     "ab_poisson3d_csr": (C.c_int, [_i64, _i64, _i64, _i64, _i64, _ptr]),
+    "ab_poisson3d_kappa_csr": (C.c_int, [_i64, _i64, _i64, _ptr, _i64, _i64, _ptr]),
     "ab_poisson2d_csr": (C.c_int, [_i64, _ptr, C.c_int, _ptr]),
     "ab_poisson2d_update": (C.c_int, [_i64, _i64, _ptr, C.c_int]),
     "ab_poisson2d_grad": (C.c_int, [_i64, _ptr, _ptr, C.c_int, _ptr]),
@@ -98,6 +99,9 @@ SIGNATURES = {
     "ab_dist_solve_grad": (C.c_int, [_i64, _ptr, _ptr, _ptr, _ptr, _dbl, C.c_int, _ptr, _ptr]),
     "ab_dist_cg_fixed": (C.c_int, [_i64, _ptr, _ptr, C.c_int, _ptr]),
     "ab_dist_destroy": (C.c_int, [_i64]),
+    "ab_dist_export_coo": (C.c_int, [_i64, _ptr, _ptr]),
+    "ab_dist_query": (C.c_int, [_i64, _ptr, _ptr, _ptr]),
+    "ab_dist_transpose": (C.c_int, [_i64, _ptr]),
     "ab_timer_reset": (C.c_int, []),
     "ab_timer_get": (_dbl, [C.c_int]),
     "ab_bench_spmv": (C.c_int, [_i64, _ptr, _ptr, C.c_int, C.c_int, _ptr]),

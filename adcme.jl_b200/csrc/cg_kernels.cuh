@@ -22,6 +22,7 @@ struct SolveScal {
     int iters;        // iterations completed
     int breakdown;    // 1 = non-SPD / zero pivot / NaN
     int bad;          // K2 saw an unusable pAp (carried to cg_fin_kernel in raw mode)
+    int half;         // BiCGSTAB: half-step flag / carried `bad` (raw mode)
 };
 
 constexpr int EW_THREADS = 256;
@@ -172,10 +173,7 @@ cg_replace_kernel(const double* __restrict__ b, const double* __restrict__ sb, c
 }
 
 // distributed mode: scalar logic after the all-reduce of SolveScal::red.  which: 0 init, 1 update
-static __global__ void cg_fin_kernel(SolveScal* s, int which, int parity, double tol) {
-    if (which == 0) cg_init_fin(s, tol, s->red[0], s->red[1]);
-    else if (!s->done) cg_update_fin(s, parity, s->red[0], s->red[1], s->bad != 0);
-}
+static __global__ void cg_fin_kernel(SolveScal* s, int which, int parity, double tol);
 
 // ---------------------------------------------------------------------------------------------
 // Symmetrically scaled form of Jacobi-PCG.  With S = D^-1/2, PCG on (A, M = D) is CG on
@@ -333,6 +331,143 @@ static __global__ void scale_values_kernel(const int32_t* __restrict__ rowptr, c
     if (r >= m) return;
     const double sr = sinv_ext[r];
     for (int j = rowptr[r]; j < rowptr[r + 1]; ++j) sv[j] = values[j] * sr * sinv_ext[colind[j]];
+}
+
+// ---------------------------------------------------------------- BiCGSTAB kernels (right-preconditioned)
+// Shared by solver.cu (raw = 0: the last CTA applies the scalar logic) and dist.cu (raw = 1: the kernel
+// only deposits this rank's partial sums in SolveScal::red; after the all-reduce the same logic runs in
+// bicg_fin_kernel / inside the peer-memory all-reduce kernel).
+__device__ __forceinline__ void bicg_init_fin(SolveScal* s, double tol, double bb) {
+    s->rho = bb; s->bb = bb; s->rr = bb;
+    s->alpha = 1.0; s->omega = 1.0;
+    s->thr = tol < 0 ? -1.0 : tol * tol * bb;
+    s->iters = 0;
+    s->bad = 0;
+    s->breakdown = isfinite(bb) ? 0 : 1;
+    s->done = (bb == 0.0 || s->breakdown) ? 1 : 0;
+}
+// ss = <s,s>; `bad` = the alpha this rank computed was unusable (same on every rank: it derives from all-reduced values)
+__device__ __forceinline__ void bicg_s_fin(SolveScal* s, double ss, bool bad) {
+    s->rr = ss;   // provisional: ||s||^2
+    s->bad = (s->thr >= 0.0 && ss <= s->thr) ? 1 : 0;   // s already below tolerance: take the half step
+    if (bad || !isfinite(ss)) { s->breakdown = 1; s->done = 1; }
+}
+// q0 = <rhat,r>, q1 = <r,r>; alpha, omega and the half-step flag were stored by the x kernel
+__device__ __forceinline__ void bicg_x_fin(SolveScal* s, double q0, double q1) {
+    const double rho_old = s->rho, alpha = s->alpha, omega = s->omega;
+    const bool half = s->half != 0;
+    s->rho = q0;
+    s->rr  = q1;
+    s->iters += 1;
+    // beta for the next direction, stored in dots[1] (dots[] are free until the next SpMV)
+    const double beta = (q0 / rho_old) * (alpha / omega);
+    s->dots[1] = beta;
+    if (!isfinite(q0) || !isfinite(q1) || !isfinite(omega)) { s->breakdown = 1; s->done = 1; }
+    else if (s->thr >= 0.0 && q1 <= s->thr) s->done = 1;
+    else if (half || omega == 0.0 || q0 == 0.0 || !isfinite(beta)) { s->breakdown = 1; s->done = 1; }
+}
+
+// r = b ; rhat = b ; p = b ; y = D^-1 p ; x = 0 ; rho = <rhat,r> = bb
+static __global__ void __launch_bounds__(EW_THREADS)
+bicg_init_kernel(const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x,
+                 double* __restrict__ r, double* __restrict__ rhat, double* __restrict__ p, double* __restrict__ y,
+                 size_t n, double tol, SolveScal* s, double* partials, uint32_t* ticket, int raw) {
+    __shared__ double sh[32];
+    double a1 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        double bi = b[i];
+        x[i] = 0.0; r[i] = bi; rhat[i] = bi; p[i] = bi; y[i] = dinv[i] * bi;
+        a1 = fma(bi, bi, a1);
+    }
+    double mine[1];
+    mine[0] = abd::block_sum<EW_THREADS>(a1, sh);
+    abd::grid_reduce<EW_THREADS, 1>(mine, partials, ticket, sh, [=](const double(&t)[1]) {
+        if (raw) { s->red[0] = t[0]; s->red[1] = 0.0; s->done = 0; }
+        else bicg_init_fin(s, tol, t[0]);
+    });
+}
+// after v = A y with dots[0] = <v, rhat>: alpha = rho/<rhat,v> ; s = r - alpha v ; z = D^-1 s ; ss = <s,s>
+static __global__ void __launch_bounds__(EW_THREADS)
+bicg_s_kernel(const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
+              double* __restrict__ sv, double* __restrict__ z, size_t n, SolveScal* s, double* partials,
+              uint32_t* ticket, int raw) {
+    __shared__ double sh[32];
+    if (s->done) return;
+    const double rv = s->dots[0];
+    const bool bad = (rv == 0.0) || !isfinite(rv) || !isfinite(s->rho);
+    const double alpha = bad ? 0.0 : s->rho / rv;
+    double a0 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        double si = fma(-alpha, v[i], r[i]);
+        sv[i] = si;
+        z[i]  = dinv[i] * si;
+        a0 = fma(si, si, a0);
+    }
+    double mine[1];
+    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
+    abd::grid_reduce<EW_THREADS, 1>(mine, partials, ticket, sh, [=](const double(&t)[1]) {
+        s->alpha = alpha;
+        if (raw) { s->red[0] = t[0]; s->red[1] = 0.0; s->half = bad ? 1 : 0; }   // `half` carries `bad` to the fin step
+        else bicg_s_fin(s, t[0], bad);
+    });
+}
+// after t = A z with dots = {<t,s>, <t,t>}: omega = ts/tt ; x += alpha y + omega z ; r = s - omega t ;
+// rho' = <rhat,r> ; rr = <r,r> ; then beta and the new direction need rho' -> separate kernel.
+static __global__ void __launch_bounds__(EW_THREADS)
+bicg_x_kernel(const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ sv,
+              const double* __restrict__ t, const double* __restrict__ rhat, double* __restrict__ x,
+              double* __restrict__ r, size_t n, SolveScal* s, double* partials, uint32_t* ticket, int raw) {
+    __shared__ double sh[32];
+    if (s->done) return;
+    const double ts = s->dots[0], tt = s->dots[1];
+    // ||s|| already tiny (tt == 0): take the half step x += alpha y and stop
+    const bool half = (tt == 0.0) || (s->bad != 0);
+    const double omega = half ? 0.0 : ts / tt;
+    const double alpha = s->alpha;
+    double a0 = 0.0, a1 = 0.0;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        double xi = fma(alpha, y[i], x[i]);
+        xi = fma(omega, z[i], xi);
+        double ri = fma(-omega, t[i], sv[i]);
+        x[i] = xi;
+        r[i] = ri;
+        a0 = fma(rhat[i], ri, a0);
+        a1 = fma(ri, ri, a1);
+    }
+    double mine[2];
+    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
+    mine[1] = abd::block_sum<EW_THREADS>(a1, sh);
+    abd::grid_reduce<EW_THREADS, 2>(mine, partials, ticket, sh, [=](const double(&q)[2]) {
+        s->omega = omega;
+        s->half = half ? 1 : 0;
+        if (raw) { s->red[0] = q[0]; s->red[1] = q[1]; }
+        else bicg_x_fin(s, q[0], q[1]);
+    });
+}
+// p = r + beta (p - omega v) ; y = D^-1 p
+static __global__ void __launch_bounds__(EW_THREADS)
+bicg_p_kernel(const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
+              double* __restrict__ p, double* __restrict__ y, size_t n, const SolveScal* __restrict__ s) {
+    if (s->done) return;
+    const double beta = s->dots[1], omega = s->omega;
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
+        double pi = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+        p[i] = pi;
+        y[i] = dinv[i] * pi;
+    }
+}
+// distributed mode: scalar logic after the all-reduce of SolveScal::red.  which: 2 init, 3 after the s kernel, 4 after the x kernel
+__device__ __forceinline__ void bicg_fin(SolveScal* s, int which, double tol, double v0, double v1) {
+    if (which == 2) bicg_init_fin(s, tol, v0);
+    else if (s->done) return;
+    else if (which == 3) bicg_s_fin(s, v0, s->half != 0);
+    else bicg_x_fin(s, v0, v1);
+}
+
+static __global__ void cg_fin_kernel(SolveScal* s, int which, int parity, double tol) {
+    if (which == 0) cg_init_fin(s, tol, s->red[0], s->red[1]);
+    else if (which >= 2) bicg_fin(s, which, tol, s->red[0], s->red[1]);
+    else if (!s->done) cg_update_fin(s, parity, s->red[0], s->red[1], s->bad != 0);
 }
 
 // shared host helpers implemented in solver.cu

@@ -375,11 +375,15 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// spins until *p has reached seq; gives up after ~2^32 clocks and reports through *err
+// spins until *p has reached seq.  Every collective entry point opens with a stream-ordered NCCL rendezvous
+// (dist.cu: dist_entry_barrier), so these spins only ever cover the skew between ranks that are already inside
+// the same call; the bound (2^36 SM clocks, about half a minute) exists so that a rank that DIED mid-solve turns
+// into an error (AB_ENCCL through *err) on its peers instead of a hung GPU.
+constexpr int AB_WAIT_CLOCKS_LOG2 = 36;
 __device__ __forceinline__ void wait_seq(const uint32_t* p, uint32_t seq, uint32_t* err) {
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys(p) - seq) < 0) {
-        if (clock64() - t0 > (1ll << 32)) { atomicExch(err, 1u); break; }
+        if (clock64() - t0 > (1ll << AB_WAIT_CLOCKS_LOG2)) { atomicExch(err, 1u); break; }
         __nanosleep(20);
     }
 }

@@ -76,110 +76,6 @@ int csr_ensure_work(Csr* c, size_t nvec) {
 }
 double* work_vec(Csr* c, int i) { return c->work + (size_t)i * work_stride(c); }
 
-// ---------------------------------------------------------------- BiCGSTAB kernels (right-preconditioned)
-// r = b ; rhat = b ; p = b ; y = D^-1 p ; x = 0 ; rho = <rhat,r> = bb
-__global__ void __launch_bounds__(EW_THREADS)
-bicg_init_kernel(const double* __restrict__ b, const double* __restrict__ dinv, double* __restrict__ x,
-                 double* __restrict__ r, double* __restrict__ rhat, double* __restrict__ p, double* __restrict__ y,
-                 size_t n, double tol, SolveScal* s, double* partials, uint32_t* ticket) {
-    __shared__ double sh[32];
-    double a1 = 0.0;
-    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
-        double bi = b[i];
-        x[i] = 0.0; r[i] = bi; rhat[i] = bi; p[i] = bi; y[i] = dinv[i] * bi;
-        a1 = fma(bi, bi, a1);
-    }
-    double mine[1];
-    mine[0] = abd::block_sum<EW_THREADS>(a1, sh);
-    abd::grid_reduce<EW_THREADS, 1>(mine, partials, ticket, sh, [=](const double(&t)[1]) {
-        s->rho = t[0]; s->bb = t[0]; s->rr = t[0];
-        s->alpha = 1.0; s->omega = 1.0;
-        s->thr = tol < 0 ? -1.0 : tol * tol * t[0];
-        s->iters = 0;
-        s->bad = 0;
-        s->breakdown = isfinite(t[0]) ? 0 : 1;
-        s->done = (t[0] == 0.0 || s->breakdown) ? 1 : 0;
-    });
-}
-// after v = A y with dots[0] = <v, rhat>: alpha = rho/<rhat,v> ; s = r - alpha v ; z = D^-1 s ; ss = <s,s>
-__global__ void __launch_bounds__(EW_THREADS)
-bicg_s_kernel(const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
-              double* __restrict__ sv, double* __restrict__ z, size_t n, SolveScal* s, double* partials,
-              uint32_t* ticket) {
-    __shared__ double sh[32];
-    if (s->done) return;
-    const double rv = s->dots[0];
-    const bool bad = (rv == 0.0) || !isfinite(rv) || !isfinite(s->rho);
-    const double alpha = bad ? 0.0 : s->rho / rv;
-    double a0 = 0.0;
-    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
-        double si = fma(-alpha, v[i], r[i]);
-        sv[i] = si;
-        z[i]  = dinv[i] * si;
-        a0 = fma(si, si, a0);
-    }
-    double mine[1];
-    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
-    abd::grid_reduce<EW_THREADS, 1>(mine, partials, ticket, sh, [=](const double(&t)[1]) {
-        s->alpha = alpha;
-        s->rr = t[0];   // provisional: ||s||^2
-        s->bad = (s->thr >= 0.0 && t[0] <= s->thr) ? 1 : 0;   // s already below tolerance: take the half step
-        if (bad || !isfinite(t[0])) { s->breakdown = 1; s->done = 1; }
-    });
-}
-// after t = A z with dots = {<t,s>, <t,t>}: omega = ts/tt ; x += alpha y + omega z ; r = s - omega t ;
-// rho' = <rhat,r> ; rr = <r,r> ; then beta and the new direction need rho' -> separate kernel.
-__global__ void __launch_bounds__(EW_THREADS)
-bicg_x_kernel(const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ sv,
-              const double* __restrict__ t, const double* __restrict__ rhat, double* __restrict__ x,
-              double* __restrict__ r, size_t n, SolveScal* s, double* partials, uint32_t* ticket) {
-    __shared__ double sh[32];
-    if (s->done) return;
-    const double ts = s->dots[0], tt = s->dots[1];
-    // ||s|| already tiny (tt == 0): take the half step x += alpha y and stop
-    const bool half = (tt == 0.0) || (s->bad != 0);
-    const double omega = half ? 0.0 : ts / tt;
-    const double alpha = s->alpha;
-    double a0 = 0.0, a1 = 0.0;
-    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
-        double xi = fma(alpha, y[i], x[i]);
-        xi = fma(omega, z[i], xi);
-        double ri = fma(-omega, t[i], sv[i]);
-        x[i] = xi;
-        r[i] = ri;
-        a0 = fma(rhat[i], ri, a0);
-        a1 = fma(ri, ri, a1);
-    }
-    double mine[2];
-    mine[0] = abd::block_sum<EW_THREADS>(a0, sh);
-    mine[1] = abd::block_sum<EW_THREADS>(a1, sh);
-    abd::grid_reduce<EW_THREADS, 2>(mine, partials, ticket, sh, [=](const double(&q)[2]) {
-        const double rho_old = s->rho;
-        s->rho = q[0];
-        s->rr  = q[1];
-        s->iters += 1;
-        // beta for the next direction, stored in dots[1] (dots[] are free until the next SpMV)
-        double beta = (q[0] / rho_old) * (alpha / omega);
-        s->dots[1] = beta;
-        s->omega = omega;
-        if (!isfinite(q[0]) || !isfinite(q[1]) || !isfinite(omega)) { s->breakdown = 1; s->done = 1; }
-        else if (s->thr >= 0.0 && q[1] <= s->thr) s->done = 1;
-        else if (half || omega == 0.0 || q[0] == 0.0 || !isfinite(beta)) { s->breakdown = 1; s->done = 1; }
-    });
-}
-// p = r + beta (p - omega v) ; y = D^-1 p
-__global__ void __launch_bounds__(EW_THREADS)
-bicg_p_kernel(const double* __restrict__ r, const double* __restrict__ v, const double* __restrict__ dinv,
-              double* __restrict__ p, double* __restrict__ y, size_t n, const SolveScal* __restrict__ s) {
-    if (s->done) return;
-    const double beta = s->dots[1], omega = s->omega;
-    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * EW_THREADS) {
-        double pi = fma(beta, fma(-omega, v[i], p[i]), r[i]);
-        p[i] = pi;
-        y[i] = dinv[i] * pi;
-    }
-}
-
 // grad_vv[t] = -x[row_t] * u[col_t]
 __global__ void grad_vv_kernel(const int32_t* __restrict__ slot, const int32_t* __restrict__ entry_row,
                                const int32_t* __restrict__ colind, const double* __restrict__ x,
@@ -343,7 +239,7 @@ static int run_bicgstab(Csr* c, const double* b, double* x, double tol, int maxi
            *sv = work_vec(c, 4), *t = work_vec(c, 5), *y = work_vec(c, 6), *z = work_vec(c, 7);
     SolveScal* s = (SolveScal*)c->scal;
     const unsigned g = ew_grid(n);
-    bicg_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->dinv, x, r, rhat, p, y, n, tol, s, c->partials, c->ticket);
+    bicg_init_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->dinv, x, r, rhat, p, y, n, tol, s, c->partials, c->ticket, 0);
     AB_LAUNCH_CHECK();
     int check = (int)opt("check_every", 0);
     if (check <= 0) check = n > (size_t)4000000 ? 8 : 32;
@@ -353,10 +249,10 @@ static int run_bicgstab(Csr* c, const double* b, double* x, double tol, int maxi
         int chunk = maxit - it < check ? maxit - it : check;
         for (int k = 0; k < chunk; ++k, ++it) {
             AB_TRY(launch_spmv(c, y, v, rhat, s->dots, c->partials, c->ticket, &s->done));
-            bicg_s_kernel<<<g, EW_THREADS, 0, stream()>>>(r, v, c->dinv, sv, z, n, s, c->partials, c->ticket);
+            bicg_s_kernel<<<g, EW_THREADS, 0, stream()>>>(r, v, c->dinv, sv, z, n, s, c->partials, c->ticket, 0);
             AB_LAUNCH_CHECK();
             AB_TRY(launch_spmv(c, z, t, sv, s->dots, c->partials, c->ticket, &s->done));
-            bicg_x_kernel<<<g, EW_THREADS, 0, stream()>>>(y, z, sv, t, rhat, x, r, n, s, c->partials, c->ticket);
+            bicg_x_kernel<<<g, EW_THREADS, 0, stream()>>>(y, z, sv, t, rhat, x, r, n, s, c->partials, c->ticket, 0);
             AB_LAUNCH_CHECK();
             bicg_p_kernel<<<g, EW_THREADS, 0, stream()>>>(r, v, c->dinv, p, y, n, s);
             AB_LAUNCH_CHECK();
@@ -630,7 +526,10 @@ static int solve_dev_impl(Csr* c, Method meth, const double* b, double* x, doubl
             AB_LAUNCH_CHECK();
         }
         if (iters) *iters = total;
-        return AB_OK;
+        if (!(tr > tol * 10)) return AB_OK;
+        // refinement ran out of rounds / iterations or its correction solve broke down with the true residual
+        // still above the bar: not a success — fall through to the fallbacks and error reporting below
+        fin.iters = total;
     }
     // breakdown or maxit: vet with the true residual (BiCGSTAB can "break down" at the solution)
     double tr = rel;

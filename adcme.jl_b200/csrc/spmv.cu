@@ -624,16 +624,7 @@ spmv_rowpat_kernel(const uint8_t* __restrict__ rowcode, const int4* __restrict__
     const unsigned nb = (LIST && hw.flags) ? min(hw.n_before, ntiles) : ntiles;
     rowpat_walk<R, LIST, false>(rowcode, s_ent, s_info, x, y, m, 0u, nb, run, tile_list, dotvec, dot, dot2);
     if (LIST && nb < ntiles) {
-        if (t < (unsigned)hw.world && hw.recv_cnt[t] > 0) {                            // acquire the halos
-            const long long t0 = clock64();
-            uint32_t v;
-            do {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(hw.flags + t) : "memory");
-                if ((int32_t)(v - hw.seq) >= 0) break;
-                if (clock64() - t0 > (1ll << 32)) { atomicExch(hw.err, 1u); break; }
-                __nanosleep(20);
-            } while (true);
-        }
+        if (t < (unsigned)hw.world && hw.recv_cnt[t] > 0) abd::wait_seq(hw.flags + t, hw.seq, hw.err);   // acquire the halos
         __syncthreads();
         // boundary tiles one per CTA (run = 1): they are few, the tail must be as short as possible
         rowpat_walk<R, LIST, true>(rowcode, s_ent, s_info, x, y, m, nb, ntiles, 1u, tile_list, dotvec, dot, dot2);

@@ -3,6 +3,8 @@
 //
 //  * ab_poisson3d_csr: 3-D 7-point Dirichlet Laplacian (diag 6, off -1), rows [row_lo,row_hi) with
 //    GLOBAL column ids — the matrix of BASELINE.json configs[1] and configs[2].
+//  * ab_poisson3d_kappa_csr: the same pattern with variable coefficients (face weights from a cell field) — the
+//    general-CSR leg of the benchmark and of the parity tests (no value dictionary applies).
 //  * ab_poisson2d_csr / _update / _grad: the reference's own inverse-problem operator,
 //    docs/src/assets/Codes/MPI/ccode/GetPoissonMatrix.h:15-72 (GetPoissonMatrixForward /
 //    GetPoissonGrad): off-diagonals kext(nb)+kext(i,j), diagonal -(sum of 4 neighbours + 4 kext(i,j)).
@@ -20,22 +22,43 @@ __global__ void p3d_count_kernel(int64_t nx, int64_t ny, int64_t nz, int64_t row
     int64_t x = r % nx, y = (r / nx) % ny, z = r / (nx * ny);
     cnt[l] = 1u + (x > 0) + (x < nx - 1) + (y > 0) + (y < ny - 1) + (z > 0) + (z < nz - 1);
 }
+// kappa == nullptr: constant coefficients (diag 6, off -1).  Otherwise the finite-volume operator of
+// -div(kappa grad u) with Dirichlet walls: the face between cells i and j weighs (kappa_i + kappa_j) / 2, a
+// wall face weighs kappa_i; off-diagonal = -w, diagonal = sum of the six face weights (symmetric, SPD for
+// kappa > 0) — the 3-D analogue of GetPoissonMatrix.h:24-45.  kappa is the GLOBAL cell field [nx*ny*nz].
 __global__ void p3d_fill_kernel(int64_t nx, int64_t ny, int64_t nz, int64_t row_lo, int64_t m,
                                 const int32_t* __restrict__ rowptr, int32_t* __restrict__ colind,
-                                double* __restrict__ values) {
+                                double* __restrict__ values, const double* __restrict__ kappa) {
     int64_t l = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= m) return;
     int64_t r = row_lo + l;
     int64_t x = r % nx, y = (r / nx) % ny, z = r / (nx * ny);
     int p = rowptr[l];
     const int64_t sxy = nx * ny;
-    if (z > 0)      { colind[p] = (int32_t)(r - sxy); values[p++] = -1.0; }
-    if (y > 0)      { colind[p] = (int32_t)(r - nx);  values[p++] = -1.0; }
-    if (x > 0)      { colind[p] = (int32_t)(r - 1);   values[p++] = -1.0; }
-    colind[p] = (int32_t)r; values[p++] = 6.0;
-    if (x < nx - 1) { colind[p] = (int32_t)(r + 1);   values[p++] = -1.0; }
-    if (y < ny - 1) { colind[p] = (int32_t)(r + nx);  values[p++] = -1.0; }
-    if (z < nz - 1) { colind[p] = (int32_t)(r + sxy); values[p++] = -1.0; }
+    if (!kappa) {
+        if (z > 0)      { colind[p] = (int32_t)(r - sxy); values[p++] = -1.0; }
+        if (y > 0)      { colind[p] = (int32_t)(r - nx);  values[p++] = -1.0; }
+        if (x > 0)      { colind[p] = (int32_t)(r - 1);   values[p++] = -1.0; }
+        colind[p] = (int32_t)r; values[p++] = 6.0;
+        if (x < nx - 1) { colind[p] = (int32_t)(r + 1);   values[p++] = -1.0; }
+        if (y < ny - 1) { colind[p] = (int32_t)(r + nx);  values[p++] = -1.0; }
+        if (z < nz - 1) { colind[p] = (int32_t)(r + sxy); values[p++] = -1.0; }
+        return;
+    }
+    const double kc = kappa[r];
+    const double wzm = z > 0      ? 0.5 * (kc + kappa[r - sxy]) : kc;
+    const double wym = y > 0      ? 0.5 * (kc + kappa[r - nx])  : kc;
+    const double wxm = x > 0      ? 0.5 * (kc + kappa[r - 1])   : kc;
+    const double wxp = x < nx - 1 ? 0.5 * (kc + kappa[r + 1])   : kc;
+    const double wyp = y < ny - 1 ? 0.5 * (kc + kappa[r + nx])  : kc;
+    const double wzp = z < nz - 1 ? 0.5 * (kc + kappa[r + sxy]) : kc;
+    if (z > 0)      { colind[p] = (int32_t)(r - sxy); values[p++] = -wzm; }
+    if (y > 0)      { colind[p] = (int32_t)(r - nx);  values[p++] = -wym; }
+    if (x > 0)      { colind[p] = (int32_t)(r - 1);   values[p++] = -wxm; }
+    colind[p] = (int32_t)r; values[p++] = ((wzm + wym) + (wxm + wxp)) + (wyp + wzp);
+    if (x < nx - 1) { colind[p] = (int32_t)(r + 1);   values[p++] = -wxp; }
+    if (y < ny - 1) { colind[p] = (int32_t)(r + nx);  values[p++] = -wyp; }
+    if (z < nz - 1) { colind[p] = (int32_t)(r + sxy); values[p++] = -wzp; }
 }
 
 #define KEXT(i, j) kext[(size_t)(i) * (n + 2) + (j)]
@@ -101,7 +124,7 @@ using namespace ab;
 
 extern "C" {
 
-int ab_poisson3d_csr(int64_t nx, int64_t ny, int64_t nz, int64_t row_lo, int64_t row_hi, int64_t* out_h) {
+static int poisson3d_impl(int64_t nx, int64_t ny, int64_t nz, const double* kappa_, int64_t row_lo, int64_t row_hi, int64_t* out_h) {
     AB_TRY(ensure_device());
     if (!out_h || nx < 1 || ny < 1 || nz < 1) return fail(AB_EINVAL, "bad grid");
     const int64_t N = nx * ny * nz;
@@ -112,6 +135,8 @@ int ab_poisson3d_csr(int64_t nx, int64_t ny, int64_t nz, int64_t row_lo, int64_t
     Csr* c = new Csr();
     c->m = m; c->n = N;
     auto body = [&]() -> int {
+        In<double> kappa;
+        if (kappa_) AB_TRY(kappa.bind(kappa_, (size_t)N));
         DevBuf<uint32_t> cnt, total;
         AB_TRY(cnt.alloc(m + 1)); AB_TRY(total.alloc(1));
         AB_TRY(dev_alloc((void**)&c->rowptr, (size_t)(m + 1) * sizeof(int32_t)));
@@ -126,16 +151,28 @@ int ab_poisson3d_csr(int64_t nx, int64_t ny, int64_t nz, int64_t row_lo, int64_t
         c->nnz = nnz; c->T = nnz;
         AB_TRY(alloc_csr(c));
         if (m) {
-            p3d_fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream()>>>(nx, ny, nz, row_lo, m, c->rowptr, c->colind, c->values);
+            p3d_fill_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream()>>>(nx, ny, nz, row_lo, m, c->rowptr, c->colind, c->values,
+                                                                             kappa_ ? kappa.d : nullptr);
             AB_LAUNCH_CHECK();
         }
         AB_TRY(csr_finalize(c));
+        if (kappa.tmp.p) AB_CUDA(cudaStreamSynchronize(stream()));
         return AB_OK;
     };
     int rc = body();
     if (rc != AB_OK) { delete c; return rc; }
     *out_h = csr_put(c);
     return AB_OK;
+}
+
+int ab_poisson3d_csr(int64_t nx, int64_t ny, int64_t nz, int64_t row_lo, int64_t row_hi, int64_t* out_h) {
+    return poisson3d_impl(nx, ny, nz, nullptr, row_lo, row_hi, out_h);
+}
+
+int ab_poisson3d_kappa_csr(int64_t nx, int64_t ny, int64_t nz, const double* kappa, int64_t row_lo, int64_t row_hi,
+                           int64_t* out_h) {
+    if (!kappa) return fail(AB_EINVAL, "kappa is null");
+    return poisson3d_impl(nx, ny, nz, kappa, row_lo, row_hi, out_h);
 }
 
 int ab_poisson2d_csr(int64_t n, const double* kext_, int sign, int64_t* out_h) {

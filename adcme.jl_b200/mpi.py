@@ -90,6 +90,18 @@ class mpi_SparseTensor:
         check(lib.ab_poisson3d_csr(nx, ny, nz, lo, hi + 1, C.byref(h)))
         return cls(SparseTensor.from_handle(h.value), lo, hi, N)
 
+    @classmethod
+    def poisson3d_kappa(cls, kappa, nx: int, ny: int, nz: int, rank: int | None = None, world: int | None = None):
+        """Same partition, variable coefficients: kappa is the GLOBAL cell field [nx*ny*nz] (host or device)."""
+        rank = _rank if rank is None else rank
+        world = _world if world is None else world
+        N = nx * ny * nz
+        lo, hi = row_partition(N, world, rank, align=nx * ny)
+        kk, pk = as_array(kappa, np.float64)
+        h = C.c_int64(0)
+        check(lib.ab_poisson3d_kappa_csr(nx, ny, nz, pk, lo, hi + 1, C.byref(h)))
+        return cls(SparseTensor.from_handle(h.value), lo, hi, N)
+
     @property
     def nloc(self) -> int:
         return self.iupper - self.ilower + 1
@@ -114,11 +126,47 @@ class mpi_SparseTensor:
         rows; grad_b_local).  Collective — every rank calls it."""
         kg, pg = as_array(grad_u_local, np.float64)
         ku, pu = as_array(u_local, np.float64)
-        nnz = self.local.query()[2]
+        nnz = self.nnz_local
         gv = empty_like_kind(kg, (nnz,), np.float64)
         gf = empty_like_kind(kg, (self.nloc,), np.float64)
         check(lib.ab_dist_solve_grad(self._dh, pg, pu, ptr(gv), ptr(gf), tol, maxit, None, None))
         return gv, gf
+
+    def adjoint(self):
+        """adjoint(A::mpi_SparseTensor) (mpi.jl:544-563): A' under the same row partition.  Collective."""
+        dh = C.c_int64(0)
+        check(lib.ab_dist_transpose(self._dh, C.byref(dh)))
+        return mpi_SparseTensor._from_dist_handle(dh.value, self.ilower, self.iupper, self.N)
+
+    @property
+    def T(self):
+        return self.adjoint()
+
+    def coo(self):
+        """This rank's rows as (idx2 [nnz,2] int64: local row, GLOBAL column; values) — mpi_get_matrix (MPITensor.h:39-52)."""
+        nnz = self.nnz_local
+        idx2, vals = np.empty((nnz, 2), np.int64), np.empty(nnz, np.float64)
+        check(lib.ab_dist_export_coo(self._dh, ptr(idx2), ptr(vals)))
+        return idx2, vals
+
+    def to_SparseTensor(self) -> SparseTensor:
+        """SparseTensor(sp::mpi_SparseTensor) (mpi.jl:502-504): the local row block, nloc x N."""
+        idx2, vals = self.coo()
+        return SparseTensor(idx2[:, 0] + 1, idx2[:, 1] + 1, vals, self.nloc, self.N)
+
+    @classmethod
+    def _from_dist_handle(cls, dh: int, ilower: int, iupper: int, N: int):
+        self = cls.__new__(cls)
+        self.local, self.ilower, self.iupper, self.N, self._dh = None, int(ilower), int(iupper), int(N), int(dh)
+        return self
+
+    @property
+    def nnz_local(self) -> int:
+        if self.local is not None:
+            return self.local.query()[2]
+        n = C.c_int64(0)
+        check(lib.ab_dist_query(self._dh, None, None, C.byref(n)))
+        return n.value
 
     def cg_fixed(self, b_local, iters: int):
         kb, pb = as_array(b_local, np.float64)

@@ -8,7 +8,7 @@ from dataclasses import dataclass, field
 @dataclass
 class OptionsSparse:
     auto_reorder: bool = True   # options.jl:12 — find() returns row-major sorted triplets
-    solver: str = "SparseLU"    # options.jl:11 — mapped: SparseLU/SparseQR -> BiCGSTAB, LLT/LDLT -> CG
+    solver: str = "SparseLU"    # options.jl:11 — mapped: LLT/LDLT -> CG; SparseLU/SparseQR/auto -> CG first when the matrix is bitwise symmetric with a positive diagonal, else BiCGSTAB (+ dense LU for n <= 2048)
     tol: float = 1e-12          # new: relative residual target of the iterative solvers
     maxiter: int = 0            # new: 0 = library default (10 n + 100, capped)
 
@@ -38,7 +38,7 @@ class OptionsNewtonRaphson:
 
 @dataclass
 class OptionsMPI:
-    solver: str = "BoomerAMG"   # options.jl:56 — accepted and mapped to Jacobi-PCG
+    solver: str = "BoomerAMG"   # options.jl:56 — BoomerAMG/auto -> CG on symmetric positive-diagonal systems, BiCGSTAB otherwise; GMRES -> BiCGSTAB
     printlevel: int = 2         # options.jl:57 — kept for signature compatibility
 
 

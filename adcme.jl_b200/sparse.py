@@ -356,15 +356,30 @@ def mul(A: SparseTensor, o):
     return _spmm_raw(A, o, False)
 
 
+def _grad_operands(A: SparseTensor, o):
+    """Tensors for the autograd path; values changed in place (an optimiser step on a parameter) are pushed to the
+    cached CSR handle first, as mul() does — otherwise x*A would multiply with stale assembled values."""
+    import torch
+
+    if not _is_torch(o):
+        o = torch.as_tensor(np.asarray(o, dtype=np.float64), device=A.vv.device)
+    vv = A.vv if _is_torch(A.vv) else torch.as_tensor(np.asarray(A.vv), device=o.device)
+    if A._h is not None and _is_torch(A.vv):
+        A._refresh_values(A.vv)
+    return vv, o
+
+
 def rmul(o, A: SparseTensor):
     """o * s = (s' o')' (sparse.jl:247-253)."""
     if len(_shape(o)) == 1:
         if _needs_grad(A.vv, o):
-            return _autograd()[0].apply(A.vv, o, A, True)
+            vv, o = _grad_operands(A, o)
+            return _autograd()[0].apply(vv, o, A, True)
         return _spmm_raw(A, o, True)
-    ot = o.t().contiguous() if _is_torch(o) else np.ascontiguousarray(np.asarray(o).T)
     if _needs_grad(A.vv, o):
-        return _autograd()[0].apply(A.vv, ot, A, True).t()
+        vv, o = _grad_operands(A, o)
+        return _autograd()[0].apply(vv, o.t().contiguous(), A, True).t()
+    ot = o.t().contiguous() if _is_torch(o) else np.ascontiguousarray(np.asarray(o).T)
     r = _spmm_raw(A, ot, True)
     return r.t() if _is_torch(r) else r.T
 

@@ -134,12 +134,21 @@ int ab_spmm_grad_dense(int64_t h, const double* dY, int64_t k, double* dX);
 /* ---- sparse `\` and its adjoint (a9, a10, a11) ------------------------
  * src/sparse.jl:413-445; SparseSolver.h:13-70; Solve.h:3-33.
  * method: "CG" | "BiCGSTAB" | "auto", plus the reference's strings mapped as
- *   "SimplicialLLT","SimplicialLDLT" -> CG ; "SparseLU","SparseQR" -> BiCGSTAB.
- * Both solvers are Jacobi-preconditioned.  tol <= 0 / maxit <= 0 pick the
- * options "tol" / "maxit".  Convergence test: ||f - A u||_2 <= tol*||f||_2 on
- * the recurrence residual.  iters / relres may be NULL.
- * Non-convergence returns AB_ENOCONV (u still holds the last iterate),
- * breakdown AB_EBREAKDOWN — never a silent NaN.
+ *   "SimplicialLLT","SimplicialLDLT" -> CG (caller asserts SPD);
+ *   "SparseLU","SparseQR","auto"    -> CG FIRST when the matrix is bitwise symmetric with a
+ *       positive diagonal (one cached check per set of values — the FEM / stencil systems
+ *       this path exists for; the adjoint then needs no transpose), BiCGSTAB otherwise or
+ *       when CG breaks down / stalls, and a one-CTA dense partial-pivot LU when BiCGSTAB
+ *       fails too and n <= 2048 (a direct solver never fails on a regular matrix).
+ * Both Krylov solvers are Jacobi-preconditioned: the supported matrix class above 2048
+ * unknowns is "Jacobi-Krylov converges" (SPD, diagonally dominant, mildly unsymmetric);
+ * strongly indefinite / saddle-point systems of that size return AB_ENOCONV / AB_EBREAKDOWN
+ * where the reference's SparseLU would succeed.  tol <= 0 / maxit <= 0 pick the options
+ * "tol" / "maxit".  The iteration stops on the recurrence residual; the answer is then VETTED
+ * by the true residual ||f - A u||_2 / ||f||_2 (one more SpMV) and refined by correction
+ * solves when it had drifted: AB_OK means true relres <= 10*tol, and *relres receives the
+ * true value.  iters / relres may be NULL.  Non-convergence returns AB_ENOCONV (u still
+ * holds the last iterate), breakdown AB_EBREAKDOWN — never a silent NaN.
  * ab_solve_grad: x = A^{-T} grad_u ; grad_f = x ; grad_vv[t] = -x[i_t]*u[j_t]
  * for every input triplet t (duplicates each get the same formula). */
 int ab_solve(int64_t h, const char* method, const double* f, double* u,
@@ -176,6 +185,11 @@ int ab_factorized_solve_grad(int64_t id, const double* grad_out, const double* o
  * built direct-to-CSR on the device.  Column ids are GLOBAL. */
 int ab_poisson3d_csr(int64_t nx, int64_t ny, int64_t nz, int64_t row_lo, int64_t row_hi,
                      int64_t* out_h);
+/* the same pattern with variable coefficients: finite-volume -div(kappa grad u), Dirichlet walls,
+ * face weight (kappa_i + kappa_j)/2 (wall faces: kappa_i); kappa is the GLOBAL cell field
+ * [nx*ny*nz] (3-D analogue of GetPoissonMatrix.h:24-45, sign chosen SPD).          */
+int ab_poisson3d_kappa_csr(int64_t nx, int64_t ny, int64_t nz, const double* kappa,
+                           int64_t row_lo, int64_t row_hi, int64_t* out_h);
 /* 2-D 5-point variable-coefficient operator from a halo-extended kext[(n+2)*(n+2)]:
  * docs/src/assets/Codes/MPI/ccode/GetPoissonMatrix.h:15-51, with sign so that
  * sign=+1 reproduces the reference values and sign=-1 the SPD matrix (-A).
@@ -288,17 +302,35 @@ int ab_dist_init(int rank, int world, const void* id128);
 int ab_dist_finalize(void);
 int ab_dist_csr_create(int64_t h_local, int64_t ilower, int64_t iupper, int64_t N,
                        int64_t* out_dh);
+/* rows owned, halo columns referenced, stored entries of this rank's block (any output may be NULL) */
+int ab_dist_query(int64_t dh, int64_t* nloc, int64_t* nhalo, int64_t* nnz_local);
 int ab_dist_spmv(int64_t dh, const double* x_local, double* y_local);
+/* method (options.mpi.solver, src/options.jl:54-58): "CG" (caller asserts SPD); "BiCGSTAB" or the reference's
+ * "GMRES" -> right-Jacobi BiCGSTAB (any regular matrix); "BoomerAMG" or "auto" -> CG when the matrix is
+ * symmetric across ranks (bitwise check, cached per set of values) with a positive diagonal, BiCGSTAB
+ * otherwise or when CG fails.  Every answer is vetted by the TRUE residual ||f - A u|| / ||f|| (one more
+ * distributed SpMV) and refined by correction solves when the recurrence residual had drifted: AB_OK means
+ * true relres <= 10 * tol, anything else returns AB_ENOCONV / AB_EBREAKDOWN (never silent).  tol <= 0 -> 1e-10
+ * (the reference's Hypre tolerance, MPITensor.h:66,91); *relres receives the true relative residual.         */
 int ab_dist_solve(int64_t dh, const char* method, const double* f_local, double* u_local,
                   double tol, int maxit, int* iters, double* relres);
 int ab_dist_cg_fixed(int64_t dh, const double* f_local, double* u_local, int iters,
                      double* relres);
-/* adjoint of the distributed solve (collective): x = A^{-1} grad_u (CG: A symmetric), grad_f = x on the
+/* adjoint of the distributed solve (collective): x = A^{-T} grad_u — solved with A itself when the matrix is
+ * symmetric across ranks, otherwise with the distributed transpose (built once per set of values) —, grad_f = x on the
  * local rows, grad_vals[e] = -x[row_e]*u[col_e] for every stored entry e of this rank's rows in the order
  * of the local CSR handle (u at off-rank columns arrives by one halo exchange).  Either output may be NULL. */
 int ab_dist_solve_grad(int64_t dh, const double* grad_u_local, const double* u_local,
                        double* grad_vals_local /*[nnz_local]*/, double* grad_f_local /*[nloc]*/,
                        double tol, int maxit, int* iters, double* relres);
+/* SparseTensor(sp::mpi_SparseTensor) — MPIGetMatrix (MPITensor.h:39-52, src/mpi.jl:502-504): this rank's rows
+ * as COO; idx2 is the row-major [nnz_local,2] int64 index matrix (row relative to ilower, GLOBAL column),
+ * entries in the order of the local CSR the handle was created from.  Either output may be NULL.            */
+int ab_dist_export_coo(int64_t dh, int64_t* idx2 /*[nnz_local,2]*/, double* vals /*[nnz_local]*/);
+/* adjoint(A::mpi_SparseTensor) — MPITensorTranspose.h:79-141, src/mpi.jl:544-563 (collective): every stored
+ * entry travels to the rank that owns its column (one all-to-all-v of COO blocks); the new handle holds this
+ * rank's rows of A' under the same row partition.                                                           */
+int ab_dist_transpose(int64_t dh, int64_t* out_dh);
 int ab_dist_destroy(int64_t dh);
 
 /* ---- timers (reference: MPITensor_Solve_Timer_*, MPITensor.cpp:15-21) -- */

@@ -326,6 +326,13 @@ function b200_poisson3d(nx::Integer, ny::Integer, nz::Integer, row_lo::Integer=0
     h[]
 end
 
+"Variable-coefficient 7-point operator from the global cell field kappa[nx*ny*nz] (rows [row_lo,row_hi))."
+function b200_poisson3d(kappa::Vector{Float64}, nx::Integer, ny::Integer, nz::Integer, row_lo::Integer=0, row_hi::Integer=nx * ny * nz)
+    h = Ref{Int64}(0)
+    chk(ccall((:ab_poisson3d_kappa_csr, LIB), Cint, (Int64, Int64, Int64, Ptr{Cdouble}, Int64, Int64, Ref{Int64}), nx, ny, nz, kappa, row_lo, row_hi, h))
+    h[]
+end
+
 # ---- mpi_SparseTensor \ b and its backward (src/mpi.jl:420-508) — one Julia process per GPU -------------
 "Rank 0 creates the 128-byte id, the host broadcasts it with its own transport (MPI.Bcast!), every rank joins."
 function b200_dist_unique_id()
