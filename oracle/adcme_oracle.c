@@ -351,6 +351,13 @@ EXPORT void orc_poisson3d_csr(int64_t nx, int64_t ny, int64_t nz, int32_t* rowpt
         if (z < nz - 1) { colind[p] = (int32_t)(r + sxy); values[p++] = -1.0; }
     }
 }
+EXPORT void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 EXPORT int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -492,6 +492,12 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the CPU baseline legs; torchrun exports OMP_NUM_THREADS=1, so bench.py sets this explicitly."""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def pcg_jacobi(rowptr, colind, values, b, tol: float = 1e-12, maxit: int = 10000):
     rowptr, colind, values, b = _i32(rowptr), _i32(colind), _f64(values), _f64(b)
     n = len(b)
