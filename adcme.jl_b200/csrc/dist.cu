@@ -372,6 +372,92 @@ cgs_direction_p2p_kernel(const double* __restrict__ r, double* __restrict__ p, d
     }
 }
 
+// K3'': K3' with the NEXT iteration's halo push folded in.  Every CTA owns one contiguous chunk of the vectors;
+// after updating its chunk of p it stores the boundary values that live in that chunk straight into the
+// consumers' halo tails (peer-mapped pointers, NVLink), and the last CTA to finish publishes the halo sequence
+// number together with the CG scalar logic.  One launch and one kernel boundary fewer per iteration; the halo
+// flight overlaps the tail of this kernel and the interior tiles of the following SpMV.  Needs n even.
+static __global__ void __launch_bounds__(EW_THREADS)
+cgs_direction_push_kernel(const double* __restrict__ r, double* __restrict__ p, double* __restrict__ x, size_t n, int parity,
+                          SolveScal* s, uint32_t* ticket, P2PBlock* blk, int world, uint32_t seq_in,
+                          const int32_t* __restrict__ send_idx, const int* __restrict__ send_off, const int* __restrict__ send_cnt,
+                          double* const* __restrict__ peer_x, P2PBlock* const* __restrict__ peer_blk, int me, uint32_t halo_seq) {
+    __shared__ double sh2[2];
+    __shared__ bool s_last;
+    __shared__ int s_rng[2];
+    if (s->done) return;                       // K2' did not run either: nothing is owed
+    const size_t n2 = n >> 1;
+    const size_t per = (n2 + gridDim.x - 1) / gridDim.x;
+    const size_t c0 = min(n2, (size_t)blockIdx.x * per), c1 = min(n2, c0 + per);
+    const double2* r2 = reinterpret_cast<const double2*>(r);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    double2* x2 = reinterpret_cast<double2*>(x);
+    // first elements in flight before the wait
+    const size_t i0 = c0 + threadIdx.x;
+    double2 rv0 = make_double2(0.0, 0.0), pv0 = rv0, xv0 = rv0;
+    if (i0 < c1) { rv0 = r2[i0]; pv0 = p2[i0]; xv0 = x2[i0]; }
+    double rr, rr_dup;
+    abd::p2p_wait_sum2(blk, world, seq_in, sh2, rr, rr_dup);
+    const bool bad = s->bad != 0;
+    const double alpha = s->alpha, rz_old = s->rz[parity];
+    const bool stop = bad || !isfinite(rr) || (s->thr >= 0.0 && rr <= s->thr);   // what cg_update_fin will decide
+    const double beta = rr / rz_old;
+    if (!stop) {
+        if (i0 < c1) {
+            xv0.x = fma(alpha, pv0.x, xv0.x); xv0.y = fma(alpha, pv0.y, xv0.y);
+            pv0.x = fma(beta, pv0.x, rv0.x);  pv0.y = fma(beta, pv0.y, rv0.y);
+            x2[i0] = xv0; p2[i0] = pv0;
+        }
+        for (size_t i = i0 + EW_THREADS; i < c1; i += EW_THREADS) {
+            double2 rv = r2[i], pv = p2[i], xv = x2[i];
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            pv.x = fma(beta, pv.x, rv.x);  pv.y = fma(beta, pv.y, rv.y);
+            x2[i] = xv;
+            p2[i] = pv;
+        }
+        __syncthreads();                        // this CTA's chunk of p is complete
+        const int lo = (int)(2 * c0), hi = (int)(2 * c1);
+        for (int pr = 0; pr < world; ++pr) {
+            const int a = send_off[pr], b = a + send_cnt[pr];
+            if (a == b) continue;
+            if (threadIdx.x < 2) {              // send_idx is ascending inside a destination group
+                const int target = threadIdx.x == 0 ? lo : hi;
+                int u = a, v = b;
+                while (u < v) { const int mid = (u + v) >> 1; if (send_idx[mid] < target) u = mid + 1; else v = mid; }
+                s_rng[threadIdx.x] = u;
+            }
+            __syncthreads();
+            const int ka = s_rng[0], kb = s_rng[1];
+            double* dst = peer_x[pr];
+            for (int k = ka + (int)threadIdx.x; k < kb; k += EW_THREADS) dst[k - a] = p[send_idx[k]];
+            __syncthreads();
+        }
+    } else {
+        if (i0 < c1) { xv0.x = fma(alpha, pv0.x, xv0.x); xv0.y = fma(alpha, pv0.y, xv0.y); x2[i0] = xv0; }
+        for (size_t i = i0 + EW_THREADS; i < c1; i += EW_THREADS) {
+            double2 pv = p2[i], xv = x2[i];
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            x2[i] = xv;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (!stop && (int)threadIdx.x < world && send_cnt[threadIdx.x] > 0)
+            abd::st_release_sys(&peer_blk[threadIdx.x]->halo_flag[me], halo_seq);
+        if (threadIdx.x == 0) {
+            *ticket = 0;
+            cg_update_fin(s, parity, rr, rr, bad);
+        }
+    }
+}
+
 // adjoint gradient of the distributed solve, per stored entry of the local block:
 // g[e] = -x[row_e] * u_ext[col_e]   (SparseSolver.h:60-68 restricted to the rows this rank owns; col_e is
 // the re-indexed column, so halo columns read the halo tail filled by the exchange)
@@ -382,8 +468,10 @@ static __global__ void dist_grad_vals_kernel(const int32_t* __restrict__ entry_r
     if (e < nnz) g[e] = -x[entry_row[e]] * uext[colind[e]];
 }
 
-static int halo_begin(DistCsr* d) {
+// pushed_already: the previous K3'' pushed this exchange under sequence number halo_seq (already advanced)
+static int halo_begin(DistCsr* d, bool pushed_already = false) {
     if (g_world == 1) return AB_OK;
+    if (d->p2p && pushed_already) return AB_OK;
     if (d->p2p) {
         ++d->halo_seq;
         if (d->nsend) {
@@ -445,10 +533,10 @@ static int allreduce2_fin(DistCsr* d, SolveScal* s, int which, int parity, doubl
 // push_seq != 0: the SpMV's last CTA pushes the fused dots into the peers' all-reduce slots under that
 // sequence number (only honoured on the one-launch path; *pushed tells the caller whether it happened)
 static int dist_spmv_dev(DistCsr* d, const double* vals, double* y, const double* dotvec, double* dots, const int* done,
-                         uint32_t push_seq = 0, bool* pushed = nullptr) {
+                         uint32_t push_seq = 0, bool* pushed = nullptr, bool halo_pushed_already = false) {
     Csr* c = d->loc;
     if (pushed) *pushed = false;
-    AB_TRY(halo_begin(d));
+    AB_TRY(halo_begin(d, halo_pushed_already));
     const bool split = g_world > 1 && d->p2p && d->tiles_int && d->n_bnd > 0;
     if (!split) {
         AB_TRY(halo_end(d));
@@ -568,6 +656,9 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
     const int defer_x = opt("cg_defer_x", 1.0) != 0.0 ? 1 : 0;   // x += alpha p rides in K3 (cg_kernels.cuh)
     int it = 0;
     SolveScal h;
+    const bool fuse_opt = opt("dist_fused_reduce", g_world <= 2 ? 1.0 : 0.0) != 0.0;
+    const bool push_opt = opt("dist_fused_push", 1.0) != 0.0;
+    bool halo_pushed = false;     // the previous iteration's K3'' already pushed the halos of the coming SpMV
     while (it < maxit) {
         int chunk = maxit - it < check ? maxit - it : check;
         for (int k = 0; k < chunk; ++k, ++it) {
@@ -577,15 +668,25 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
             // Measured at 512^3 (same box A/B): N=2 902 vs 880 it/s with the reductions folded in, N=8 2855 vs
             // 2994 — with eight ranks the 1184 CTAs of K2'/K3' all polling the same eight flag words slow the
             // arrival of the remote stores more than the two saved launches return.  Default: on for <= 2 ranks.
-            const bool fuse = raw && scaled && defer_x && d->p2p && opt("dist_fused_reduce", g_world <= 2 ? 1.0 : 0.0) != 0.0;
+            const bool fuse = raw && scaled && defer_x && d->p2p && fuse_opt;
             bool pushed = false;
-            AB_TRY(dist_spmv_dev(d, vals, Ap, p, s->dots, &s->done, fuse ? d->red_seq + 1 : 0, &pushed));
+            AB_TRY(dist_spmv_dev(d, vals, Ap, p, s->dots, &s->done, fuse ? d->red_seq + 1 : 0, &pushed, halo_pushed));
+            halo_pushed = false;
             if (pushed) {
                 const uint32_t seq1 = ++d->red_seq, seq2 = ++d->red_seq;
                 cgs_update_p2p_kernel<<<g, EW_THREADS, 0, stream()>>>(Ap, r, n, parity, s, c->partials, c->ticket, d->blk,
                                                                       d->d_peer_blk, g_world, g_rank, seq1, seq2);
                 AB_LAUNCH_CHECK();
-                cgs_direction_p2p_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, s, c->ticket, d->blk, g_world, seq2);
+                if (push_opt && (n & 1) == 0 && n >= 2 && d->tiles_all && d->next > 0) {
+                    // K3'' also pushes the halos of the NEXT SpMV (sequence number advanced here)
+                    ++d->halo_seq;
+                    cgs_direction_push_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, s, c->ticket, d->blk, g_world, seq2,
+                                                                              d->send_idx, d->d_send_off, d->d_send_cnt, d->d_peer_x,
+                                                                              d->d_peer_blk, g_rank, d->halo_seq);
+                    halo_pushed = true;
+                } else {
+                    cgs_direction_p2p_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, s, c->ticket, d->blk, g_world, seq2);
+                }
                 AB_LAUNCH_CHECK();
                 continue;
             }
