@@ -158,6 +158,97 @@ spmm_warp_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
         }
     }
 }
+// k >= 32, short rows: one warp per GROUP of 8 consecutive rows.  A power-law matrix is mostly rows of 1-3
+// entries; with a warp per row such a row keeps one 256-byte X gather in flight and the kernel is latency-bound
+// (C5: 0.51 of the gather-model roofline).  Here the group's entries (<= 32 in total) are fetched by one
+// coalesced load, their X-row gathers are issued eight at a time ACROSS row boundaries, and the running sum is
+// flushed to Y whenever the row changes (warp-uniform branch).  Per-row summation order is unchanged (stored
+// order), so Y is bit-identical to the warp-per-row kernel.  Groups holding more than 32 entries (or a long
+// row) fall back to the row-at-a-time walk.
+constexpr int SPMM_GROUP = 8;
+template <int NC>
+__global__ void __launch_bounds__(256)
+spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
+                  const double* __restrict__ values, const double* __restrict__ X, double* __restrict__ Y,
+                  int64_t m, int k, int c0, int long_thresh) {
+    constexpr int UB = NC == 1 ? 8 : 4;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * 256) >> 5;
+    const int64_t ngroups = (m + SPMM_GROUP - 1) / SPMM_GROUP;
+    for (int64_t grp = warp0; grp < ngroups; grp += nwarp) {
+        const int64_t row0 = grp * SPMM_GROUP;
+        const int nr = (int)min((int64_t)SPMM_GROUP, m - row0);
+        const int rp = lane <= nr ? rowptr[row0 + lane] : 0;
+        const int a = __shfl_sync(0xffffffffu, rp, 0), b = __shfl_sync(0xffffffffu, rp, nr);
+        const int cnt = b - a;
+        if (cnt > 32) {
+            // row at a time (long rows are left to the chunk kernels)
+            for (int rr = 0; rr < nr; ++rr) {
+                const int ra = __shfl_sync(0xffffffffu, rp, rr), rb = __shfl_sync(0xffffffffu, rp, rr + 1);
+                if (rb - ra > long_thresh) continue;
+                double acc[NC];
+#pragma unroll
+                for (int q = 0; q < NC; ++q) acc[q] = 0.0;
+                spmm_range<NC>(colind, values, X, k, c0, ra, rb, lane, acc);
+                double* yr = Y + (size_t)(row0 + rr) * k + c0;
+#pragma unroll
+                for (int u = 0; u < NC; ++u) {
+                    const int cc = lane + 32 * u;
+                    if (c0 + cc < k) yr[cc] = acc[u];
+                }
+            }
+            continue;
+        }
+        int cj = 0, rid = 0;
+        double vj = 0.0;
+        if (lane < cnt) { cj = colind[a + lane]; vj = values[a + lane]; }
+        for (int rr = 1; rr <= nr; ++rr) rid += (__shfl_sync(0xffffffffu, rp, rr) <= a + lane) ? 1 : 0;   // row (within the group) of entry `lane`
+        double acc[NC];
+#pragma unroll
+        for (int q = 0; q < NC; ++q) acc[q] = 0.0;
+        int cur = 0;
+        auto flush_to = [&](int upto) {
+            while (cur < upto) {
+                double* yr = Y + (size_t)(row0 + cur) * k + c0;
+#pragma unroll
+                for (int u = 0; u < NC; ++u) {
+                    const int cc = lane + 32 * u;
+                    if (c0 + cc < k) yr[cc] = acc[u];
+                    acc[u] = 0.0;
+                }
+                ++cur;
+            }
+        };
+        for (int q0 = 0; q0 < cnt; q0 += UB) {
+            double xv[UB][NC], vq[UB];
+            int rq[UB];
+#pragma unroll
+            for (int b8 = 0; b8 < UB; ++b8) {
+                const int q = q0 + b8;
+                const int cq = __shfl_sync(0xffffffffu, cj, q & 31);
+                vq[b8] = __shfl_sync(0xffffffffu, vj, q & 31);
+                rq[b8] = __shfl_sync(0xffffffffu, rid, q & 31);
+                const double* xr = X + (size_t)cq * k + c0;
+#pragma unroll
+                for (int u = 0; u < NC; ++u) {
+                    const int cc = lane + 32 * u;
+                    xv[b8][u] = (q < cnt && c0 + cc < k) ? __ldg(xr + cc) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int b8 = 0; b8 < UB; ++b8) {
+                if (q0 + b8 < cnt) {
+                    flush_to(rq[b8]);
+#pragma unroll
+                    for (int u = 0; u < NC; ++u) acc[u] = fma(vq[b8], xv[b8][u], acc[u]);
+                }
+            }
+        }
+        flush_to(nr);
+    }
+}
+
 // one warp per CHUNK of a long row -> partial[chunk, :]
 template <int NC>
 __global__ void __launch_bounds__(256)
@@ -211,11 +302,18 @@ int launch_spmm(const Csr* c_, const double* X, int64_t k, double* Y) {
         DevBuf<double> partial;
         if (c->long_nrows > 0) AB_TRY(partial.alloc((size_t)c->long_nchunks * kk));
         unsigned gridc = (unsigned)((c->long_nchunks + 7) / 8);
+        // rows of a few entries dominate (average <= 24 per row): a warp per group of 8 rows keeps the gathers in flight
+        const bool grouped = opt("spmm_group", 1.0) != 0.0 && (double)c->nnz <= 24.0 * (double)c->m;
+        int64_t nblkg = ((c->m + SPMM_GROUP - 1) / SPMM_GROUP + 7) / 8;
+        unsigned gridg = (unsigned)(nblkg < cap ? (nblkg > 0 ? nblkg : 1) : cap);
         for (int c0 = 0; c0 < kk; c0 += 128) {
             const int rem = kk - c0;
 #define AB_W(NCC)                                                                                                   \
     do {                                                                                                            \
-        spmm_warp_kernel<NCC><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, Y, c->m, kk, c0, thresh); \
+        if (grouped)                                                                                                \
+            spmm_group_kernel<NCC><<<gridg, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, Y, c->m, kk, c0, thresh); \
+        else                                                                                                        \
+            spmm_warp_kernel<NCC><<<grid, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, Y, c->m, kk, c0, thresh); \
         AB_LAUNCH_CHECK();                                                                                          \
         if (c->long_nrows > 0) {                                                                                    \
             spmm_chunk_kernel<NCC><<<gridc, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, X, c->long_chunk_row, \
