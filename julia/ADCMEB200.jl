@@ -13,6 +13,7 @@ export B200SparseTensor, b200_spmm, b200_solve, b200_solve_grad, B200Assembler, 
        b200_assemble, b200_compress, b200_factorize, b200_fsolve, b200_zero_out_row, b200_scatter_update,
        b200_getindex, b200_spgemm, b200_add, b200_trisolve, b200_newton_step, b200_find, b200_dense_to_sparse,
        b200_to_dense, b200_concat, b200_transpose, b200_poisson2d, b200_poisson3d, b200_dist_unique_id, b200_dist_init,
+       b200_dist_query, b200_dist_get_matrix, b200_dist_adjoint,
        b200_dist_create, b200_dist_solve, b200_dist_solve_grad, b200_dist_spmv, b200_dist_destroy, b200_dist_finalize
 
 const LIB = get(ENV, "ADCME_B200_LIB", joinpath(@__DIR__, "..", "adcme.jl_b200", "libadcme_b200.so"))
@@ -369,5 +370,69 @@ function b200_dist_spmv(dh::Int64, x_local::Vector{Float64})
     y
 end
 b200_dist_destroy(dh::Int64) = chk(ccall((:ab_dist_destroy, LIB), Cint, (Int64,), dh))
+"(rows owned, halo columns referenced, stored entries) of this rank's block."
+function b200_dist_query(dh::Int64)
+    nloc = Ref{Int64}(0); nh = Ref{Int64}(0); nnz = Ref{Int64}(0)
+    chk(ccall((:ab_dist_query, LIB), Cint, (Int64, Ref{Int64}, Ref{Int64}, Ref{Int64}), dh, nloc, nh, nnz))
+    nloc[], nh[], nnz[]
+end
+"SparseTensor(sp::mpi_SparseTensor) — src/mpi.jl:502-504 / MPIGetMatrix: (indices [nnz,2] 0-based: local row, GLOBAL column; values)."
+function b200_dist_get_matrix(dh::Int64)
+    nnz = b200_dist_query(dh)[3]
+    idx2 = Matrix{Int64}(undef, 2, nnz); vals = Vector{Float64}(undef, nnz)       # column-major 2 x nnz == row-major nnz x 2
+    chk(ccall((:ab_dist_export_coo, LIB), Cint, (Int64, Ptr{Int64}, Ptr{Cdouble}), dh, idx2, vals))
+    permutedims(idx2), vals
+end
+"adjoint(A::mpi_SparseTensor) — src/mpi.jl:544-563: handle of A' under the same row partition.  Collective."
+function b200_dist_adjoint(dh::Int64)
+    out = Ref{Int64}(0)
+    chk(ccall((:ab_dist_transpose, LIB), Cint, (Int64, Ref{Int64}), dh, out))
+    out[]
+end
+
+# ---- the drop-in: ADCME's own methods re-pointed at this library ---------------------------------------------
+# Included from inside ADCME (after src/sparse.jl and src/mpi.jl) these definitions REPLACE the bodies of
+# `PyCall.:*(::SparseTensor, ::PyObject)` (src/sparse.jl:227), `PyCall.:*(::PyObject, ::SparseTensor)` (:247),
+# `PyCall.:\(::SparseTensor, ::PyObject, ::String)` (:413) and `LinearAlgebra.:\(::mpi_SparseTensor, ...)`
+# (src/mpi.jl:493): the user-facing API (SparseTensor, `*`, `\`, gradients through `gradients(loss, vv)`) is
+# unchanged; only the kernels behind it move to the GPU library.  The graph node is a `tf.py_function` wrapped by
+# ADCME's `register(forward, backward)` (src/extra.jl:516-541), whose backward calls the `*_grad` entry points.
+# Guarded by `@isdefined` so that this file also loads stand-alone (tests/test_abi.py parses the ccalls above).
+if @isdefined(ADCME_DROPIN_HOST)
+    import PyCall
+    const _PATTERNS = Dict{UInt64,B200SparseTensor}()       # assembled pattern cache: hash(ii, jj, m, n) -> handle
+    function _handle(ii, jj, vv, m, n)
+        key = hash((ii, jj, m, n))
+        if haskey(_PATTERNS, key)
+            update_values!(_PATTERNS[key], vv)                # ab_csr_update_values: no re-sort
+        else
+            _PATTERNS[key] = B200SparseTensor(ii, jj, vv, m, n)   # ab_csr_from_coo (1-based, duplicates summed)
+        end
+        _PATTERNS[key]
+    end
+    _pyfun(f, inputs, n_out) = ADCME_DROPIN_HOST.tf.py_function(func=f, inp=inputs, Tout=[ADCME_DROPIN_HOST.tf.float64 for _ = 1:n_out])
+
+    # s * o  (src/sparse.jl:227-241): SpMV / SpMM, gradients w.r.t. values (per input triplet) and the dense operand
+    function PyCall.:*(s::ADCME_DROPIN_HOST.SparseTensor, o::PyCall.PyObject)
+        ii, jj, vv = ADCME_DROPIN_HOST.find(s); m, n = size(s)
+        fwd = (ii_, jj_, vv_, x) -> _pyfun((a, b, c, d) -> b200_spmm(_handle(a.numpy(), b.numpy(), c.numpy(), m, n), d.numpy()), [ii_, jj_, vv_, x], 1)[1]
+        bwd = (dy, y, ii_, jj_, vv_, x) -> begin
+            g = _pyfun((a, b, c, d, e) -> b200_spmm_grad(_handle(a.numpy(), b.numpy(), c.numpy(), m, n), e.numpy(), d.numpy()), [ii_, jj_, vv_, x, dy], 2)
+            (nothing, nothing, g[1], g[2])
+        end
+        ADCME_DROPIN_HOST.register(fwd, bwd)(ii, jj, vv, o)
+    end
+    # s \ o  (src/sparse.jl:413-445): square systems; the method strings of options.sparse.solver pass through
+    function PyCall.:\(s::ADCME_DROPIN_HOST.SparseTensor, o::PyCall.PyObject, method::String="auto")
+        method == "auto" && (method = ADCME_DROPIN_HOST.options.sparse.solver)
+        ii, jj, vv = ADCME_DROPIN_HOST.find(s); m, n = size(s)
+        fwd = (ii_, jj_, vv_, f) -> _pyfun((a, b, c, d) -> b200_solve(_handle(a.numpy(), b.numpy(), c.numpy(), m, n), d.numpy(), method), [ii_, jj_, vv_, f], 1)[1]
+        bwd = (du, u, ii_, jj_, vv_, f) -> begin
+            g = _pyfun((a, b, c, d, e) -> b200_solve_grad(_handle(a.numpy(), b.numpy(), c.numpy(), m, n), e.numpy(), d.numpy(), method), [ii_, jj_, vv_, u, du], 2)
+            (nothing, nothing, g[1], g[2])
+        end
+        ADCME_DROPIN_HOST.register(fwd, bwd)(ii, jj, vv, o)
+    end
+end
 
 end # module
