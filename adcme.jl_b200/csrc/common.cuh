@@ -157,6 +157,13 @@ struct Csr {
     void*     rw_ent   = nullptr;  // [npat_ent] x {double value; int32 stage index rel. to the local row; int32 pad}
     uint8_t*  rw_tmask = nullptr;  // [ceil(m/1024)] bit i: interval i is referenced by a row of the tile
     int       rw_ok = -1;
+    // marching form (lazy, spmv.cu: spmv_rowmarch_kernel): chains of tiles M rows apart share their windows
+    void*     rm_plan  = nullptr;  // host RowMarchPlan
+    void*     rm_ent   = nullptr;  // [npat_ent] x {double value; int32 offset inside the plane buffer; int32 plane}
+    int32_t*  rm_items = nullptr;  // [2 * rm_nitems]: first tile of each work item, then its length
+    int       rm_nitems = 0;
+    int64_t   rm_nrest = 0;        // tiles no chain covers (they reference other intervals)
+    int       rm_ok = 0;
     // triplet bookkeeping (null when the handle was created from CSR: identity map)
     uint32_t* perm     = nullptr; // [T]  sorted position -> input triplet
     uint32_t* segstart = nullptr; // [nnz+1] first sorted position of each stored entry

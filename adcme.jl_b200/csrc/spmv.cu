@@ -735,12 +735,15 @@ rowpat_assign_kernel(const int32_t* __restrict__ rowptr, const uint8_t* __restri
 }
 
 static int csr_build_rowwin(Csr* c, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat);
+struct RowWinPlan;
+static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat);
 
 // npat > 0 afterwards: rowcode/pat_ent/pat_info encode the matrix the pattern codes encode
 static int csr_ensure_rowpat(Csr* c) {
     if (c->npat >= 0 && c->ncode > 0) return AB_OK;     // csr_ensure_code resets npat when it rebuilds
     c->npat = 0;
     c->rw_ok = 0;
+    c->rm_ok = 0;
     if (c->ncode <= 0 || c->m == 0) return AB_OK;
     DevBuf<unsigned long long> gtab; DevBuf<int> grep, gcount;
     AB_TRY(gtab.alloc(VAL_HASH)); AB_TRY(grep.alloc(VAL_HASH)); AB_TRY(gcount.alloc(1));
@@ -983,6 +986,177 @@ spmv_rowwin_kernel(const __grid_constant__ RowWinPlan P, const uint8_t* __restri
     AB_TILE_EPILOGUE(RW_T)
 }
 
+// ---- marching form of the x-window kernel ---------------------------------------------------------
+// Measured (B200, 512^3): spmv_rowwin_kernel 0.73 ms = spmv_rowpat_kernel 0.75 ms although it issues a quarter
+// of the instructions — both move ~42 bytes per row between L2 and the SMs (three 1024-row windows + margins,
+// y, codes: 5.6 GB per launch, i.e. ~8-10 TB/s, which is what the L2 <-> SM fabric sustains), while HBM
+// only has to deliver 17.  When the interval plan consists of a centre interval and two copies of it shifted
+// by -M and +M rows with M a multiple of the tile size (3-D stencils: M = nx*ny), the tile M rows ahead
+// needs as its "-M" window exactly what this tile needs as its centre window.  So a CTA MARCHES: it walks
+// the chain of tiles T, T+S, T+2S, ... (S = M / 1024) and keeps the centre windows of the last three chain
+// positions in a ring of four shared-memory buffers; per tile ONE new window (1024 + margins doubles) is
+// streamed by the TMA unit, prefetched two chain positions ahead — the 2.5-D blocking of stencil codes,
+// driven entirely by the pattern tables (no grid geometry enters the kernel).  L2 -> SM traffic drops to
+// 8 * len / 1024 + 9 bytes per row (25 at 512^3).  Chains are cut into work items of <= Lmax tiles; the
+// fused dots are reduced per ITEM and summed in item order, so results do not depend on which CTA ran what.
+// Tiles that reference any other interval (halo columns of a distributed block) are left to spmv_rowwin_kernel.
+constexpr int RM_NB = 4;             // ring buffers
+struct RowMarchPlan {
+    int M, S;               // march stride in rows / in tiles
+    int lo, len;            // centre interval (relative to the tile's first row; even) and its length in doubles
+    int dom, dk, center;    // dominant pattern; stage offset of x[row] inside the centre buffer relative to the local row
+    int ntiles;
+    int dsoff[RW_MAXK];     // dominant pattern: offset inside its plane's buffer relative to the local row
+    int dplane[RW_MAXK];    // -1, 0, +1
+    double dval[RW_MAXK];
+};
+
+template <int K, int CK>
+__global__ void __launch_bounds__(RW_T)
+spmv_rowmarch_kernel(const __grid_constant__ RowMarchPlan P, const uint8_t* __restrict__ rowcode, const int4* __restrict__ ent,
+                     int nent, const uint32_t* __restrict__ pinfo, const double* __restrict__ x, long long xlen,
+                     double* __restrict__ y, unsigned m, const int32_t* __restrict__ item_first,
+                     const int32_t* __restrict__ item_count, unsigned nitems, const double* __restrict__ dotvec,
+                     int dot_in_window, double* partials, uint32_t* ticket, double* dot_result,
+                     const int* __restrict__ done) {
+    extern __shared__ __align__(128) unsigned char rm_smem[];
+    double*   s_ring = reinterpret_cast<double*>(rm_smem);                                     // [RM_NB][P.len]
+    uint8_t*  s_code = rm_smem + (size_t)RM_NB * P.len * 8;                                    // [RM_NB][RW_R]
+    int4*     s_ent  = reinterpret_cast<int4*>(s_code + RM_NB * RW_R);                         // [nent]
+    uint32_t* s_info = reinterpret_cast<uint32_t*>(s_ent + nent);                              // [256]
+    __shared__ alignas(8) uint64_t bar[RM_NB];
+    __shared__ double s_red[32];
+    __shared__ bool s_last;
+    if (done && *done) return;
+    const unsigned t = threadIdx.x;
+    for (int i = t; i < nent; i += RW_T) s_ent[i] = ent[i];
+    for (int i = t; i < 256; i += RW_T) s_info[i] = pinfo[i];
+    if (t == 0) {
+#pragma unroll
+        for (int b = 0; b < RM_NB; ++b) abd::mbar_init(&bar[b], 1);
+        abd::mbar_fence_init();
+    }
+    __syncthreads();
+    unsigned phasebits = 0;                     // bit b: parity the next wait on bar[b] expects
+    const int len = P.len;
+
+    // chain position q (0 = the tile before the item's first one) -> ring slot q & 3
+    auto issue = [&](int first, int q) {        // thread 0 only
+        const int slot = q & (RM_NB - 1);
+        const long long tile = (long long)first + (long long)(q - 1) * P.S;
+        unsigned bytes = 0, cbytes = 0;
+        long long a = 0, b = 0, tail = -1, base = 0;
+        unsigned r0 = 0;
+        if (tile >= 0 && tile < P.ntiles) {
+            r0 = (unsigned)tile * (unsigned)RW_R;
+            const unsigned nr = min((unsigned)RW_R, m - r0);
+            cbytes = (nr + 15u) & ~15u;
+            base = (long long)r0 + P.lo;
+            a = base; b = base + len;
+            if (a < 0) a = 0;
+            if (b > xlen) { b = xlen; if (b & 1) { b -= 1; tail = b; } }
+            if (b > a) bytes = (unsigned)(b - a) * 8u;
+            if (tail >= a && tail >= 0) s_ring[(size_t)slot * len + (tail - base)] = x[tail];
+        }
+        abd::mbar_expect_tx(&bar[slot], bytes + cbytes);
+        if (cbytes) abd::bulk_g2s(s_code + slot * RW_R, rowcode + r0, cbytes, &bar[slot]);
+        if (bytes) abd::bulk_g2s(s_ring + (size_t)slot * len + (a - base), x + a, bytes, &bar[slot]);
+    };
+    auto wait_slot = [&](int q) {
+        const int slot = q & (RM_NB - 1);
+        abd::mbar_wait(&bar[slot], (phasebits >> slot) & 1u);
+        phasebits ^= 1u << slot;
+    };
+
+    for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int first = item_first[item], L = item_count[item];
+        double dot = 0.0, dot2 = 0.0;
+        if (t == 0) { issue(first, 0); issue(first, 1); if (L >= 1) issue(first, 2); }
+        for (int k = 0; k < L; ++k) {
+            // positions: k (previous tile), k+1 (this tile), k+2 (next tile); prefetch position k+3
+            if (t == 0 && k + 3 <= L + 1) issue(first, k + 3);
+            if (k == 0) { wait_slot(0); wait_slot(1); }
+            wait_slot(k + 2);
+            const unsigned tile = (unsigned)(first + k * P.S);
+            const unsigned r0 = tile * (unsigned)RW_R;
+            const unsigned nr = min((unsigned)RW_R, m - r0);
+            const double* pb[3];
+            pb[0] = s_ring + (size_t)((k) & (RM_NB - 1)) * len + t;
+            pb[1] = s_ring + (size_t)((k + 1) & (RM_NB - 1)) * len + t;
+            pb[2] = s_ring + (size_t)((k + 2) & (RM_NB - 1)) * len + t;
+            const uint8_t* codes = s_code + ((k + 1) & (RM_NB - 1)) * RW_R;
+            const double* pk[K > 0 ? K : 1];
+#pragma unroll
+            for (int e = 0; e < K; ++e) {
+                const int pl = P.dplane[e];
+                pk[e] = (pl == 0 ? pb[1] : (pl < 0 ? pb[0] : pb[2])) + P.dsoff[e];
+            }
+#pragma unroll
+            for (int j = 0; j < RW_J; ++j) {
+                const unsigned tl = t + (unsigned)j * RW_T;
+                if (tl < nr) {
+                    const unsigned code = codes[tl];
+                    double acc = 0.0, xc = 0.0;
+                    bool have_xc = false;
+                    if (K > 0 && code == (unsigned)P.dom) {
+#pragma unroll
+                        for (int e = 0; e < K; ++e) {
+                            const double xk = pk[e][j * RW_T];
+                            if (e == CK) xc = xk;
+                            acc = fma(P.dval[e], xk, acc);
+                        }
+                        have_xc = CK >= 0;
+                    } else {
+                        const uint32_t info = s_info[code];
+                        const int4* e = s_ent + (info & 0xffffu);
+                        const int elen = (int)(info >> 16);
+                        for (int q = 0; q < elen; ++q) {
+                            const int4 qe = e[q];
+                            const double* bq = qe.w == 0 ? pb[1] : (qe.w < 0 ? pb[0] : pb[2]);
+                            acc = fma(__hiloint2double(qe.y, qe.x), bq[qe.z + j * RW_T], acc);
+                        }
+                    }
+                    y[r0 + tl] = acc;
+                    if (dotvec) {
+                        const double w = have_xc ? xc : (dot_in_window ? pb[1][P.center + j * RW_T] : dotvec[r0 + tl]);
+                        dot  = fma(acc, w, dot);
+                        dot2 = fma(acc, acc, dot2);
+                    }
+                }
+            }
+            __syncthreads();   // ring slot k & 3 is refilled by the next prefetch
+        }
+        if (dotvec) {
+            const double d0 = abd::block_sum<RW_T>(dot, s_red);
+            const double d1 = abd::block_sum<RW_T>(dot2, s_red);
+            if (t == 0) { partials[item] = d0; partials[(size_t)nitems + item] = d1; }
+        }
+    }
+    if (dotvec) {
+        // deterministic grid reduction over ITEMS (fixed order, independent of the item -> CTA assignment)
+        if (t == 0) {
+            __threadfence();
+            const uint32_t tk = atomicAdd(ticket, 1u);
+            s_last = (tk == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double a0 = 0.0, a1 = 0.0;
+            const volatile double* p0 = partials;
+            const volatile double* p1 = partials + nitems;
+            for (unsigned i = t; i < nitems; i += RW_T) { a0 += p0[i]; a1 += p1[i]; }
+            a0 = abd::block_sum<RW_T>(a0, s_red);
+            a1 = abd::block_sum<RW_T>(a1, s_red);
+            if (t == 0) {
+                *ticket = 0;
+                dot_result[0] = a0;
+                dot_result[1] = a1;
+            }
+        }
+    }
+}
+
 // rows per pattern (dominant pattern = argmax)
 __global__ void __launch_bounds__(256)
 rowcode_hist_kernel(const uint8_t* __restrict__ rowcode, int64_t m, unsigned long long* __restrict__ hist) {
@@ -1098,6 +1272,108 @@ static int csr_build_rowwin(Csr* c, const std::vector<CodeEnt>& pent, const std:
     if (!c->rw_plan) return fail(AB_ECUDA, "out of host memory");
     memcpy(c->rw_plan, &P, sizeof(P));
     c->rw_ok = 1;
+    return csr_build_rowmarch(c, P, pent, pinfo, npat);
+}
+
+// rm_ok = 1 afterwards when chains of tiles can share their windows (see spmv_rowmarch_kernel)
+static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat) {
+    c->rm_ok = 0;
+    int ic = -1;
+    for (int i = 0; i < W.ni; ++i) if (0 >= W.lo[i] && RW_R <= W.lo[i] + W.len[i]) ic = i;
+    if (ic < 0) return AB_OK;
+    const long long loc = W.lo[ic], lenc = W.len[ic];
+    // the stride: a multiple of the tile size that puts the next interval inside the shifted centre window
+    const int iu = ic + 1 < W.ni ? ic + 1 : -1, il = ic - 1 >= 0 ? ic - 1 : -1;
+    long long M = 0;
+    auto stride_for = [&](long long lo_o, long long len_o, int sign) -> long long {      // interval [lo_o, lo_o+len_o) inside centre shifted by sign*M
+        // sign*M in [lo_o + len_o - loc - lenc, lo_o - loc]
+        long long a = lo_o + len_o - loc - lenc, b = lo_o - loc;
+        if (sign < 0) { const long long t = -a; a = -b; b = t; }                         // M in [-(lo_o-loc), -(lo_o+len_o-loc-lenc)]
+        long long Mc = (a + RW_R - 1) / RW_R * RW_R;
+        if (a <= 0) Mc = RW_R;                                                           // M must be positive
+        return (Mc >= a && Mc <= b && Mc > 0) ? Mc : 0;
+    };
+    if (iu >= 0) M = stride_for(W.lo[iu], W.len[iu], +1);
+    if (M == 0 && il >= 0) M = stride_for(W.lo[il], W.len[il], -1);
+    if (M <= 0) return AB_OK;
+    auto inside = [&](int i, long long shift) { return i >= 0 && W.lo[i] >= loc + shift && W.lo[i] + W.len[i] <= loc + shift + lenc; };
+    const bool has_u = inside(iu, M), has_l = inside(il, -M);
+    if (!has_u && !has_l) return AB_OK;
+    unsigned marchmask = 1u << ic;
+    if (has_u) marchmask |= 1u << iu;
+    if (has_l) marchmask |= 1u << il;
+    const size_t smem = (size_t)RM_NB * lenc * 8 + (size_t)RM_NB * RW_R + pent.size() * 16 + 1024;
+    if (smem > RW_SMEM_MAX) return AB_OK;
+    RowMarchPlan Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.M = (int)M; Q.S = (int)(M / RW_R); Q.lo = (int)loc; Q.len = (int)lenc; Q.dom = -1;
+    Q.center = (int)(0 - loc);
+    Q.ntiles = (int)((c->m + RW_R - 1) / RW_R);
+    // entries: (offset inside the plane buffer, plane)
+    struct MEnt { double v; int32_t soff; int32_t plane; };
+    std::vector<MEnt> ment(pent.size());
+    std::vector<char> pat_ok(256, 1);
+    for (int p = 0; p < npat; ++p) {
+        const int st = (int)(pinfo[p] & 0xffffu), len = (int)(pinfo[p] >> 16);
+        for (int k = 0; k < len; ++k) {
+            const long long o = pent[st + k].off;
+            MEnt e; e.v = pent[st + k].v; e.soff = 0; e.plane = 0;
+            if (o >= loc && o + RW_R <= loc + lenc) { e.plane = 0; e.soff = (int)(o - loc); }
+            else if (has_u && o - M >= loc && o - M + RW_R <= loc + lenc) { e.plane = 1; e.soff = (int)(o - M - loc); }
+            else if (has_l && o + M >= loc && o + M + RW_R <= loc + lenc) { e.plane = -1; e.soff = (int)(o + M - loc); }
+            else pat_ok[p] = 0;
+            ment[st + k] = e;
+        }
+    }
+    if (W.dom >= 0 && pat_ok[W.dom]) {
+        const int st = (int)(pinfo[W.dom] & 0xffffu);
+        Q.dom = W.dom; Q.dk = W.dk;
+        for (int k = 0; k < W.dk; ++k) { Q.dsoff[k] = ment[st + k].soff; Q.dplane[k] = ment[st + k].plane; Q.dval[k] = ment[st + k].v; }
+    }
+    // ---- work items: runs of chain-consecutive tiles whose rows only touch the three marching intervals
+    const int ntiles = Q.ntiles, S = Q.S;
+    std::vector<uint8_t> hmask((size_t)ntiles);
+    AB_CUDA(cudaMemcpyAsync(hmask.data(), c->rw_tmask, (size_t)ntiles, cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    long long npure = 0;
+    for (int tI = 0; tI < ntiles; ++tI) npure += ((hmask[tI] & ~marchmask) == 0);
+    if (npure == 0) return AB_OK;
+    const long long slots = (long long)sm_count() * 3;
+    long long Lmax = (npure + 4 * slots - 1) / (4 * slots);
+    if (Lmax < 4) Lmax = 4;
+    if (Lmax > 128) Lmax = 128;
+    const int Z = (ntiles + S - 1) / S;
+    std::vector<int32_t> first, count;
+    for (int pass = 0; pass < 2 && (pass == 0 || first.size() > 8000); ++pass) {
+        if (pass == 1) Lmax *= (long long)(first.size() / 8000 + 1);
+        first.clear(); count.clear();
+        for (int z0 = 0; z0 < Z; z0 += (int)Lmax)
+            for (int tI = 0; tI < S; ++tI) {
+                int run = 0, start = 0;
+                for (int z = z0; z < Z && z < z0 + (int)Lmax; ++z) {
+                    const long long tile = (long long)z * S + tI;
+                    const bool pure = tile < ntiles && (hmask[tile] & ~marchmask) == 0;
+                    if (pure) { if (run == 0) start = (int)tile; ++run; }
+                    if ((!pure || z + 1 == Z || z + 1 == z0 + (int)Lmax) && run) { first.push_back(start); count.push_back(run); run = 0; }
+                }
+            }
+    }
+    const int nitems = (int)first.size();
+    if (nitems == 0 || nitems > 16000) return AB_OK;
+    dev_free(c->rm_ent); c->rm_ent = nullptr;
+    dev_free(c->rm_items); c->rm_items = nullptr;
+    AB_TRY(dev_alloc(&c->rm_ent, ment.size() * sizeof(MEnt)));
+    AB_TRY(dev_alloc((void**)&c->rm_items, (size_t)2 * nitems * sizeof(int32_t)));
+    AB_CUDA(cudaMemcpyAsync(c->rm_ent, ment.data(), ment.size() * sizeof(MEnt), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemcpyAsync(c->rm_items, first.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemcpyAsync(c->rm_items + nitems, count.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    if (!c->rm_plan) c->rm_plan = malloc(sizeof(RowMarchPlan));
+    if (!c->rm_plan) return fail(AB_ECUDA, "out of host memory");
+    memcpy(c->rm_plan, &Q, sizeof(Q));
+    c->rm_nitems = nitems;
+    c->rm_nrest = (long long)ntiles - npure;
+    c->rm_ok = 1;
     return AB_OK;
 }
 
@@ -1157,6 +1433,7 @@ static int launch_rowwin(const Csr* c, const double* x, double* y, const double*
     if (hwp) hw = *hwp;
     const size_t smem = (size_t)P.wtot * 8 + (size_t)c->npat_ent * 16 + 1024 + RW_R;
     int cps = (int)((227 * 1024) / (smem + 1280));
+    if (cps > 4) cps = 4;   // measured (512^3): the 5th CTA of an SM is not resident (48 registers x 256 threads + stage); 4 -> 0.73 ms, 5 -> 1.05 ms
     const int cps_opt = (int)opt("spmv_rowwin_ctas", 0.0);
     if (cps_opt > 0 && cps_opt < cps) cps = cps_opt;
     if (cps > 8) cps = 8;
@@ -1191,6 +1468,48 @@ static int launch_rowwin(const Csr* c, const double* x, double* y, const double*
     else AB_RW2(0, -1);
 #undef AB_RW2
 #undef AB_RW
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
+static int launch_rowmarch(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result, double* partials,
+                           uint32_t* ticket, const int* done_flag) {
+    const RowMarchPlan& P = *reinterpret_cast<const RowMarchPlan*>(c->rm_plan);
+    const size_t smem = (size_t)RM_NB * P.len * 8 + (size_t)RM_NB * RW_R + (size_t)c->npat_ent * 16 + 1024;
+    const int dot_in_window = (dotvec == x) ? 1 : 0;
+    int ck = -1;
+    for (int k = 0; k < P.dk; ++k) if (P.dom >= 0 && P.dplane[k] == 0 && P.dsoff[k] == P.center) ck = k;
+    if (!dot_in_window) ck = -1;
+    const bool fast = P.dom >= 0 && opt("spmv_rowwin_dom", 1.0) != 0.0;
+    const unsigned nitems = (unsigned)c->rm_nitems;
+#define AB_RM(KK, CC)                                                                                                         \
+    do {                                                                                                                      \
+        auto kern = spmv_rowmarch_kernel<KK, CC>;                                                                             \
+        static int occ = 0;                                                                                                   \
+        static size_t smem_set = 0;                                                                                           \
+        if (smem > smem_set || occ == 0) {                                                                                    \
+            AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RW_SMEM_MAX));               \
+            AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));                         \
+            AB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, RW_T, smem));                                   \
+            if (occ < 1) occ = 1;                                                                                             \
+            smem_set = smem;                                                                                                  \
+        }                                                                                                                     \
+        int cps = occ;                                                                                                        \
+        const int cps_opt = (int)opt("spmv_rowmarch_ctas", 0.0);                                                              \
+        if (cps_opt > 0 && cps_opt < cps) cps = cps_opt;                                                                      \
+        unsigned grid = (unsigned)(sm_count() * cps);                                                                         \
+        if (grid > nitems) grid = nitems;                                                                                     \
+        kern<<<grid, RW_T, smem, stream()>>>(P, c->rowcode, (const int4*)c->rm_ent, c->npat_ent, c->pat_info, x,              \
+                                             (long long)c->n, y, (unsigned)c->m, c->rm_items, c->rm_items + nitems, nitems,  \
+                                             dotvec, dot_in_window, partials, ticket, dot_result, done_flag);                \
+    } while (0)
+    if (fast && P.dk == 7 && ck == 3) AB_RM(7, 3);
+    else if (fast && P.dk == 7) AB_RM(7, -1);
+    else if (fast && P.dk == 5 && ck == 2) AB_RM(5, 2);
+    else if (fast && P.dk == 5) AB_RM(5, -1);
+    else if (fast && P.dk == 3 && ck == 1) AB_RM(3, 1);
+    else AB_RM(0, -1);
+#undef AB_RM
     AB_LAUNCH_CHECK();
     return AB_OK;
 }
@@ -1318,6 +1637,9 @@ static int launch_spmv_impl(const Csr* c, const double* vals, const double* x, d
             AB_TRY(csr_ensure_code(const_cast<Csr*>(c), vals));
             if (c->ncode > 0 && c->npat < 0) AB_TRY(csr_ensure_rowpat(const_cast<Csr*>(c)));
         }
+        if (rowwin_ready(c, vals, x) && !tile_list && !accumulate && c->rm_ok == 1 && c->rm_nrest == 0 && c->rm_plan &&
+            (!dotvec || partials) && opt("spmv_rowmarch", 1.0) != 0.0)
+            return launch_rowmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag);
         if (rowwin_ready(c, vals, x) && (!tile_list || list_rows == RW_R))
             return launch_rowwin(c, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, accumulate, hwp);
         if (tile_list && list_rows == RW_R) return fail(AB_EINVAL, "tile list built for the x-window kernel, which is not available");
@@ -1369,6 +1691,8 @@ extern "C" int ab_csr_get_info(int64_t h, const char* key, double* value) {
     else if (!strcmp(key, "npat")) *value = (c->code_version == c->values_version && c->ncode > 0) ? c->npat : -1;
     else if (!strcmp(key, "ncode")) *value = (c->code_version == c->values_version) ? c->ncode : -1;
     else if (!strcmp(key, "rowwin")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0) ? c->rw_ok : -1;
+    else if (!strcmp(key, "rowmarch")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0 && c->rw_ok == 1) ? c->rm_ok : -1;
+    else if (!strcmp(key, "rowmarch_items")) *value = c->rm_nitems;
     else if (!strcmp(key, "tile_rows")) *value = ab::spmv_tile_rows(c);
     else if (!strcmp(key, "max_row_nnz")) *value = c->max_row_nnz;
     else if (!strcmp(key, "scaled")) *value = (c->scaled_version == c->values_version && c->scaled_ok) ? 1 : 0;

@@ -258,7 +258,7 @@ def spmv_form(lib, h, nloc: int, nnz_loc: int):
     return {"kernel": name, "index_value_bytes": f"{per} per stored entry", "streamed_bytes": per * nnz_loc + 4.0 * (nloc + 1) + 16.0 * nloc}
 
 
-def cg_leg(pkg, A, args, rank, world, dev, e2e: bool, sample_clocks: bool):
+def cg_leg(pkg, A, args, rank, world, dev, e2e: bool, sample_clocks: bool, constant_diagonal: bool = True):
     """Times `steps` calls of ab_dist_cg_fixed (ITERS_PER_STEP iterations each) on the distributed handle A:
     device-resident f/u, and (e2e) pinned-host f/u with both copies inside the timed region."""
     import torch
@@ -310,8 +310,10 @@ def cg_leg(pkg, A, args, rank, world, dev, e2e: bool, sample_clocks: bool):
     else:
         bnorm = float(b.norm().item())
     err = true_res / bnorm
-    if not (err < 0.9 and abs(err - relres_dev) <= 1e-5 * max(err, 1e-300) + 1e-9):
-        raise SystemExit(f"bench sanity check failed: true relres {err} vs reported {relres_dev}")
+    # (constant diagonal: the solver's scaled-norm residual IS the true one; variable coefficients: same order of magnitude)
+    same = (abs(err - relres_dev) <= 1e-5 * max(err, 1e-300) + 1e-9) if constant_diagonal else (0.05 * relres_dev <= err <= 20 * relres_dev)
+    if not (err < 0.9 and same):
+        raise RuntimeError(f"bench sanity check failed: true relres {err} vs reported {relres_dev}")
     out = {"ms_dev": ms_dev, "launches": int(launches), "clocks": clocks, "relres": relres_dev, "true_relres": err,
            "value": ITERS_PER_STEP * args.steps / (ms_dev * 1e-3)}
     if e2e:
@@ -450,7 +452,7 @@ def run_gpu(args, rank: int, world: int, local_rank: int):
             kappa = torch.exp(torch.rand(N, dtype=torch.float64, device=dev, generator=g) * 2 - 1)    # exp(U(-1,1)), same on every rank
             G = pkg.mpi_SparseTensor.poisson3d_kappa(kappa, n, n, n, rank, world)
             del kappa
-            gl = cg_leg(pkg, G, args, rank, world, dev, e2e=False, sample_clocks=False)
+            gl = cg_leg(pkg, G, args, rank, world, dev, e2e=False, sample_clocks=False, constant_diagonal=False)
             general = {"workload": f"Jacobi-PCG on the variable-coefficient 7-point operator -div(kappa grad u), {n}^3, "
                                    "kappa = exp(U(-1,1)) per cell (seed 233), face weights (kappa_i+kappa_j)/2, b = A*1, x0 = 0",
                        "value": gl["value"], "unit": UNIT, "ms_per_step": gl["ms_dev"] / args.steps, "gpu_launches": gl["launches"],

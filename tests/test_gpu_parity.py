@@ -670,23 +670,21 @@ def test_pattern_code_spmv_is_lossless(pkg):
     run-to-run deterministic."""
     import torch
 
-    forms = (("rowwin", 1.0, 1.0, 1.0, 1.0), ("rowpat", 1.0, 1.0, 1.0, 0.0), ("code", 0.0, 1.0, 1.0, 0.0),
-             ("off8", 0.0, 0.0, 1.0, 0.0), ("plain", 0.0, 0.0, 0.0, 0.0))
+    # name -> (spmv_rowpat, spmv_code, spmv_off8, spmv_rowwin, spmv_rowmarch)
+    forms = (("rowmarch", 1.0, 1.0, 1.0, 1.0, 1.0), ("rowwin", 1.0, 1.0, 1.0, 1.0, 0.0), ("rowpat", 1.0, 1.0, 1.0, 0.0, 0.0),
+             ("code", 0.0, 1.0, 1.0, 0.0, 0.0), ("off8", 0.0, 0.0, 1.0, 0.0, 0.0), ("plain", 0.0, 0.0, 0.0, 0.0, 0.0))
+    keys = (b"spmv_rowpat", b"spmv_code", b"spmv_off8", b"spmv_rowwin", b"spmv_rowmarch")
 
-    def with_form(rowpat, code, off8, rowwin, fn):
-        pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", rowpat))
-        pkg.check(pkg.lib.ab_set_option(b"spmv_code", code))
-        pkg.check(pkg.lib.ab_set_option(b"spmv_off8", off8))
-        pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin", rowwin))
+    def with_form(rowpat, code, off8, rowwin, rowmarch, fn):
+        for k, v in zip(keys, (rowpat, code, off8, rowwin, rowmarch)):
+            pkg.check(pkg.lib.ab_set_option(k, v))
         try:
             return fn()
         finally:
-            pkg.check(pkg.lib.ab_set_option(b"spmv_rowpat", 1.0))
-            pkg.check(pkg.lib.ab_set_option(b"spmv_code", 1.0))
-            pkg.check(pkg.lib.ab_set_option(b"spmv_off8", 1.0))
-            pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin", 1.0))
+            for k in keys:
+                pkg.check(pkg.lib.ab_set_option(k, 1.0))
 
-    for n in (48, 67):                         # 67: tiles straddle planes, odd sizes
+    for n in (48, 67, 64):                     # 67: tiles straddle planes, odd sizes; 64: n^2 is a multiple of the 1024-row tile -> marching kernel
         N = n ** 3
         h = C.c_int64(0)
         pkg.check(pkg.lib.ab_poisson3d_csr(n, n, n, 0, N, C.byref(h)))
@@ -706,25 +704,26 @@ def test_pattern_code_spmv_is_lossless(pkg):
             pkg.check(pkg.lib.ab_cg_fixed(A.handle(), f.data_ptr(), u.data_ptr(), 40, C.byref(rr)))
             return u
 
-        ys = {name: with_form(a, b, c, d, spmv) for name, a, b, c, d in forms}
+        ys = {name: with_form(a, b, c, d, e, spmv) for name, a, b, c, d, e in forms}
         pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin_dom", 0.0))                # every row walks its pattern out of the stage
         try:
-            ys["rowwin_generic"] = with_form(1.0, 1.0, 1.0, 1.0, spmv)
+            ys["rowwin_generic"] = with_form(1.0, 1.0, 1.0, 1.0, 0.0, spmv)
+            ys["rowmarch_generic"] = with_form(1.0, 1.0, 1.0, 1.0, 1.0, spmv)
         finally:
             pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin_dom", 1.0))
-        assert torch.equal(ys["rowwin_generic"], ys["plain"])
-        for name in ("rowwin", "rowpat", "code", "off8"):
+        assert torch.equal(ys["rowwin_generic"], ys["plain"]) and torch.equal(ys["rowmarch_generic"], ys["plain"])
+        for name in ("rowmarch", "rowwin", "rowpat", "code", "off8"):
             assert torch.equal(ys[name], ys["plain"]), name                      # lossless: same bits
         S = A.to_scipy()
         dinv = 1.0 / np.sqrt(S.diagonal())
         y0 = dinv * (S @ (dinv * x.cpu().numpy()))
         assert np.max(np.abs(ys["plain"].cpu().numpy() - y0)) <= 1e-13 * np.max(np.abs(y0))
-        us = {name: with_form(a, b, c, d, cg) for name, a, b, c, d in forms}
-        for name in ("rowwin", "rowpat", "code", "off8"):
+        us = {name: with_form(a, b, c, d, e, cg) for name, a, b, c, d, e in forms}
+        for name in ("rowmarch", "rowwin", "rowpat", "code", "off8"):
             assert float((us[name] - us["plain"]).abs().max() / us["plain"].abs().max()) <= 1e-11, name
-        assert torch.equal(with_form(1.0, 1.0, 1.0, 0.0, cg), us["rowpat"])     # deterministic run to run
-        assert torch.equal(with_form(1.0, 1.0, 1.0, 1.0, cg), us["rowwin"])
-        pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"rowwin", C.byref(C.c_double(0))))
+        assert torch.equal(with_form(1.0, 1.0, 1.0, 0.0, 0.0, cg), us["rowpat"])     # deterministic run to run
+        assert torch.equal(with_form(1.0, 1.0, 1.0, 1.0, 0.0, cg), us["rowwin"])
+        assert torch.equal(with_form(1.0, 1.0, 1.0, 1.0, 1.0, cg), us["rowmarch"])
         pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin", 0.0))               # the cg_defer_x checks below compare with us["rowpat"]
         # the x update riding in K3 (10 vector passes) is the same arithmetic, only moved
         pkg.check(pkg.lib.ab_set_option(b"cg_defer_x", 0.0))
@@ -744,6 +743,8 @@ def test_pattern_code_spmv_is_lossless(pkg):
         info = C.c_double(0)
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"rowwin", C.byref(info)))
         assert info.value == 1                 # the x-window form was built for the stencil
+        pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"rowmarch", C.byref(info)))
+        assert info.value == (1 if n == 64 else 0)      # chains need n^2 to be a multiple of the tile size
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"npat", C.byref(info)))
         assert info.value == 27                # interior + face / edge / corner variants of the 7-point stencil
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"ncode", C.byref(info)))
@@ -802,6 +803,8 @@ def test_window_spmv_matrix_classes(pkg):
         "2d_5pt": stencil((97, 131), [((0, 1), -1.0), ((0, -1), -1.0), ((1, 0), -1.0), ((-1, 0), -1.0)]),
         "3d_7pt_aniso": stencil((21, 33, 40), [((0, 0, 1), -1.0), ((0, 0, -1), -1.0), ((0, 1, 0), -0.5), ((0, -1, 0), -0.5),
                                                 ((1, 0, 0), -0.25), ((-1, 0, 0), -0.25)]),
+        "3d_7pt_march": stencil((8, 64, 64), [((0, 0, 1), -1.0), ((0, 0, -1), -1.0), ((0, 1, 0), -0.5), ((0, -1, 0), -0.5),
+                                              ((1, 0, 0), -0.25), ((-1, 0, 0), -0.25)]),      # plane = 4 tiles: marching kernel
         "2d_9pt": stencil((64, 80), [((a, b), -0.5) for a in (-1, 0, 1) for b in (-1, 0, 1) if (a, b) != (0, 0)]),
         "tiny": stencil((7,), [((1,), -1.0), ((-1,), -1.0)]),
     }
