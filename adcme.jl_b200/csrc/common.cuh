@@ -162,8 +162,10 @@ struct Csr {
     void*     rm_ent   = nullptr;  // [npat_ent] x {double value; int32 offset inside the plane buffer; int32 plane}
     int32_t*  rm_items = nullptr;  // [2 * rm_nitems]: first tile of each work item, then its length
     int       rm_nitems = 0;
-    int64_t   rm_nrest = 0;        // tiles no chain covers (they reference other intervals)
+    int64_t   rm_nrest = 0;        // tiles no chain covers (they reference other intervals, or are excluded)
+    int32_t*  rm_rest = nullptr;   // [rm_nrest] those tiles, ascending
     int       rm_ok = 0;
+    uint8_t*  rw_exclude = nullptr;  // [ceil(m/1024)] optional (dist.cu): tiles that must not join a chain (they read halo columns)
     // triplet bookkeeping (null when the handle was created from CSR: identity map)
     uint32_t* perm     = nullptr; // [T]  sorted position -> input triplet
     uint32_t* segstart = nullptr; // [nnz+1] first sorted position of each stored entry
@@ -269,6 +271,12 @@ bool spmv_supports_halo_wait(const Csr* c, const double* vals);
 int  launch_spmv_halo(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
                       double* dot_result, double* partials, uint32_t* ticket, const int* done_flag,
                       const int32_t* tile_list, int64_t nlist, const HaloWait& hw, int list_rows);
+// Distributed SpMV with the marching kernel: chains (tiles that read no halo column) first, then — after the
+// in-kernel acquire of the peers' halo flags — the remaining tiles through the x-window kernel, which adds its share
+// of the fused dots and, when hw.peer_blk is set, pushes the totals to the peers.  false: not available for (c, vals, x).
+bool spmv_march_halo_ready(const Csr* c, const double* vals, const double* x);
+int  launch_spmv_march_halo(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec, double* dot_result,
+                            double* partials, uint32_t* ticket, const int* done_flag, const HaloWait& hw);
 // rows per tile that launch_spmv_halo expects in its tile list for this matrix / operand (0: unsupported)
 int  spmv_halo_tile_rows(const Csr* c, const double* vals, const double* x);
 constexpr int SPMV_WINDOW_TILE_ROWS = 1024;   // tile size of the x-window SpMV kernel (spmv.cu RW_R)

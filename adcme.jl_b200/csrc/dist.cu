@@ -200,6 +200,10 @@ __global__ void tile_halo_flag_kernel(const int32_t* __restrict__ rowptr, const 
     __syncthreads();
     if (threadIdx.x == 0) flags[tile] = any ? 1u : 0u;
 }
+__global__ void flags_to_bytes_kernel(const uint32_t* __restrict__ flags, int64_t n, uint8_t* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = flags[t] ? 1 : 0;
+}
 __global__ void tile_split_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ excl, int64_t ntiles,
                                   int32_t* __restrict__ t_int, int32_t* __restrict__ t_bnd) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -544,6 +548,15 @@ static int dist_spmv_dev(DistCsr* d, const double* vals, double* y, const double
     }
     if (d->tiles_all && d->next > 0 && opt("dist_fused_wait", 1.0) != 0.0 && spmv_supports_halo_wait(c, vals)) {
         // one launch: interior tiles, in-kernel acquire of the peers' halo flags, boundary tiles
+        if (spmv_march_halo_ready(c, vals, d->xext)) {
+            // marching kernel over the chains of tiles that read no halo column, then (in-kernel acquire) the rest
+            HaloWait hm{d->blk->halo_flag, d->d_recv_cnt, g_world, d->halo_seq, 0u, &d->blk->err};
+            if (push_seq && dotvec) {
+                hm.peer_blk = d->d_peer_blk; hm.me = g_rank; hm.red_seq = push_seq;
+                if (pushed) *pushed = true;
+            }
+            return launch_spmv_march_halo(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, hm);
+        }
         const int lrows = spmv_halo_tile_rows(c, vals, d->xext);
         const bool win = lrows == SPMV_WINDOW_TILE_ROWS && d->wtiles_all;
         HaloWait hw{d->blk->halo_flag, d->d_recv_cnt, g_world, d->halo_seq, (unsigned)(win ? d->wn_int : d->n_int), &d->blk->err};
@@ -657,7 +670,9 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
     int it = 0;
     SolveScal h;
     const bool fuse_opt = opt("dist_fused_reduce", g_world <= 2 ? 1.0 : 0.0) != 0.0;
-    const bool push_opt = opt("dist_fused_push", 1.0) != 0.0;
+    // measured at 512^3, N=2 (profiles/bench_n2_r02c_*.log): 927 it/s without the folded-in halo push, 769 with it — the
+    // contiguous per-CTA chunks its push needs cost K3'' more bandwidth than the saved launch returns.  Default: off.
+    const bool push_opt = opt("dist_fused_push", 0.0) != 0.0;
     bool halo_pushed = false;     // the previous iteration's K3'' already pushed the halos of the coming SpMV
     while (it < maxit) {
         int chunk = maxit - it < check ? maxit - it : check;
@@ -844,12 +859,14 @@ static __global__ void halo_flag_kernel(const int32_t* __restrict__ colind, size
     size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < nnz) flags[e] = colind[e] >= nloc ? 1u : 0u;
 }
-static __global__ void gather_trip_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx, size_t n,
-                                          const int32_t* __restrict__ entry_row, const double* __restrict__ values, int64_t ilower,
+// idx: the sort's payload = position in the selection it sorted (radix_sort_u64 synthesises it); sel maps that position
+// to the stored entry (null: every entry was selected, position == entry)
+static __global__ void gather_trip_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ sel,
+                                          size_t n, const int32_t* __restrict__ entry_row, const double* __restrict__ values, int64_t ilower,
                                           int64_t* __restrict__ rr, int64_t* __restrict__ cc, double* __restrict__ vv) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const uint32_t e = idx[k];
+    const uint32_t e = sel ? sel[idx[k]] : idx[k];
     rr[k] = ilower + entry_row[e]; cc[k] = (int64_t)keys[k]; vv[k] = values[e];
 }
 // pos[p] = first sorted key >= lows[p]   (p = 0..world; lows[world] = N)
@@ -893,14 +910,14 @@ static int entries_by_col_owner(DistCsr* d, bool only_ext, TripBuf* out, std::ve
     AB_TRY(out->r.alloc(nsel)); AB_TRY(out->c.alloc(nsel)); AB_TRY(out->v.alloc(nsel));
     out->n = nsel;
     if (nsel == 0) return AB_OK;
-    DevBuf<uint64_t> k0, k1; DevBuf<uint32_t> p0, p1;
-    AB_TRY(k0.alloc(nsel)); AB_TRY(k1.alloc(nsel)); AB_TRY(p0.alloc(nsel)); AB_TRY(p1.alloc(nsel));
-    col_keys_kernel<<<nb, 256, 0, stream()>>>(c->colind, nnz, d->nloc, d->ilower, d->ext_glob, only_ext ? excl.p : nullptr, k0.p, p0.p);
+    DevBuf<uint64_t> k0, k1; DevBuf<uint32_t> p0, p1, sel;
+    AB_TRY(k0.alloc(nsel)); AB_TRY(k1.alloc(nsel)); AB_TRY(p0.alloc(nsel)); AB_TRY(p1.alloc(nsel)); AB_TRY(sel.alloc(nsel));
+    col_keys_kernel<<<nb, 256, 0, stream()>>>(c->colind, nnz, d->nloc, d->ilower, d->ext_glob, only_ext ? excl.p : nullptr, k0.p, sel.p);
     AB_LAUNCH_CHECK();
     uint64_t* ks; uint32_t* ps;
     int nbits = 1; while (nbits < 40 && ((int64_t)1 << nbits) < d->N) ++nbits;
     AB_TRY(radix_sort_u64(k0.p, p0.p, k1.p, p1.p, nsel, nbits, &ks, &ps));
-    gather_trip_kernel<<<(unsigned)((nsel + 255) / 256), 256, 0, stream()>>>(ks, ps, nsel, c->entry_row, c->values, d->ilower, out->r.p, out->c.p, out->v.p);
+    gather_trip_kernel<<<(unsigned)((nsel + 255) / 256), 256, 0, stream()>>>(ks, ps, only_ext ? sel.p : nullptr, nsel, c->entry_row, c->values, d->ilower, out->r.p, out->c.p, out->v.p);
     AB_LAUNCH_CHECK();
     std::vector<int64_t> lows(g_world + 1), pos(g_world + 1);
     for (int p = 0; p < g_world; ++p) lows[p] = d->ranges[2 * p];
@@ -1012,6 +1029,12 @@ static int dist_check_symmetric(DistCsr* d, bool* sym) {
         std::vector<int64_t> cnt;
         AB_TRY(entries_by_col_owner(d, true, &mine, &cnt));
         AB_TRY(exchange_triplets(mine.r.p, mine.c.p, mine.v.p, cnt, &got));
+        if (opt("verbose", 0.0) != 0.0) {
+            int hb0 = 0;
+            AB_CUDA(cudaMemcpyAsync(&hb0, bad.p, sizeof(int), cudaMemcpyDeviceToHost, stream()));
+            AB_CUDA(cudaStreamSynchronize(stream()));
+            fprintf(stderr, "[adcme_b200] rank %d symmetry check: local part %d, sent %zu, received %zu off-rank entries\n", g_rank, hb0, mine.n, got.n);
+        }
         if (got.n) {
             dist_sym_cross_kernel<<<(unsigned)((got.n + 255) / 256), 256, 0, stream()>>>(got.r.p, got.c.p, got.v.p, got.n, c->rowptr, c->colind,
                                                                                          c->values, d->nloc, d->ilower, d->ext_glob, bad.p);
@@ -1023,6 +1046,7 @@ static int dist_check_symmetric(DistCsr* d, bool* sym) {
     AB_CUDA(cudaStreamSynchronize(stream()));
     SolveScal* s = (SolveScal*)c->scal;
     double hv[2] = {(double)hb, 0.0};
+    if (opt("verbose", 0.0) != 0.0) fprintf(stderr, "[adcme_b200] rank %d symmetry check: local verdict %d\n", g_rank, hb);
     AB_CUDA(cudaMemcpyAsync(s->red, hv, sizeof(hv), cudaMemcpyHostToDevice, stream()));
     AB_TRY(allreduce2(d, s->red));
     AB_CUDA(cudaMemcpyAsync(hv, s->red, sizeof(hv), cudaMemcpyDeviceToHost, stream()));
@@ -1330,6 +1354,10 @@ int ab_dist_csr_create(int64_t h_local, int64_t ilower, int64_t iupper, int64_t 
             AB_CUDA(cudaMemcpyAsync(&nb_, tot.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream()));
             AB_CUDA(cudaStreamSynchronize(stream()));
             d->wn_bnd = nb_; d->wn_int = wnt - nb_;
+            // the marching SpMV must keep these tiles out of its chains (they read the halo tail)
+            AB_TRY(dev_alloc((void**)&c->rw_exclude, (size_t)wnt));
+            flags_to_bytes_kernel<<<(unsigned)((wnt + 255) / 256), 256, 0, stream()>>>(wf.p, wnt, c->rw_exclude);
+            AB_LAUNCH_CHECK();
             tile_split_kernel<<<(unsigned)((wnt + 255) / 256), 256, 0, stream()>>>(wf.p, we.p, wnt, wi.p, wb.p);
             AB_LAUNCH_CHECK();
             AB_TRY(dev_alloc((void**)&d->wtiles_all, (size_t)(wnt + 1) * sizeof(int32_t)));

@@ -976,9 +976,11 @@ spmv_rowwin_kernel(const __grid_constant__ RowWinPlan P, const uint8_t* __restri
             const int world = hw.world, me = hw.me;
             const uint32_t rseq = hw.red_seq;
             abd::grid_reduce<RW_T, 2>(mine, partials, ticket, s_red, [=](const double(&tot)[2]) {
-                dot_result[0] = tot[0];
-                dot_result[1] = tot[1];
-                abd::p2p_push2(pb, world, me, rseq, tot[0], tot[1]);
+                const double t0 = accumulate ? dot_result[0] + tot[0] : tot[0];
+                const double t1 = accumulate ? dot_result[1] + tot[1] : tot[1];
+                dot_result[0] = t0;
+                dot_result[1] = t1;
+                abd::p2p_push2(pb, world, me, rseq, t0, t1);
             });
         }
         return;
@@ -1335,8 +1337,20 @@ static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<Cod
     std::vector<uint8_t> hmask((size_t)ntiles);
     AB_CUDA(cudaMemcpyAsync(hmask.data(), c->rw_tmask, (size_t)ntiles, cudaMemcpyDeviceToHost, stream()));
     AB_CUDA(cudaStreamSynchronize(stream()));
+    if (c->rw_exclude) {
+        std::vector<uint8_t> hex((size_t)ntiles);
+        AB_CUDA(cudaMemcpyAsync(hex.data(), c->rw_exclude, (size_t)ntiles, cudaMemcpyDeviceToHost, stream()));
+        AB_CUDA(cudaStreamSynchronize(stream()));
+        for (int tI = 0; tI < ntiles; ++tI) if (hex[tI]) hmask[tI] = 0xff;      // excluded: never "pure"
+        if (marchmask == 0xffu) return AB_OK;
+    }
     long long npure = 0;
-    for (int tI = 0; tI < ntiles; ++tI) npure += ((hmask[tI] & ~marchmask) == 0);
+    std::vector<int32_t> rest;
+    for (int tI = 0; tI < ntiles; ++tI) {
+        const bool pure = (hmask[tI] & ~marchmask) == 0;
+        npure += pure;
+        if (!pure) rest.push_back(tI);
+    }
     if (npure == 0) return AB_OK;
     const long long slots = (long long)sm_count() * 3;
     long long Lmax = (npure + 4 * slots - 1) / (4 * slots);
@@ -1367,6 +1381,11 @@ static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<Cod
     AB_CUDA(cudaMemcpyAsync(c->rm_ent, ment.data(), ment.size() * sizeof(MEnt), cudaMemcpyHostToDevice, stream()));
     AB_CUDA(cudaMemcpyAsync(c->rm_items, first.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
     AB_CUDA(cudaMemcpyAsync(c->rm_items + nitems, count.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    dev_free(c->rm_rest); c->rm_rest = nullptr;
+    if (!rest.empty()) {
+        AB_TRY(dev_alloc((void**)&c->rm_rest, rest.size() * sizeof(int32_t)));
+        AB_CUDA(cudaMemcpyAsync(c->rm_rest, rest.data(), rest.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    }
     AB_CUDA(cudaStreamSynchronize(stream()));
     if (!c->rm_plan) c->rm_plan = malloc(sizeof(RowMarchPlan));
     if (!c->rm_plan) return fail(AB_ECUDA, "out of host memory");
@@ -1609,6 +1628,19 @@ int launch_spmv_halo(const Csr* c, const double* vals, const double* x, double* 
     if (!tile_list || !rowpat_ready(c, vals)) return fail(AB_EUNSUPPORTED, "in-kernel halo wait needs the row-pattern SpMV form");
     if (list_rows != spmv_halo_tile_rows(c, vals, x)) return fail(AB_EINVAL, "tile list built for %d-row tiles, kernel uses %d", list_rows, spmv_halo_tile_rows(c, vals, x));
     return launch_spmv_impl(c, vals, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, 0, &hw, list_rows);
+}
+
+bool spmv_march_halo_ready(const Csr* c, const double* vals, const double* x) {
+    return rowpat_ready(c, vals) && rowwin_ready(c, vals, x) && c->rm_ok == 1 && c->rm_plan && c->rm_nrest > 0 && c->rm_rest &&
+           c->rw_exclude && opt("spmv_rowmarch", 1.0) != 0.0;
+}
+int launch_spmv_march_halo(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec, double* dot_result,
+                           double* partials, uint32_t* ticket, const int* done_flag, const HaloWait& hw_) {
+    if (!spmv_march_halo_ready(c, vals, x)) return fail(AB_EUNSUPPORTED, "marching halo SpMV is not available for this matrix");
+    AB_TRY(launch_rowmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag));
+    HaloWait hw = hw_;
+    hw.n_before = 0;      // every remaining tile comes after the acquire
+    return launch_rowwin(c, x, y, dotvec, dot_result, partials, ticket, done_flag, c->rm_rest, c->rm_nrest, dotvec ? 1 : 0, &hw);
 }
 
 int launch_spmv_vals(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,

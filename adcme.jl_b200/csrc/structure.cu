@@ -272,10 +272,11 @@ __global__ void sidx_grad_kernel(const int64_t* __restrict__ ii0, const int64_t*
                                  const double* __restrict__ g0, size_t nout, const int64_t* __restrict__ ii, int64_t ni,
                                  const int64_t* __restrict__ jj, int64_t nj, const int32_t* __restrict__ rowptr,
                                  const int32_t* __restrict__ colind, const uint32_t* __restrict__ segstart,
-                                 const uint32_t* __restrict__ perm, int64_t m, int64_t n, double* __restrict__ g1,
+                                 const uint32_t* __restrict__ perm, int64_t m, int64_t n, uint64_t* __restrict__ tkey,
                                  int* __restrict__ err) {
     size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nout) return;
+    tkey[k] = ~0ull;            // error exits leave a key no target carries
     const int64_t a = ii0[k] - 1, b = jj0[k] - 1;
     if (a < 0 || a >= ni || b < 0 || b >= nj) { atomicExch(err, 1); return; }
     const int64_t r = ii[a] - 1, c = jj[b] - 1;
@@ -289,7 +290,19 @@ __global__ void sidx_grad_kernel(const int64_t* __restrict__ ii0, const int64_t*
     }
     if (e < 0) { atomicExch(err, 2); return; }
     const uint32_t t = perm ? perm[segstart[e + 1] - 1] : (uint32_t)e;
-    atomicAdd(&g1[t], g0[k]);
+    tkey[k] = (uint64_t)t;      // summed per target in ascending k by sidx_grad_reduce_kernel (no fp atomics)
+}
+// keys sorted by target triplet (stable: ascending k inside a target); the head of each run adds its run left to
+// right — the order of the reference's sequential loop — so repeated (ii, jj) positions give a reproducible sum
+__global__ void sidx_grad_reduce_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ kidx, size_t nout,
+                                        const double* __restrict__ g0, double* __restrict__ g1) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nout) return;
+    const uint64_t key = keys[p];
+    if (key == ~0ull || (p > 0 && keys[p - 1] == key)) return;
+    double sum = g0[kidx[p]];
+    for (size_t q = p + 1; q < nout && keys[q] == key; ++q) sum += g0[kidx[q]];
+    g1[key] = sum;
 }
 
 // ================================================================ CSR -> COO, scaling, SpGEMM expansion
@@ -675,8 +688,16 @@ int ab_sparse_indexing_grad(int64_t h, const int64_t* ii_, int64_t ni, const int
     AB_TRY(err.alloc(1));
     AB_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), stream()));
     if (nout) {
+        DevBuf<uint64_t> k0, k1; DevBuf<uint32_t> p0, p1;
+        AB_TRY(k0.alloc(nout)); AB_TRY(k1.alloc(nout)); AB_TRY(p0.alloc(nout)); AB_TRY(p1.alloc(nout));
         sidx_grad_kernel<<<nblk(nout), 256, 0, stream()>>>(ii0.d, jj0.d, g0.d, (size_t)nout, ii.d, ni, jj.d, nj, c->rowptr, c->colind,
-                                                          c->segstart, c->perm, c->m, c->n, g1.d, err.p);
+                                                          c->segstart, c->perm, c->m, c->n, k0.p, err.p);
+        AB_LAUNCH_CHECK();
+        uint64_t* ks; uint32_t* ps;
+        int nbits = 1;
+        while (nbits < 40 && ((int64_t)1 << nbits) < c->T) ++nbits;
+        AB_TRY(radix_sort_u64(k0.p, p0.p, k1.p, p1.p, (size_t)nout, nbits, &ks, &ps));  // error keys (~0) abort the call below anyway
+        sidx_grad_reduce_kernel<<<nblk(nout), 256, 0, stream()>>>(ks, ps, (size_t)nout, g0.d, g1.d);
         AB_LAUNCH_CHECK();
     }
     int herr = 0;

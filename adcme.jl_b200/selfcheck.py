@@ -82,7 +82,7 @@ def dist_parity(pkg, rank: int, world: int, dev, n: int = 96, variants: bool = T
         for k in combos[0]:
             v = C.c_double(0)
             saved[k] = v.value if lib.ab_get_option(k.encode(), C.byref(v)) == 0 else None
-        defaults = dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=(1 if world <= 2 else 0), dist_fused_push=1, spmv_rowwin=1)
+        defaults = dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=(1 if world <= 2 else 0), dist_fused_push=0, spmv_rowwin=1)
         defaults.update({k: v for k, v in saved.items() if v is not None})       # A/B switches of the caller survive
         for cmb in combos:
             _set(lib, check, **cmb)

@@ -118,10 +118,11 @@ def test_handle_misuse_and_shape_errors(pkg):
     h = C.c_int64(0)
     assert pkg.lib.ab_spgemm(111, 222, 0, C.byref(h)) == -2
     A = pkg.SparseTensor(np.array([1]), np.array([2]), np.array([1.0]), 2, 3)
+    one2, out2 = np.ones(2), np.ones(2)
     with pytest.raises(pkg.ADCMEError):
-        pkg.check(pkg.lib.ab_solve(A.handle(), b"CG", np.ones(2).ctypes.data, np.ones(2).ctypes.data, 0.0, 0, None, None))
+        pkg.check(pkg.lib.ab_solve(A.handle(), b"CG", one2.ctypes.data, out2.ctypes.data, 0.0, 0, None, None))
     with pytest.raises(pkg.ADCMEError):
-        pkg.check(pkg.lib.ab_solve(A.handle(), b"NoSuchSolver", np.ones(2).ctypes.data, np.ones(2).ctypes.data, 0.0, 0, None, None))
+        pkg.check(pkg.lib.ab_solve(A.handle(), b"NoSuchSolver", one2.ctypes.data, out2.ctypes.data, 0.0, 0, None, None))
     with pytest.raises(ValueError):
         A @ np.ones(2)
     hc = C.c_int64(0)

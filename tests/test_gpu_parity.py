@@ -763,10 +763,11 @@ def test_pattern_code_spmv_is_lossless(pkg):
     assert np.linalg.norm(S @ u - f) / np.linalg.norm(f) <= TOL_SOLVE
     # new values on the same pattern invalidate the codes (values_version): constant -> scaled by 3
     h2 = C.c_int64(0)
-    pkg.check(pkg.lib.ab_poisson2d_csr(n, np.ones((n + 2, n + 2)).ctypes.data, -1, C.byref(h2)))
+    k_one, k_three = np.ones((n + 2, n + 2)), 3.0 * np.ones((n + 2, n + 2))      # kept alive: ctypes.data of a temporary dangles
+    pkg.check(pkg.lib.ab_poisson2d_csr(n, k_one.ctypes.data, -1, C.byref(h2)))
     B = pkg.SparseTensor.from_handle(h2.value)
     u1 = pkg.backslash(B, f, "CG")
-    pkg.check(pkg.lib.ab_poisson2d_update(h2.value, n, (3.0 * np.ones((n + 2, n + 2))).ctypes.data, -1))
+    pkg.check(pkg.lib.ab_poisson2d_update(h2.value, n, k_three.ctypes.data, -1))
     u3 = pkg.backslash(B, f, "CG")
     assert np.linalg.norm(3.0 * u3 - u1) / np.linalg.norm(u1) <= 1e-9
 
