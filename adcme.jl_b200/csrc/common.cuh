@@ -165,6 +165,13 @@ struct Csr {
     int64_t   rm_nrest = 0;        // tiles no chain covers (they reference other intervals, or are excluded)
     int32_t*  rm_rest = nullptr;   // [rm_nrest] those tiles, ascending
     int       rm_ok = 0;
+    void*     zm_plan  = nullptr;  // host copy of the z-register marching plan (spmv.cu ZMarchPlan)
+    int32_t*  zm_items = nullptr;  // [2 * zm_nitems]: first chain position (group of G tiles) of each work item, then its length
+    int       zm_nitems = 0;
+    int64_t   zm_nrest = 0;        // 1024-row tiles no item covers
+    int32_t*  zm_rest = nullptr;   // [zm_nrest] those tiles, ascending
+    int       zm_ok = 0;
+    uint8_t*  zm_mask = nullptr;   // [256] per pattern: which entries of the dominant pattern it keeps (0x80: walk the table)
     uint8_t*  rw_exclude = nullptr;  // [ceil(m/1024)] optional (dist.cu): tiles that must not join a chain (they read halo columns)
     // triplet bookkeeping (null when the handle was created from CSR: identity map)
     uint32_t* perm     = nullptr; // [T]  sorted position -> input triplet

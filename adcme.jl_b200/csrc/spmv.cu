@@ -737,6 +737,10 @@ rowpat_assign_kernel(const int32_t* __restrict__ rowptr, const uint8_t* __restri
 static int csr_build_rowwin(Csr* c, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat);
 struct RowWinPlan;
 static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat);
+struct RowMarchPlan;
+struct MarchEnt { double v; int32_t soff; int32_t plane; };     // pattern entry of the marching kernels (16 bytes, read as int4)
+static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<MarchEnt>& ment, const std::vector<uint32_t>& pinfo, int npat,
+                            const std::vector<char>& pat_ok, const std::vector<uint8_t>& hmask, unsigned marchmask);
 
 // npat > 0 afterwards: rowcode/pat_ent/pat_info encode the matrix the pattern codes encode
 static int csr_ensure_rowpat(Csr* c) {
@@ -744,6 +748,7 @@ static int csr_ensure_rowpat(Csr* c) {
     c->npat = 0;
     c->rw_ok = 0;
     c->rm_ok = 0;
+    c->zm_ok = 0;
     if (c->ncode <= 0 || c->m == 0) return AB_OK;
     DevBuf<unsigned long long> gtab; DevBuf<int> grep, gcount;
     AB_TRY(gtab.alloc(VAL_HASH)); AB_TRY(grep.alloc(VAL_HASH)); AB_TRY(gcount.alloc(1));
@@ -1159,6 +1164,321 @@ spmv_rowmarch_kernel(const __grid_constant__ RowMarchPlan P, const uint8_t* __re
     }
 }
 
+// ---- z-register marching form -----------------------------------------------------------------------
+// Measured (B200, 512^3, profiles/spmv_rowmarch_r02b_*): spmv_rowmarch_kernel 0.664 ms = 3.4 TB/s of HBM for
+// 17 B/row — no pipe is busy (issue slots 51 %, DRAM 42 %, L2<->SM 6.7 TB/s); the top stall is the CTA barrier
+// that closes every 1024-row tile, and a ring of four windows of which three are live leaves ONE window (8 KB
+// of HBM data) in flight per CTA.  This form changes three things:
+//  * the planes -M and +M are not kept in shared memory.  When every entry of plane -1 / +1 sits exactly M rows
+//    below / above its row (3-D 7-point, 2-D 5-point with long lines, ...), thread t owns the same local rows at
+//    every chain position, so x[row - M] and x[row] are simply the values it read one and two positions ago:
+//    they live in registers (prv, cur), and only the window AHEAD is read once per row (nxt).  Two windows are
+//    live, so a ring of four keeps TWO windows in flight; a row costs 4 + 1 LDS.64 instead of 7.
+//  * a chain position is G consecutive 1024-row tiles (G = 4 at 512^3: 8 lines of the plane per window, one line
+//    of margin on each side), so the margins add 25 % to the x bytes that cross the L2 -> SM fabric instead of
+//    100 %: 10 + 1 + 8 bytes per row through L2 instead of 25 (the fabric saturates near 9-10 TB/s).
+//  * no CTA-wide barrier: one producer warp drives the TMA unit, sixteen consumer warps synchronise with it only
+//    through per-slot mbarriers (full: bytes landed; empty: all sixteen warps are done with the slot), so warps
+//    drift up to two positions apart instead of meeting after every tile.
+// One CTA per SM (4 x 41 KB ring at 512^3).  Summation order inside a row is the stored order: y is bit-identical
+// to every other form.  The fused dots are reduced per ITEM and summed in item order.
+constexpr int ZM_NT = 512;                  // consumer threads
+constexpr int ZM_NPW = 2;                   // producer warps
+constexpr int ZM_THREADS = ZM_NT + 32 * ZM_NPW;
+constexpr int ZM_NB_MAX = 8;                // ring slots: 4 or 8 (as many as fit)
+constexpr size_t ZM_SMEM_MAX = 225 * 1024;
+struct ZMarchPlan {
+    int G, S;               // 1024-row tiles per chain position; march stride in positions
+    int lo, len;            // window: x[r0 + lo, r0 + lo + len), r0 = first row of the position; len in doubles (even)
+    int center;             // offset of x[row] inside the window relative to the local row (= -lo)
+    int dom, dk;            // dominant pattern and its length (dom < 0: every row walks its pattern)
+    int nsuper;             // chain positions (groups of G tiles) in the matrix
+    int nb;                 // ring slots (power of two <= ZM_NB_MAX)
+    int chunk;              // TMA mode: bytes per bulk copy (a window is streamed as several copies on the same mbarrier)
+    int tma;                // 1: windows by cp.async.bulk (one thread); 0: by 16-byte cp.async of the producer warps (LDGSTS)
+    int dsoff[RW_MAXK];     // dominant pattern, plane-0 entries: window offset relative to the local row
+    double dval[RW_MAXK];
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(abd::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void zm_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(ZM_NT) : "memory"); }
+// 16-byte global -> shared copy through the LSU (SASS: LDGSTS), bypassing registers and L1
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(abd::smem_u32(dst)), "l"(src) : "memory");
+}
+// the executing thread arrives on `bar` once all its earlier cp.async copies have landed (the arrival is part of the
+// barrier's initial count: .noinc)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(abd::smem_u32(bar)) : "memory");
+}
+
+// K > 0: the dominant pattern is {plane -1 @centre, K-2 entries of plane 0, plane +1 @centre} with values and offsets in
+// the kernel parameters; CK: position of the diagonal (centre, plane 0) inside it, -1 if it has none.
+template <int G, int K, int CK>
+__global__ void __launch_bounds__(ZM_THREADS, 1)
+spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restrict__ rowcode, const int4* __restrict__ ent,
+                   int nent, const uint32_t* __restrict__ pinfo, const uint8_t* __restrict__ pmask, const double* __restrict__ x, long long xlen,
+                   double* __restrict__ y, unsigned m, const int32_t* __restrict__ item_first,
+                   const int32_t* __restrict__ item_count, unsigned nitems, const double* __restrict__ dotvec,
+                   int dot_in_window, double* partials, uint32_t* ticket, double* dot_result,
+                   const int* __restrict__ done) {
+    constexpr int TR = G * RW_R;
+    constexpr int RPT = TR / ZM_NT;
+    extern __shared__ __align__(128) unsigned char zm_smem[];
+    const int len = P.len;
+    const unsigned NB = (unsigned)P.nb, NBM = NB - 1u;
+    const int nbsh = 31 - __clz((int)NB);
+    double*   s_ring = reinterpret_cast<double*>(zm_smem);                                     // [NB][len]
+    uint8_t*  s_code = zm_smem + (size_t)NB * len * 8;                                         // [NB][TR]
+    int4*     s_ent  = reinterpret_cast<int4*>(s_code + NB * TR);                              // [nent]
+    uint32_t* s_info = reinterpret_cast<uint32_t*>(s_ent + nent);                              // [256]
+    __shared__ alignas(8) uint64_t full[ZM_NB_MAX], empty[ZM_NB_MAX];
+    __shared__ double s_red[32];
+    __shared__ uint8_t s_mask[256];
+    __shared__ bool s_last;
+    if (done && *done) return;
+    const unsigned t = threadIdx.x;
+    for (int i = t; i < nent; i += ZM_THREADS) s_ent[i] = ent[i];
+    for (int i = t; i < 256; i += ZM_THREADS) { s_info[i] = pinfo[i]; s_mask[i] = pmask[i]; }
+    if (t == 0) {
+#pragma unroll
+        for (int b = 0; b < ZM_NB_MAX; ++b) { abd::mbar_init(&full[b], P.tma ? 1 : 32 * ZM_NPW); abd::mbar_init(&empty[b], ZM_NT / 32); }
+        abd::mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (t >= ZM_NT) {
+        // ---------------- producers: feed the ring, L + 2 windows per item (positions -1 .. L)
+        // Two delivery paths, same speed (0.4393 vs 0.4397 ms at 512^3, profiles/bench_n1_r02f_*): cp.async.bulk issued by
+        // one thread (TMA unit, default) or 16-byte cp.async copies issued by both producer warps (LDGSTS), arriving on the
+        // slot's mbarrier through cp.async.mbarrier.arrive — kept as the A/B that showed the delivery path was never the
+        // limit (the boundary-lane table walks were; see the mask comment below).
+        const unsigned pt = t - ZM_NT;             // 0 .. 32 * ZM_NPW - 1
+        const bool tma = P.tma != 0;
+        if (!tma || pt == 0) {
+            unsigned cnt = 0;
+            for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int first = item_first[item], L = item_count[item];
+                for (int q = 0; q < L + 2; ++q, ++cnt) {
+                    const unsigned slot = cnt & NBM, use = cnt >> nbsh;
+                    if (use > 0) abd::mbar_wait(&empty[slot], (use - 1) & 1u);
+                    const long long u = (long long)first + (long long)(q - 1) * P.S;
+                    unsigned bytes = 0, cbytes = 0, r0 = 0;
+                    long long a = 0, b = 0, tail = -1, base = 0;
+                    if (u >= 0 && u < P.nsuper) {
+                        r0 = (unsigned)u * (unsigned)TR;
+                        const unsigned nr = min((unsigned)TR, m - r0);
+                        cbytes = (nr + 15u) & ~15u;
+                        base = (long long)r0 + P.lo;
+                        a = base; b = base + len;
+                        if (a < 0) a = 0;
+                        if (b > xlen) { b = xlen; if (b & 1) { b -= 1; tail = b; } }
+                        if (b > a) bytes = (unsigned)(b - a) * 8u;
+                        if (tail >= a && tail >= 0 && pt == 0) {
+                            s_ring[(size_t)slot * len + (tail - base)] = x[tail];
+                            __threadfence_block();
+                        }
+                    }
+                    const unsigned char* src = reinterpret_cast<const unsigned char*>(x + a);
+                    unsigned char* dst = reinterpret_cast<unsigned char*>(s_ring + (size_t)slot * len + (a - base));
+                    if (tma) {
+                        abd::mbar_expect_tx(&full[slot], bytes + cbytes);
+                        if (cbytes) abd::bulk_g2s(s_code + slot * TR, rowcode + r0, cbytes, &full[slot]);
+                        for (unsigned o = 0; o < bytes; o += (unsigned)P.chunk)
+                            abd::bulk_g2s(dst + o, src + o, min((unsigned)P.chunk, bytes - o), &full[slot]);
+                    } else {
+                        for (unsigned o = pt * 16u; o < bytes; o += 32u * ZM_NPW * 16u) cp_async16(dst + o, src + o);
+                        for (unsigned o = pt * 16u; o < cbytes; o += 32u * ZM_NPW * 16u) cp_async16(s_code + slot * TR + o, rowcode + r0 + o);
+                        cp_async_arrive(&full[slot]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- consumers
+        const unsigned lane = t & 31u, w = t >> 5;
+        unsigned cnt = 0;                          // ring position of the centre window
+        auto wait_full = [&](unsigned c) { abd::mbar_wait(&full[c & NBM], (c >> nbsh) & 1u); };
+        auto release = [&](unsigned c) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[c & NBM]);
+        };
+        for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int first = item_first[item], L = item_count[item];
+            double dot = 0.0, dot2 = 0.0;
+            double prv[RPT], cur[RPT];
+            wait_full(cnt);
+            {
+                const double* wp = s_ring + (size_t)(cnt & NBM) * len + P.center + t;
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) prv[j] = wp[j * ZM_NT];
+            }
+            release(cnt);
+            ++cnt;
+            wait_full(cnt);
+            {
+                const double* wp = s_ring + (size_t)(cnt & NBM) * len + P.center + t;
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) cur[j] = wp[j * ZM_NT];
+            }
+            for (int k = 0; k < L; ++k) {
+                wait_full(cnt + 1);
+                const unsigned r0 = (unsigned)(first + k * P.S) * (unsigned)TR;
+                const unsigned nr = min((unsigned)TR, m - r0);
+                const double* wc = s_ring + (size_t)(cnt & NBM) * len + t;                       // + window offset + j * ZM_NT
+                const double* wn = s_ring + (size_t)((cnt + 1) & NBM) * len + P.center + t;
+                const uint8_t* codes = s_code + (cnt & NBM) * TR + t;
+                if (K > 0) {
+                    // straight-line over the thread's RPT rows (independent FMA chains, loads hoisted).  A row whose pattern
+                    // is the dominant one with some entries MISSING (Dirichlet faces / edges / corners of a stencil: same
+                    // offsets, same values) runs the same code with those FMAs predicated off by its mask — so the two lanes
+                    // of every line that sit on the x-boundary do not send their warps through the table walk 2 * RPT times
+                    // per position (measured: those warps were the critical path of the whole CTA).  Operands of masked-off
+                    // entries are still loaded: they lie inside the ring slot whatever the row.  Bit 7 of the mask: the
+                    // pattern is something else and is walked from its table.
+                    constexpr int JB = RPT > 4 ? 4 : RPT;          // rows in flight per thread (register budget: 96)
+                    constexpr unsigned FULL = (1u << K) - 1u;
+#pragma unroll
+                    for (int jb = 0; jb < RPT; jb += JB) {
+                    double nx[JB], acc[JB];
+                    unsigned mk[JB];
+                    bool allfull = true;
+#pragma unroll
+                    for (int j = 0; j < JB; ++j) { nx[j] = wn[(jb + j) * ZM_NT]; mk[j] = codes[(jb + j) * ZM_NT]; }
+#pragma unroll
+                    for (int j = 0; j < JB; ++j) { mk[j] = s_mask[mk[j]] | (mk[j] << 8); allfull = allfull && (mk[j] & 0xffu) == FULL; }
+                    if (__all_sync(0xffffffffu, allfull)) {
+#pragma unroll
+                        for (int j = 0; j < JB; ++j) acc[j] = fma(P.dval[0], prv[jb + j], 0.0);
+#pragma unroll
+                        for (int e = 1; e < K - 1; ++e) {
+#pragma unroll
+                            for (int j = 0; j < JB; ++j) {
+                                const double xk = (e == CK) ? cur[jb + j] : wc[P.dsoff[e] + (jb + j) * ZM_NT];
+                                acc[j] = fma(P.dval[e], xk, acc[j]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < JB; ++j) acc[j] = fma(P.dval[K > 0 ? K - 1 : 0], nx[j], acc[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < JB; ++j) acc[j] = (mk[j] & 1u) ? fma(P.dval[0], prv[jb + j], 0.0) : 0.0;
+#pragma unroll
+                        for (int e = 1; e < K - 1; ++e) {
+#pragma unroll
+                            for (int j = 0; j < JB; ++j) {
+                                const double xk = (e == CK) ? cur[jb + j] : wc[P.dsoff[e] + (jb + j) * ZM_NT];
+                                if ((mk[j] >> e) & 1u) acc[j] = fma(P.dval[e], xk, acc[j]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < JB; ++j)
+                            if ((mk[j] >> (K > 0 ? K - 1 : 0)) & 1u) acc[j] = fma(P.dval[K > 0 ? K - 1 : 0], nx[j], acc[j]);
+#pragma unroll
+                        for (int j = 0; j < JB; ++j) {
+                            if (mk[j] & 0x80u) {
+                                const uint32_t info = s_info[mk[j] >> 8];
+                                const int4* e = s_ent + (info & 0xffffu);
+                                const int elen = (int)(info >> 16);
+                                double a = 0.0;
+                                for (int q = 0; q < elen; ++q) {
+                                    const int4 qe = e[q];
+                                    const double xv = qe.w == 0 ? wc[qe.z + (jb + j) * ZM_NT] : (qe.w < 0 ? prv[jb + j] : nx[j]);
+                                    a = fma(__hiloint2double(qe.y, qe.x), xv, a);
+                                }
+                                acc[j] = a;
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < JB; ++j) {
+                        const unsigned tl = t + (unsigned)(jb + j) * ZM_NT;
+                        if (tl < nr) {
+                            y[r0 + tl] = acc[j];
+                            if (dotvec) {
+                                const double wv = dot_in_window ? cur[jb + j] : dotvec[r0 + tl];
+                                dot  = fma(acc[j], wv, dot);
+                                dot2 = fma(acc[j], acc[j], dot2);
+                            }
+                        }
+                        prv[jb + j] = cur[jb + j];
+                        cur[jb + j] = nx[j];
+                    }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < RPT; ++j) {
+                        const unsigned tl = t + (unsigned)j * ZM_NT;
+                        const double nx = wn[j * ZM_NT];
+                        if (tl < nr) {
+                            const uint32_t info = s_info[codes[j * ZM_NT]];
+                            const int4* e = s_ent + (info & 0xffffu);
+                            const int elen = (int)(info >> 16);
+                            double acc = 0.0;
+                            for (int q = 0; q < elen; ++q) {
+                                const int4 qe = e[q];
+                                const double xv = qe.w == 0 ? wc[qe.z + j * ZM_NT] : (qe.w < 0 ? prv[j] : nx);
+                                acc = fma(__hiloint2double(qe.y, qe.x), xv, acc);
+                            }
+                            y[r0 + tl] = acc;
+                            if (dotvec) {
+                                const double wv = dot_in_window ? cur[j] : dotvec[r0 + tl];
+                                dot  = fma(acc, wv, dot);
+                                dot2 = fma(acc, acc, dot2);
+                            }
+                        }
+                        prv[j] = cur[j];
+                        cur[j] = nx;
+                    }
+                }
+                release(cnt);
+                ++cnt;
+            }
+            release(cnt);                          // the window ahead of the last position was only read for nxt
+            ++cnt;
+            if (dotvec) {
+                const double d0 = abd::warp_sum(dot), d1 = abd::warp_sum(dot2);
+                if (lane == 0) { s_red[w] = d0; s_red[16 + w] = d1; }
+                zm_consumer_sync();
+                if (w == 0) {
+                    double a0 = lane < ZM_NT / 32 ? s_red[lane] : 0.0, a1 = lane < ZM_NT / 32 ? s_red[16 + lane] : 0.0;
+                    a0 = abd::warp_sum(a0);
+                    a1 = abd::warp_sum(a1);
+                    if (lane == 0) { partials[item] = a0; partials[(size_t)nitems + item] = a1; }
+                }
+                zm_consumer_sync();
+            }
+        }
+    }
+    if (dotvec) {
+        // deterministic grid reduction over ITEMS (fixed order, independent of the item -> CTA assignment)
+        __syncthreads();
+        if (t == 0) {
+            __threadfence();
+            const uint32_t tk = atomicAdd(ticket, 1u);
+            s_last = (tk == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            double a0 = 0.0, a1 = 0.0;
+            const volatile double* p0 = partials;
+            const volatile double* p1 = partials + nitems;
+            for (unsigned i = t; i < nitems; i += ZM_THREADS) { a0 += p0[i]; a1 += p1[i]; }
+            a0 = abd::block_sum<ZM_THREADS>(a0, s_red);
+            a1 = abd::block_sum<ZM_THREADS>(a1, s_red);
+            if (t == 0) {
+                *ticket = 0;
+                dot_result[0] = a0;
+                dot_result[1] = a1;
+            }
+        }
+    }
+}
+
 // rows per pattern (dominant pattern = argmax)
 __global__ void __launch_bounds__(256)
 rowcode_hist_kernel(const uint8_t* __restrict__ rowcode, int64_t m, unsigned long long* __restrict__ hist) {
@@ -1280,6 +1600,7 @@ static int csr_build_rowwin(Csr* c, const std::vector<CodeEnt>& pent, const std:
 // rm_ok = 1 afterwards when chains of tiles can share their windows (see spmv_rowmarch_kernel)
 static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat) {
     c->rm_ok = 0;
+    c->zm_ok = 0;
     int ic = -1;
     for (int i = 0; i < W.ni; ++i) if (0 >= W.lo[i] && RW_R <= W.lo[i] + W.len[i]) ic = i;
     if (ic < 0) return AB_OK;
@@ -1312,7 +1633,7 @@ static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<Cod
     Q.center = (int)(0 - loc);
     Q.ntiles = (int)((c->m + RW_R - 1) / RW_R);
     // entries: (offset inside the plane buffer, plane)
-    struct MEnt { double v; int32_t soff; int32_t plane; };
+    typedef MarchEnt MEnt;
     std::vector<MEnt> ment(pent.size());
     std::vector<char> pat_ok(256, 1);
     for (int p = 0; p < npat; ++p) {
@@ -1393,6 +1714,129 @@ static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<Cod
     c->rm_nitems = nitems;
     c->rm_nrest = (long long)ntiles - npure;
     c->rm_ok = 1;
+    return csr_build_zmarch(c, Q, ment, pinfo, npat, pat_ok, hmask, marchmask);
+}
+
+// zm_ok = 1 afterwards when the z-register marching kernel applies: every entry of the planes -M / +M sits exactly M rows
+// from its row (so those operands are what the owning thread read one / two chain positions earlier).
+static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<MarchEnt>& ment, const std::vector<uint32_t>& pinfo, int npat,
+                            const std::vector<char>& pat_ok, const std::vector<uint8_t>& hmask, unsigned marchmask) {
+    c->zm_ok = 0;
+    for (int p = 0; p < npat; ++p) {
+        if (!pat_ok[p]) continue;
+        const int st = (int)(pinfo[p] & 0xffffu), len = (int)(pinfo[p] >> 16);
+        for (int k = 0; k < len; ++k)
+            if (ment[st + k].plane != 0 && ment[st + k].soff != Q.center) return AB_OK;
+    }
+    const int margins = Q.len - RW_R;
+    auto smem_for = [&](int g, int nb) { return (size_t)nb * (margins + g * RW_R) * 8 + (size_t)nb * g * RW_R + ment.size() * 16 + 1024; };
+    int G = 0;
+    for (int g = 4; g >= 1 && !G; g >>= 1)
+        if (Q.S % g == 0 && smem_for(g, 4) <= ZM_SMEM_MAX) G = g;
+    const int gopt = (int)opt("spmv_zmarch_g", 0.0);
+    if (gopt == 1 || gopt == 2) { if (G >= gopt && Q.S % gopt == 0) G = gopt; }
+    if (!G) return AB_OK;
+    int NB = smem_for(G, 8) <= ZM_SMEM_MAX ? 8 : 4;
+    const int nbopt = (int)opt("spmv_zmarch_nb", 0.0);
+    if (nbopt == 4) NB = 4;
+    ZMarchPlan Z;
+    memset(&Z, 0, sizeof(Z));
+    Z.G = G; Z.S = Q.S / G; Z.lo = Q.lo; Z.len = margins + G * RW_R; Z.center = Q.center; Z.dom = -1;
+    Z.nb = NB;
+    Z.chunk = (int)opt("spmv_zmarch_chunk", 4096.0) & ~15;
+    if (Z.chunk < 512) Z.chunk = 512;
+    Z.tma = opt("spmv_zmarch_tma", 1.0) != 0.0 ? 1 : 0;
+    const int ntiles = Q.ntiles;
+    Z.nsuper = (ntiles + G - 1) / G;
+    // dominant pattern in the kernel parameters only in the shape {plane -1 @centre, plane 0 ..., plane +1 @centre}
+    if (Q.dom >= 0 && Q.dk >= 3 && Q.dplane[0] == -1 && Q.dsoff[0] == Q.center && Q.dplane[Q.dk - 1] == 1 && Q.dsoff[Q.dk - 1] == Q.center) {
+        bool mid0 = true;
+        for (int k = 1; k + 1 < Q.dk; ++k) mid0 = mid0 && Q.dplane[k] == 0;
+        if (mid0) {
+            Z.dom = Q.dom; Z.dk = Q.dk;
+            for (int k = 0; k < Q.dk; ++k) { Z.dsoff[k] = Q.dsoff[k]; Z.dval[k] = Q.dval[k]; }
+        }
+    }
+    // ---- per-pattern masks: which entries of the dominant pattern a row pattern keeps (same plane, offset and value bits,
+    // same order); 0x80: not a sub-pattern of the dominant one — walked from the table
+    std::vector<uint8_t> pmask(256, 0x80);
+    if (Z.dom >= 0) {
+        const int dst = (int)(pinfo[Z.dom] & 0xffffu);
+        for (int p = 0; p < npat; ++p) {
+            if (!pat_ok[p]) continue;
+            const int st = (int)(pinfo[p] & 0xffffu), len = (int)(pinfo[p] >> 16);
+            unsigned mask = 0;
+            int k = 0;
+            for (int e = 0; e < Z.dk && k < len; ++e) {
+                const MarchEnt &a = ment[dst + e], &b = ment[st + k];
+                if (a.plane == b.plane && a.soff == b.soff && memcmp(&a.v, &b.v, sizeof(double)) == 0) { mask |= 1u << e; ++k; }
+            }
+            if (k == len && Z.dk <= 7) pmask[p] = (uint8_t)mask;
+        }
+    }
+    if (!c->zm_mask) AB_TRY(dev_alloc((void**)&c->zm_mask, 256));
+    AB_CUDA(cudaMemcpyAsync(c->zm_mask, pmask.data(), 256, cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    // ---- chain positions that only touch the three marching intervals
+    const int ns = Z.nsuper, Sp = Z.S;
+    std::vector<uint8_t> pure((size_t)ns);
+    std::vector<uint8_t> covered((size_t)ntiles, 0);
+    for (int u = 0; u < ns; ++u) {
+        bool ok = true;
+        for (int i = 0; i < G && u * G + i < ntiles; ++i) ok = ok && (hmask[(size_t)u * G + i] & ~marchmask) == 0;
+        pure[u] = ok;
+    }
+    const int Zc = (ns + Sp - 1) / Sp;                 // chain length
+    // segment length: rounds x (L + 2 windows per item), plus a quarter of the total window count (traffic)
+    const int grid = sm_count();
+    int bestL = Zc; double bestc = 1e300;
+    for (int nseg = 1; nseg <= Zc && nseg <= 256; ++nseg) {
+        const int Ls = (Zc + nseg - 1) / nseg;
+        if (nseg > 1 && (Zc + nseg - 2) / (nseg - 1) == Ls) continue;      // same length as the previous candidate
+        const long long nit = (long long)Sp * ((Zc + Ls - 1) / Ls);
+        if (nit > 16000) break;
+        const long long rounds = (nit + grid - 1) / grid;
+        const double cost = (double)rounds * (Ls + 2) + 0.25 * (double)nit * (Ls + 2) / grid;
+        if (cost < bestc) { bestc = cost; bestL = Ls; }
+    }
+    const int lopt = (int)opt("spmv_zmarch_len", 0.0);
+    if (lopt > 0) bestL = lopt;
+    std::vector<int32_t> first, count;
+    for (int z0 = 0; z0 < Zc; z0 += bestL)
+        for (int tI = 0; tI < Sp; ++tI) {
+            int run = 0, start = 0;
+            for (int z = z0; z < Zc && z < z0 + bestL; ++z) {
+                const long long u = (long long)z * Sp + tI;
+                const bool ok = u < ns && pure[u];
+                if (ok) { if (run == 0) start = (int)u; ++run; }
+                if ((!ok || z + 1 == Zc || z + 1 == z0 + bestL) && run) {
+                    first.push_back(start); count.push_back(run);
+                    for (int q = 0; q < run; ++q)
+                        for (int i = 0; i < G; ++i) { const long long tt = ((long long)start + (long long)q * Sp) * G + i; if (tt < ntiles) covered[tt] = 1; }
+                    run = 0;
+                }
+            }
+        }
+    const int nitems = (int)first.size();
+    if (nitems == 0 || nitems > 16000) return AB_OK;
+    std::vector<int32_t> rest;
+    for (int tI = 0; tI < ntiles; ++tI) if (!covered[tI]) rest.push_back(tI);
+    dev_free(c->zm_items); c->zm_items = nullptr;
+    dev_free(c->zm_rest); c->zm_rest = nullptr;
+    AB_TRY(dev_alloc((void**)&c->zm_items, (size_t)2 * nitems * sizeof(int32_t)));
+    AB_CUDA(cudaMemcpyAsync(c->zm_items, first.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemcpyAsync(c->zm_items + nitems, count.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    if (!rest.empty()) {
+        AB_TRY(dev_alloc((void**)&c->zm_rest, rest.size() * sizeof(int32_t)));
+        AB_CUDA(cudaMemcpyAsync(c->zm_rest, rest.data(), rest.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    }
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    if (!c->zm_plan) c->zm_plan = malloc(sizeof(ZMarchPlan));
+    if (!c->zm_plan) return fail(AB_ECUDA, "out of host memory");
+    memcpy(c->zm_plan, &Z, sizeof(Z));
+    c->zm_nitems = nitems;
+    c->zm_nrest = (long long)rest.size();
+    c->zm_ok = 1;
     return AB_OK;
 }
 
@@ -1533,6 +1977,41 @@ static int launch_rowmarch(const Csr* c, const double* x, double* y, const doubl
     return AB_OK;
 }
 
+static bool zmarch_ready(const Csr* c) { return c->zm_ok == 1 && c->zm_plan && opt("spmv_zmarch", 1.0) != 0.0; }
+static int launch_zmarch(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result, double* partials,
+                         uint32_t* ticket, const int* done_flag) {
+    const ZMarchPlan& P = *reinterpret_cast<const ZMarchPlan*>(c->zm_plan);
+    const size_t smem = (size_t)P.nb * P.len * 8 + (size_t)P.nb * P.G * RW_R + (size_t)c->npat_ent * 16 + 1024;
+    const int dot_in_window = (dotvec == x) ? 1 : 0;
+    int ck = -1;
+    for (int k = 1; k + 1 < P.dk; ++k) if (P.dom >= 0 && P.dsoff[k] == P.center) ck = k;
+    const bool fast = P.dom >= 0 && opt("spmv_rowwin_dom", 1.0) != 0.0;
+    const unsigned nitems = (unsigned)c->zm_nitems;
+    unsigned grid = (unsigned)sm_count();
+    if (grid > nitems) grid = nitems;
+#define AB_ZM(GG, KK, CC)                                                                                                     \
+    do {                                                                                                                      \
+        auto kern = spmv_zmarch_kernel<GG, KK, CC>;                                                                           \
+        static size_t smem_set = 0;                                                                                           \
+        if (smem > smem_set) {                                                                                                \
+            AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZM_SMEM_MAX));               \
+            smem_set = ZM_SMEM_MAX;                                                                                           \
+        }                                                                                                                     \
+        kern<<<grid, ZM_THREADS, smem, stream()>>>(P, c->rowcode, (const int4*)c->rm_ent, c->npat_ent, c->pat_info, c->zm_mask, x, \
+                                                   (long long)c->n, y, (unsigned)c->m, c->zm_items, c->zm_items + nitems,    \
+                                                   nitems, dotvec, dot_in_window, partials, ticket, dot_result, done_flag);  \
+    } while (0)
+#define AB_ZMG(KK, CC) do { if (P.G == 4) AB_ZM(4, KK, CC); else if (P.G == 2) AB_ZM(2, KK, CC); else AB_ZM(1, KK, CC); } while (0)
+    if (fast && P.dk == 7 && ck == 3) AB_ZMG(7, 3);
+    else if (fast && P.dk == 5 && ck == 2) AB_ZMG(5, 2);
+    else if (fast && P.dk == 3 && ck == 1) AB_ZMG(3, 1);
+    else AB_ZMG(0, -1);
+#undef AB_ZMG
+#undef AB_ZM
+    AB_LAUNCH_CHECK();
+    return AB_OK;
+}
+
 static int pick_vector_lanes(const Csr* c) {
     double avg = c->m ? (double)c->nnz / (double)c->m : 0.0;
     if (avg <= 3) return 2;
@@ -1637,9 +2116,13 @@ bool spmv_march_halo_ready(const Csr* c, const double* vals, const double* x) {
 int launch_spmv_march_halo(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec, double* dot_result,
                            double* partials, uint32_t* ticket, const int* done_flag, const HaloWait& hw_) {
     if (!spmv_march_halo_ready(c, vals, x)) return fail(AB_EUNSUPPORTED, "marching halo SpMV is not available for this matrix");
-    AB_TRY(launch_rowmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag));
     HaloWait hw = hw_;
     hw.n_before = 0;      // every remaining tile comes after the acquire
+    if (zmarch_ready(c) && c->zm_nrest > 0 && c->zm_rest) {
+        AB_TRY(launch_zmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag));
+        return launch_rowwin(c, x, y, dotvec, dot_result, partials, ticket, done_flag, c->zm_rest, c->zm_nrest, dotvec ? 1 : 0, &hw);
+    }
+    AB_TRY(launch_rowmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag));
     return launch_rowwin(c, x, y, dotvec, dot_result, partials, ticket, done_flag, c->rm_rest, c->rm_nrest, dotvec ? 1 : 0, &hw);
 }
 
@@ -1669,9 +2152,11 @@ static int launch_spmv_impl(const Csr* c, const double* vals, const double* x, d
             AB_TRY(csr_ensure_code(const_cast<Csr*>(c), vals));
             if (c->ncode > 0 && c->npat < 0) AB_TRY(csr_ensure_rowpat(const_cast<Csr*>(c)));
         }
-        if (rowwin_ready(c, vals, x) && !tile_list && !accumulate && c->rm_ok == 1 && c->rm_nrest == 0 && c->rm_plan &&
-            (!dotvec || partials) && opt("spmv_rowmarch", 1.0) != 0.0)
-            return launch_rowmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag);
+        if (rowwin_ready(c, vals, x) && !tile_list && !accumulate && c->rm_ok == 1 && c->rm_plan && (!dotvec || partials) &&
+            opt("spmv_rowmarch", 1.0) != 0.0) {
+            if (zmarch_ready(c) && c->zm_nrest == 0) return launch_zmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag);
+            if (c->rm_nrest == 0) return launch_rowmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag);
+        }
         if (rowwin_ready(c, vals, x) && (!tile_list || list_rows == RW_R))
             return launch_rowwin(c, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, accumulate, hwp);
         if (tile_list && list_rows == RW_R) return fail(AB_EINVAL, "tile list built for the x-window kernel, which is not available");
@@ -1725,6 +2210,9 @@ extern "C" int ab_csr_get_info(int64_t h, const char* key, double* value) {
     else if (!strcmp(key, "rowwin")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0) ? c->rw_ok : -1;
     else if (!strcmp(key, "rowmarch")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0 && c->rw_ok == 1) ? c->rm_ok : -1;
     else if (!strcmp(key, "rowmarch_items")) *value = c->rm_nitems;
+    else if (!strcmp(key, "zmarch")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0 && c->rw_ok == 1 && c->rm_ok == 1) ? c->zm_ok : -1;
+    else if (!strcmp(key, "zmarch_items")) *value = c->zm_nitems;
+    else if (!strcmp(key, "zmarch_g")) *value = c->zm_plan ? reinterpret_cast<const ab::ZMarchPlan*>(c->zm_plan)->G : 0;
     else if (!strcmp(key, "tile_rows")) *value = ab::spmv_tile_rows(c);
     else if (!strcmp(key, "max_row_nnz")) *value = c->max_row_nnz;
     else if (!strcmp(key, "scaled")) *value = (c->scaled_version == c->values_version && c->scaled_ok) ? 1 : 0;

@@ -245,6 +245,13 @@ def spmv_form(lib, h, nloc: int, nnz_loc: int):
         return int(info.value)
 
     ncode, noff, npat, rowwin = q(b"ncode"), q(b"noff"), q(b"npat"), q(b"rowwin")
+    if npat > 0 and rowwin == 1 and q(b"zmarch") == 1:
+        return {"kernel": f"spmv_zmarch_kernel<G={q(b'zmarch_g')}> (1 byte per ROW names its {{offset,value}} pattern; x windows of {q(b'zmarch_g')} x 1024 rows + "
+                          "margins streamed by TMA through a 4-slot mbarrier ring, planes -M/+M carried in registers along z-chains)",
+                "index_value_bytes": "1 per row", "streamed_bytes": 17.0 * nloc}
+    if npat > 0 and rowwin == 1 and q(b"rowmarch") == 1:
+        return {"kernel": "spmv_rowmarch_kernel (1 byte per ROW names its {offset,value} pattern; ring of x windows marched along z-chains, staged by TMA)",
+                "index_value_bytes": "1 per row", "streamed_bytes": 17.0 * nloc}
     if npat > 0 and rowwin == 1:
         return {"kernel": "spmv_rowwin_kernel (1 byte per ROW names its {offset,value} pattern; x intervals staged by TMA)",
                 "index_value_bytes": "1 per row", "streamed_bytes": 17.0 * nloc}

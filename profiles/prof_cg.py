@@ -16,6 +16,9 @@ import __graft_entry__ as ge  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 pkg = ge.load_package()
+for kv in filter(None, os.environ.get("AB_OPTS", "").split(",")):      # A/B switches, e.g. AB_OPTS=spmv_zmarch_g=2
+    k_, v_ = kv.split("=")
+    pkg.check(pkg.lib.ab_set_option(k_.strip().encode(), float(v_)))
 h = C.c_int64(0)
 pkg.check(pkg.lib.ab_poisson3d_csr(n, n, n, 0, n ** 3, C.byref(h)))
 A = pkg.SparseTensor.from_handle(h.value)

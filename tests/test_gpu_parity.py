@@ -670,13 +670,14 @@ def test_pattern_code_spmv_is_lossless(pkg):
     run-to-run deterministic."""
     import torch
 
-    # name -> (spmv_rowpat, spmv_code, spmv_off8, spmv_rowwin, spmv_rowmarch)
-    forms = (("rowmarch", 1.0, 1.0, 1.0, 1.0, 1.0), ("rowwin", 1.0, 1.0, 1.0, 1.0, 0.0), ("rowpat", 1.0, 1.0, 1.0, 0.0, 0.0),
-             ("code", 0.0, 1.0, 1.0, 0.0, 0.0), ("off8", 0.0, 0.0, 1.0, 0.0, 0.0), ("plain", 0.0, 0.0, 0.0, 0.0, 0.0))
-    keys = (b"spmv_rowpat", b"spmv_code", b"spmv_off8", b"spmv_rowwin", b"spmv_rowmarch")
+    # name -> (spmv_rowpat, spmv_code, spmv_off8, spmv_rowwin, spmv_rowmarch, spmv_zmarch)
+    forms = (("zmarch", 1.0, 1.0, 1.0, 1.0, 1.0, 1.0), ("rowmarch", 1.0, 1.0, 1.0, 1.0, 1.0, 0.0), ("rowwin", 1.0, 1.0, 1.0, 1.0, 0.0, 0.0),
+             ("rowpat", 1.0, 1.0, 1.0, 0.0, 0.0, 0.0), ("code", 0.0, 1.0, 1.0, 0.0, 0.0, 0.0), ("off8", 0.0, 0.0, 1.0, 0.0, 0.0, 0.0),
+             ("plain", 0.0, 0.0, 0.0, 0.0, 0.0, 0.0))
+    keys = (b"spmv_rowpat", b"spmv_code", b"spmv_off8", b"spmv_rowwin", b"spmv_rowmarch", b"spmv_zmarch")
 
-    def with_form(rowpat, code, off8, rowwin, rowmarch, fn):
-        for k, v in zip(keys, (rowpat, code, off8, rowwin, rowmarch)):
+    def with_form(rowpat, code, off8, rowwin, rowmarch, zmarch, fn):
+        for k, v in zip(keys, (rowpat, code, off8, rowwin, rowmarch, zmarch)):
             pkg.check(pkg.lib.ab_set_option(k, v))
         try:
             return fn()
@@ -684,7 +685,9 @@ def test_pattern_code_spmv_is_lossless(pkg):
             for k in keys:
                 pkg.check(pkg.lib.ab_set_option(k, 1.0))
 
-    for n in (48, 67, 64):                     # 67: tiles straddle planes, odd sizes; 64: n^2 is a multiple of the 1024-row tile -> marching kernel
+    # 67: tiles straddle planes, odd sizes; 64, 96, 128: n^2 is a multiple of the 1024-row tile -> marching kernels
+    # (z-register form with 4 / 1 / 4 tiles per chain position and 1 / 9 / 4 chains)
+    for n in (48, 67, 64, 96, 128):
         N = n ** 3
         h = C.c_int64(0)
         pkg.check(pkg.lib.ab_poisson3d_csr(n, n, n, 0, N, C.byref(h)))
@@ -704,26 +707,33 @@ def test_pattern_code_spmv_is_lossless(pkg):
             pkg.check(pkg.lib.ab_cg_fixed(A.handle(), f.data_ptr(), u.data_ptr(), 40, C.byref(rr)))
             return u
 
-        ys = {name: with_form(a, b, c, d, e, spmv) for name, a, b, c, d, e in forms}
+        ys = {name: with_form(a, b, c, d, e, g, spmv) for name, a, b, c, d, e, g in forms}
+        if n in (64, 96, 128):
+            zi = C.c_double(0)
+            pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"zmarch", C.byref(zi)))
+            assert zi.value == 1.0, "the z-register marching kernel should apply to this grid"
         pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin_dom", 0.0))                # every row walks its pattern out of the stage
         try:
-            ys["rowwin_generic"] = with_form(1.0, 1.0, 1.0, 1.0, 0.0, spmv)
-            ys["rowmarch_generic"] = with_form(1.0, 1.0, 1.0, 1.0, 1.0, spmv)
+            ys["rowwin_generic"] = with_form(1.0, 1.0, 1.0, 1.0, 0.0, 0.0, spmv)
+            ys["rowmarch_generic"] = with_form(1.0, 1.0, 1.0, 1.0, 1.0, 0.0, spmv)
+            ys["zmarch_generic"] = with_form(1.0, 1.0, 1.0, 1.0, 1.0, 1.0, spmv)
         finally:
             pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin_dom", 1.0))
         assert torch.equal(ys["rowwin_generic"], ys["plain"]) and torch.equal(ys["rowmarch_generic"], ys["plain"])
-        for name in ("rowmarch", "rowwin", "rowpat", "code", "off8"):
+        assert torch.equal(ys["zmarch_generic"], ys["plain"])
+        for name in ("zmarch", "rowmarch", "rowwin", "rowpat", "code", "off8"):
             assert torch.equal(ys[name], ys["plain"]), name                      # lossless: same bits
         S = A.to_scipy()
         dinv = 1.0 / np.sqrt(S.diagonal())
         y0 = dinv * (S @ (dinv * x.cpu().numpy()))
         assert np.max(np.abs(ys["plain"].cpu().numpy() - y0)) <= 1e-13 * np.max(np.abs(y0))
-        us = {name: with_form(a, b, c, d, e, cg) for name, a, b, c, d, e in forms}
-        for name in ("rowmarch", "rowwin", "rowpat", "code", "off8"):
+        us = {name: with_form(a, b, c, d, e, g, cg) for name, a, b, c, d, e, g in forms}
+        for name in ("zmarch", "rowmarch", "rowwin", "rowpat", "code", "off8"):
             assert float((us[name] - us["plain"]).abs().max() / us["plain"].abs().max()) <= 1e-11, name
-        assert torch.equal(with_form(1.0, 1.0, 1.0, 0.0, 0.0, cg), us["rowpat"])     # deterministic run to run
-        assert torch.equal(with_form(1.0, 1.0, 1.0, 1.0, 0.0, cg), us["rowwin"])
-        assert torch.equal(with_form(1.0, 1.0, 1.0, 1.0, 1.0, cg), us["rowmarch"])
+        assert torch.equal(with_form(1.0, 1.0, 1.0, 0.0, 0.0, 0.0, cg), us["rowpat"])     # deterministic run to run
+        assert torch.equal(with_form(1.0, 1.0, 1.0, 1.0, 0.0, 0.0, cg), us["rowwin"])
+        assert torch.equal(with_form(1.0, 1.0, 1.0, 1.0, 1.0, 0.0, cg), us["rowmarch"])
+        assert torch.equal(with_form(1.0, 1.0, 1.0, 1.0, 1.0, 1.0, cg), us["zmarch"])
         pkg.check(pkg.lib.ab_set_option(b"spmv_rowwin", 0.0))               # the cg_defer_x checks below compare with us["rowpat"]
         # the x update riding in K3 (10 vector passes) is the same arithmetic, only moved
         pkg.check(pkg.lib.ab_set_option(b"cg_defer_x", 0.0))
@@ -744,7 +754,7 @@ def test_pattern_code_spmv_is_lossless(pkg):
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"rowwin", C.byref(info)))
         assert info.value == 1                 # the x-window form was built for the stencil
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"rowmarch", C.byref(info)))
-        assert info.value == (1 if n == 64 else 0)      # chains need n^2 to be a multiple of the tile size
+        assert info.value == (1 if n in (64, 96, 128) else 0)      # chains need n^2 to be a multiple of the tile size
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"npat", C.byref(info)))
         assert info.value == 27                # interior + face / edge / corner variants of the 7-point stencil
         pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"ncode", C.byref(info)))
