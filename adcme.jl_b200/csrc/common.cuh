@@ -171,6 +171,7 @@ struct Csr {
     int64_t   zm_nrest = 0;        // 1024-row tiles no item covers
     int32_t*  zm_rest = nullptr;   // [zm_nrest] those tiles, ascending
     int       zm_ok = 0;
+    uint8_t*  zm_rowmask = nullptr; // [m + pad] zm_mask[rowcode[r]]: the byte stream the kernel stages when the dominant pattern is in its parameters
     uint8_t*  zm_mask = nullptr;   // [256] per pattern: which entries of the dominant pattern it keeps (0x80: walk the table)
     uint8_t*  rw_exclude = nullptr;  // [ceil(m/1024)] optional (dist.cu): tiles that must not join a chain (they read halo columns)
     // triplet bookkeeping (null when the handle was created from CSR: identity map)

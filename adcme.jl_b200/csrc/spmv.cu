@@ -1218,8 +1218,8 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
 // the kernel parameters; CK: position of the diagonal (centre, plane 0) inside it, -1 if it has none.
 template <int G, int K, int CK>
 __global__ void __launch_bounds__(ZM_THREADS, 1)
-spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restrict__ rowcode, const int4* __restrict__ ent,
-                   int nent, const uint32_t* __restrict__ pinfo, const uint8_t* __restrict__ pmask, const double* __restrict__ x, long long xlen,
+spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restrict__ rowcode, const uint8_t* __restrict__ rowpat,
+                   const int4* __restrict__ ent, int nent, const uint32_t* __restrict__ pinfo, const double* __restrict__ x, long long xlen,
                    double* __restrict__ y, unsigned m, const int32_t* __restrict__ item_first,
                    const int32_t* __restrict__ item_count, unsigned nitems, const double* __restrict__ dotvec,
                    int dot_in_window, double* partials, uint32_t* ticket, double* dot_result,
@@ -1236,12 +1236,11 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
     uint32_t* s_info = reinterpret_cast<uint32_t*>(s_ent + nent);                              // [256]
     __shared__ alignas(8) uint64_t full[ZM_NB_MAX], empty[ZM_NB_MAX];
     __shared__ double s_red[32];
-    __shared__ uint8_t s_mask[256];
     __shared__ bool s_last;
     if (done && *done) return;
     const unsigned t = threadIdx.x;
     for (int i = t; i < nent; i += ZM_THREADS) s_ent[i] = ent[i];
-    for (int i = t; i < 256; i += ZM_THREADS) { s_info[i] = pinfo[i]; s_mask[i] = pmask[i]; }
+    for (int i = t; i < 256; i += ZM_THREADS) s_info[i] = pinfo[i];
     if (t == 0) {
 #pragma unroll
         for (int b = 0; b < ZM_NB_MAX; ++b) { abd::mbar_init(&full[b], P.tma ? 1 : 32 * ZM_NPW); abd::mbar_init(&empty[b], ZM_NT / 32); }
@@ -1337,76 +1336,91 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
                     // offsets, same values) runs the same code with those FMAs predicated off by its mask — so the two lanes
                     // of every line that sit on the x-boundary do not send their warps through the table walk 2 * RPT times
                     // per position (measured: those warps were the critical path of the whole CTA).  Operands of masked-off
-                    // entries are still loaded: they lie inside the ring slot whatever the row.  Bit 7 of the mask: the
-                    // pattern is something else and is walked from its table.
+                    // entries are still loaded: they lie inside the ring slot whatever the row.  The byte stream staged with
+                    // the window holds these masks (K > 0: `rowcode` is the per-row mask array); bit 7: the pattern is
+                    // something else — its id comes from `rowpat` and it is walked from its table.
                     constexpr int JB = RPT > 4 ? 4 : RPT;          // rows in flight per thread (register budget: 96)
                     constexpr unsigned FULL = (1u << K) - 1u;
+                    const double* pe[K > 2 ? K - 2 : 1];             // plane-0 operands of the dominant pattern, this position
+#pragma unroll
+                    for (int e = 1; e < K - 1; ++e) pe[e - 1] = wc + P.dsoff[e];
+                    const int dmode = !dotvec ? 0 : (dot_in_window ? 1 : 2);
 #pragma unroll
                     for (int jb = 0; jb < RPT; jb += JB) {
-                    double nx[JB], acc[JB];
-                    unsigned mk[JB];
-                    bool allfull = true;
+                        double nx[JB], acc[JB];
+                        unsigned mk[JB];
+                        bool allfull = true;
 #pragma unroll
-                    for (int j = 0; j < JB; ++j) { nx[j] = wn[(jb + j) * ZM_NT]; mk[j] = codes[(jb + j) * ZM_NT]; }
+                        for (int j = 0; j < JB; ++j) { nx[j] = wn[(jb + j) * ZM_NT]; mk[j] = codes[(jb + j) * ZM_NT]; }
 #pragma unroll
-                    for (int j = 0; j < JB; ++j) { mk[j] = s_mask[mk[j]] | (mk[j] << 8); allfull = allfull && (mk[j] & 0xffu) == FULL; }
-                    if (__all_sync(0xffffffffu, allfull)) {
+                        for (int j = 0; j < JB; ++j) allfull = allfull && mk[j] == FULL;
+                        if (__all_sync(0xffffffffu, allfull)) {
 #pragma unroll
-                        for (int j = 0; j < JB; ++j) acc[j] = fma(P.dval[0], prv[jb + j], 0.0);
+                            for (int j = 0; j < JB; ++j) acc[j] = fma(P.dval[0], prv[jb + j], 0.0);
 #pragma unroll
-                        for (int e = 1; e < K - 1; ++e) {
+                            for (int e = 1; e < K - 1; ++e) {
 #pragma unroll
-                            for (int j = 0; j < JB; ++j) {
-                                const double xk = (e == CK) ? cur[jb + j] : wc[P.dsoff[e] + (jb + j) * ZM_NT];
-                                acc[j] = fma(P.dval[e], xk, acc[j]);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < JB; ++j) acc[j] = fma(P.dval[K > 0 ? K - 1 : 0], nx[j], acc[j]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < JB; ++j) acc[j] = (mk[j] & 1u) ? fma(P.dval[0], prv[jb + j], 0.0) : 0.0;
-#pragma unroll
-                        for (int e = 1; e < K - 1; ++e) {
-#pragma unroll
-                            for (int j = 0; j < JB; ++j) {
-                                const double xk = (e == CK) ? cur[jb + j] : wc[P.dsoff[e] + (jb + j) * ZM_NT];
-                                if ((mk[j] >> e) & 1u) acc[j] = fma(P.dval[e], xk, acc[j]);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < JB; ++j)
-                            if ((mk[j] >> (K > 0 ? K - 1 : 0)) & 1u) acc[j] = fma(P.dval[K > 0 ? K - 1 : 0], nx[j], acc[j]);
-#pragma unroll
-                        for (int j = 0; j < JB; ++j) {
-                            if (mk[j] & 0x80u) {
-                                const uint32_t info = s_info[mk[j] >> 8];
-                                const int4* e = s_ent + (info & 0xffffu);
-                                const int elen = (int)(info >> 16);
-                                double a = 0.0;
-                                for (int q = 0; q < elen; ++q) {
-                                    const int4 qe = e[q];
-                                    const double xv = qe.w == 0 ? wc[qe.z + (jb + j) * ZM_NT] : (qe.w < 0 ? prv[jb + j] : nx[j]);
-                                    a = fma(__hiloint2double(qe.y, qe.x), xv, a);
+                                for (int j = 0; j < JB; ++j) {
+                                    const double xk = (e == CK) ? cur[jb + j] : pe[e - 1][(jb + j) * ZM_NT];
+                                    acc[j] = fma(P.dval[e], xk, acc[j]);
                                 }
-                                acc[j] = a;
+                            }
+#pragma unroll
+                            for (int j = 0; j < JB; ++j) acc[j] = fma(P.dval[K > 0 ? K - 1 : 0], nx[j], acc[j]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < JB; ++j) acc[j] = (mk[j] & 1u) ? fma(P.dval[0], prv[jb + j], 0.0) : 0.0;
+#pragma unroll
+                            for (int e = 1; e < K - 1; ++e) {
+#pragma unroll
+                                for (int j = 0; j < JB; ++j) {
+                                    const double xk = (e == CK) ? cur[jb + j] : pe[e - 1][(jb + j) * ZM_NT];
+                                    if ((mk[j] >> e) & 1u) acc[j] = fma(P.dval[e], xk, acc[j]);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < JB; ++j)
+                                if ((mk[j] >> (K > 0 ? K - 1 : 0)) & 1u) acc[j] = fma(P.dval[K > 0 ? K - 1 : 0], nx[j], acc[j]);
+#pragma unroll
+                            for (int j = 0; j < JB; ++j) {
+                                const unsigned tl = t + (unsigned)(jb + j) * ZM_NT;
+                                if ((mk[j] & 0x80u) && tl < nr) {
+                                    const uint32_t info = s_info[rowpat[r0 + tl]];
+                                    const int4* e = s_ent + (info & 0xffffu);
+                                    const int elen = (int)(info >> 16);
+                                    double a = 0.0;
+                                    for (int q = 0; q < elen; ++q) {
+                                        const int4 qe = e[q];
+                                        const double xv = qe.w == 0 ? wc[qe.z + (jb + j) * ZM_NT] : (qe.w < 0 ? prv[jb + j] : nx[j]);
+                                        a = fma(__hiloint2double(qe.y, qe.x), xv, a);
+                                    }
+                                    acc[j] = a;
+                                }
                             }
                         }
-                    }
+                        if (nr == (unsigned)TR && dmode == 1) {
 #pragma unroll
-                    for (int j = 0; j < JB; ++j) {
-                        const unsigned tl = t + (unsigned)(jb + j) * ZM_NT;
-                        if (tl < nr) {
-                            y[r0 + tl] = acc[j];
-                            if (dotvec) {
-                                const double wv = dot_in_window ? cur[jb + j] : dotvec[r0 + tl];
-                                dot  = fma(acc[j], wv, dot);
+                            for (int j = 0; j < JB; ++j) {
+                                y[r0 + t + (unsigned)(jb + j) * ZM_NT] = acc[j];
+                                dot  = fma(acc[j], cur[jb + j], dot);
                                 dot2 = fma(acc[j], acc[j], dot2);
                             }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < JB; ++j) {
+                                const unsigned tl = t + (unsigned)(jb + j) * ZM_NT;
+                                if (tl < nr) {
+                                    y[r0 + tl] = acc[j];
+                                    if (dmode) {
+                                        const double wv = dmode == 1 ? cur[jb + j] : dotvec[r0 + tl];
+                                        dot  = fma(acc[j], wv, dot);
+                                        dot2 = fma(acc[j], acc[j], dot2);
+                                    }
+                                }
+                            }
                         }
-                        prv[jb + j] = cur[jb + j];
-                        cur[jb + j] = nx[j];
-                    }
+#pragma unroll
+                        for (int j = 0; j < JB; ++j) { prv[jb + j] = cur[jb + j]; cur[jb + j] = nx[j]; }
                     }
                 } else {
 #pragma unroll
@@ -1477,6 +1491,15 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
             }
         }
     }
+}
+
+// rowmask[r] = pmask[rowcode[r]]
+__global__ void __launch_bounds__(256)
+rowmask_kernel(const uint8_t* __restrict__ rowcode, int64_t m, const uint8_t* __restrict__ pmask, uint8_t* __restrict__ rowmask) {
+    __shared__ uint8_t s_pm[256];
+    s_pm[threadIdx.x] = pmask[threadIdx.x];
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < m; r += (int64_t)gridDim.x * 256) rowmask[r] = s_pm[rowcode[r]];
 }
 
 // rows per pattern (dominant pattern = argmax)
@@ -1776,6 +1799,16 @@ static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<Mar
     }
     if (!c->zm_mask) AB_TRY(dev_alloc((void**)&c->zm_mask, 256));
     AB_CUDA(cudaMemcpyAsync(c->zm_mask, pmask.data(), 256, cudaMemcpyHostToDevice, stream()));
+    if (Z.dom >= 0) {
+        // the per-row mask stream the kernel stages instead of the pattern ids (same 1 byte per row)
+        if (!c->zm_rowmask) {
+            AB_TRY(dev_alloc((void**)&c->zm_rowmask, (size_t)c->m + RW_PAD));
+            AB_CUDA(cudaMemsetAsync(c->zm_rowmask + c->m, 0, RW_PAD, stream()));
+        }
+        int64_t nblk = (c->m + 255) / 256, cap = (int64_t)sm_count() * 16;
+        rowmask_kernel<<<(unsigned)(nblk < cap ? nblk : cap), 256, 0, stream()>>>(c->rowcode, c->m, c->zm_mask, c->zm_rowmask);
+        AB_LAUNCH_CHECK();
+    }
     AB_CUDA(cudaStreamSynchronize(stream()));
     // ---- chain positions that only touch the three marching intervals
     const int ns = Z.nsuper, Sp = Z.S;
@@ -1997,7 +2030,8 @@ static int launch_zmarch(const Csr* c, const double* x, double* y, const double*
             AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZM_SMEM_MAX));               \
             smem_set = ZM_SMEM_MAX;                                                                                           \
         }                                                                                                                     \
-        kern<<<grid, ZM_THREADS, smem, stream()>>>(P, c->rowcode, (const int4*)c->rm_ent, c->npat_ent, c->pat_info, c->zm_mask, x, \
+        kern<<<grid, ZM_THREADS, smem, stream()>>>(P, (KK) > 0 ? c->zm_rowmask : c->rowcode, c->rowcode, (const int4*)c->rm_ent,  \
+                                                   c->npat_ent, c->pat_info, x,                                               \
                                                    (long long)c->n, y, (unsigned)c->m, c->zm_items, c->zm_items + nitems,    \
                                                    nitems, dotvec, dot_in_window, partials, ticket, dot_result, done_flag);  \
     } while (0)
