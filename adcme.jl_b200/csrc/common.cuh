@@ -168,6 +168,8 @@ struct Csr {
     void*     zm_plan  = nullptr;  // host copy of the z-register marching plan (spmv.cu ZMarchPlan)
     int32_t*  zm_items = nullptr;  // [2 * zm_nitems]: first chain position (group of G tiles) of each work item, then its length
     int       zm_nitems = 0;
+    int32_t*  zm_cta_first = nullptr; // [zm_ncta + 1] balanced partition: CTA b runs items [zm_cta_first[b], zm_cta_first[b+1]) (null: round-robin)
+    int       zm_ncta = 0;
     int64_t   zm_nrest = 0;        // 1024-row tiles no item covers
     int32_t*  zm_rest = nullptr;   // [zm_nrest] those tiles, ascending
     int       zm_ok = 0;

@@ -127,6 +127,9 @@ struct DistCsr {
     uint64_t th_version = 0;
     uint64_t sym_version = 0;                // values_version the symmetry verdict belongs to (0: none)
     bool     is_sym = false;
+    // send lists that are contiguous runs of rows (slab partitions): K3 can push the halos while it sweeps (-1: not checked)
+    int      sr_ok = -1;
+    struct SendRanges { int n; int peer[4]; long long lo[4], hi[4]; } sr = {};
     ~DistCsr() {
         delete loc;
         dev_free(ext_glob);
@@ -246,6 +249,76 @@ halo_push_kernel(const int32_t* __restrict__ send_idx, const double* __restrict_
         if (threadIdx.x == 0) my_blk->ticket = 0;
         if ((int)threadIdx.x < world && send_cnt[threadIdx.x] > 0)
             st_release_sys(&peer_blk[threadIdx.x]->halo_flag[me], seq);
+    }
+}
+
+// K3 of the default path (scalars already all-reduced by p2p_allreduce2_kernel): x += alpha p_old, p = r + beta p, and the new
+// p of the rows a peer needs goes straight into that peer's halo tail while the grid-stride sweep passes over them (the send
+// lists are contiguous runs of rows: sr).  The last CTA then publishes halo_seq, so the next SpMV needs no halo_push_kernel
+// launch.  Same `done` / `iters` logic as cgs_direction_kernel; nothing is pushed when p is not updated (the SpMV launches
+// that follow exit on the same `done` flag before they would wait for it).
+__global__ void __launch_bounds__(EW_THREADS)
+cgs_direction_halo_kernel(const double* __restrict__ r, double* __restrict__ p, double* __restrict__ x, size_t n, int parity, int it,
+                          int defer_x, const SolveScal* __restrict__ s, DistCsr::SendRanges sr, double* const* __restrict__ peer_x,
+                          P2PBlock* const* __restrict__ peer_blk, P2PBlock* my_blk, int me, uint32_t halo_seq) {
+    __shared__ bool s_last;
+    const bool upd_x = defer_x && (s->iters == it + 1);
+    const bool upd_p = !s->done;
+    if (!upd_x && !upd_p) return;
+    const double alpha = s->alpha;
+    const double beta = upd_p ? s->rz[parity ^ 1] / s->rz[parity] : 0.0;
+    const size_t n2 = n >> 1;
+    const double2* r2 = reinterpret_cast<const double2*>(r);
+    double2* p2 = reinterpret_cast<double2*>(p);
+    double2* x2 = reinterpret_cast<double2*>(x);
+    if (!upd_p) {
+        for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+            double2 pv = p2[i], xv = x2[i];
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            x2[i] = xv;
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) x[n - 1] = fma(alpha, p[n - 1], x[n - 1]);
+        return;
+    }
+    auto push = [&](long long row, double v) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q < sr.n && row >= sr.lo[q] && row < sr.hi[q]) peer_x[sr.peer[q]][row - sr.lo[q]] = v;
+    };
+    for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+        double2 rv = r2[i], pv = p2[i];
+        if (upd_x) {
+            double2 xv = x2[i];
+            xv.x = fma(alpha, pv.x, xv.x); xv.y = fma(alpha, pv.y, xv.y);
+            x2[i] = xv;
+        }
+        pv.x = fma(beta, pv.x, rv.x);  pv.y = fma(beta, pv.y, rv.y);
+        p2[i] = pv;
+        const long long row = (long long)(2 * i);
+        bool near = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) near = near || (q < sr.n && row + 1 >= sr.lo[q] && row < sr.hi[q]);
+        if (near) { push(row, pv.x); push(row + 1, pv.y); }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const size_t i = n - 1;
+        const double pv = p[i];
+        if (upd_x) x[i] = fma(alpha, pv, x[i]);
+        const double pn = fma(beta, pv, r[i]);
+        p[i] = pn;
+        push((long long)i, pn);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&my_blk->ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x == 0) my_blk->ticket = 0;
+        if ((int)threadIdx.x < sr.n) st_release_sys(&peer_blk[sr.peer[threadIdx.x]]->halo_flag[me], halo_seq);
     }
 }
 
@@ -644,6 +717,27 @@ static int dist_ensure_scaled(DistCsr* d) {
     return AB_OK;
 }
 
+// are this rank's send lists contiguous runs of rows (at most four peers)?  Cached in d->sr_ok / d->sr.
+static int dist_check_send_ranges(DistCsr* d) {
+    if (d->sr_ok >= 0) return AB_OK;
+    d->sr_ok = 0;
+    d->sr.n = 0;
+    if (g_world == 1 || !d->p2p || d->nsend == 0) return AB_OK;
+    std::vector<int32_t> h((size_t)d->nsend);
+    AB_CUDA(cudaMemcpyAsync(h.data(), d->send_idx, (size_t)d->nsend * sizeof(int32_t), cudaMemcpyDeviceToHost, stream()));
+    AB_CUDA(cudaStreamSynchronize(stream()));
+    for (int p = 0; p < g_world; ++p) {
+        const int cnt = d->send_cnt[p], off = d->send_off[p];
+        if (cnt == 0) continue;
+        if (d->sr.n == 4) { d->sr.n = 0; return AB_OK; }
+        for (int k = 1; k < cnt; ++k) if (h[off + k] != h[off] + k) { d->sr.n = 0; return AB_OK; }
+        d->sr.peer[d->sr.n] = p; d->sr.lo[d->sr.n] = h[off]; d->sr.hi[d->sr.n] = (long long)h[off] + cnt;
+        ++d->sr.n;
+    }
+    d->sr_ok = d->sr.n > 0 ? 1 : 0;
+    return AB_OK;
+}
+
 // CG over the row-block partition.  b, x: local device vectors of length nloc.  tol < 0: fixed count.
 static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int maxit, SolveScal* fin) {
     Csr* c = d->loc;
@@ -669,11 +763,16 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
     const int defer_x = opt("cg_defer_x", 1.0) != 0.0 ? 1 : 0;   // x += alpha p rides in K3 (cg_kernels.cuh)
     int it = 0;
     SolveScal h;
-    const bool fuse_opt = opt("dist_fused_reduce", g_world <= 2 ? 1.0 : 0.0) != 0.0;
+    // measured (profiles/bench_n2_r02j_*, bench_n8_r02h_*): separate all-reduce launches win at every N once K3 pushes the
+    // halos itself (N=2: 1066 vs 1058 it/s, N=8: 3192 vs 3027) — folded-in reductions are an option, not the default
+    const bool fuse_opt = opt("dist_fused_reduce", 0.0) != 0.0;
     // measured at 512^3, N=2 (profiles/bench_n2_r02c_*.log): 927 it/s without the folded-in halo push, 769 with it — the
     // contiguous per-CTA chunks its push needs cost K3'' more bandwidth than the saved launch returns.  Default: off.
     const bool push_opt = opt("dist_fused_push", 0.0) != 0.0;
     bool halo_pushed = false;     // the previous iteration's K3'' already pushed the halos of the coming SpMV
+    // K3 that pushes the halos of the next SpMV while it sweeps (default path; needs contiguous send runs)
+    bool k3_halo = raw && scaled && d->p2p && d->next > 0 && opt("dist_k3_halo", 1.0) != 0.0;
+    if (k3_halo) { AB_TRY(dist_check_send_ranges(d)); k3_halo = d->sr_ok == 1; }
     while (it < maxit) {
         int chunk = maxit - it < check ? maxit - it : check;
         for (int k = 0; k < chunk; ++k, ++it) {
@@ -710,7 +809,12 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
             else cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, raw);
             AB_LAUNCH_CHECK();
             if (raw) AB_TRY(allreduce2_fin(d, s, 1, parity, tol));
-            if (scaled) cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, it, defer_x, s);
+            if (scaled && k3_halo) {
+                ++d->halo_seq;
+                cgs_direction_halo_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, it, defer_x, s, d->sr, d->d_peer_x,
+                                                                          d->d_peer_blk, d->blk, g_rank, d->halo_seq);
+                halo_pushed = true;
+            } else if (scaled) cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, it, defer_x, s);
             else cg_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, c->dinv, p, n, parity, s);
             AB_LAUNCH_CHECK();
         }

@@ -1221,9 +1221,9 @@ __global__ void __launch_bounds__(ZM_THREADS, 1)
 spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restrict__ rowcode, const uint8_t* __restrict__ rowpat,
                    const int4* __restrict__ ent, int nent, const uint32_t* __restrict__ pinfo, const double* __restrict__ x, long long xlen,
                    double* __restrict__ y, unsigned m, const int32_t* __restrict__ item_first,
-                   const int32_t* __restrict__ item_count, unsigned nitems, const double* __restrict__ dotvec,
-                   int dot_in_window, double* partials, uint32_t* ticket, double* dot_result,
-                   const int* __restrict__ done) {
+                   const int32_t* __restrict__ item_count, unsigned nitems, const int32_t* __restrict__ cta_first,
+                   const double* __restrict__ dotvec, int dot_in_window, double* partials, uint32_t* ticket,
+                   double* dot_result, const int* __restrict__ done) {
     constexpr int TR = G * RW_R;
     constexpr int RPT = TR / ZM_NT;
     extern __shared__ __align__(128) unsigned char zm_smem[];
@@ -1239,6 +1239,10 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
     __shared__ bool s_last;
     if (done && *done) return;
     const unsigned t = threadIdx.x;
+    // items of this CTA: every gridDim.x-th one, or (balanced partition) the contiguous run cta_first names
+    const unsigned ibeg = cta_first ? (unsigned)cta_first[blockIdx.x] : blockIdx.x;
+    const unsigned iend = cta_first ? (unsigned)cta_first[blockIdx.x + 1] : nitems;
+    const unsigned istep = cta_first ? 1u : gridDim.x;
     for (int i = t; i < nent; i += ZM_THREADS) s_ent[i] = ent[i];
     for (int i = t; i < 256; i += ZM_THREADS) s_info[i] = pinfo[i];
     if (t == 0) {
@@ -1258,7 +1262,7 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
         const bool tma = P.tma != 0;
         if (!tma || pt == 0) {
             unsigned cnt = 0;
-            for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+            for (unsigned item = ibeg; item < iend; item += istep) {
                 const int first = item_first[item], L = item_count[item];
                 for (int q = 0; q < L + 2; ++q, ++cnt) {
                     const unsigned slot = cnt & NBM, use = cnt >> nbsh;
@@ -1305,7 +1309,7 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[c & NBM]);
         };
-        for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+        for (unsigned item = ibeg; item < iend; item += istep) {
             const int first = item_first[item], L = item_count[item];
             double dot = 0.0, dot2 = 0.0;
             double prv[RPT], cur[RPT];
@@ -1753,12 +1757,40 @@ static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<Mar
     }
     const int margins = Q.len - RW_R;
     auto smem_for = [&](int g, int nb) { return (size_t)nb * (margins + g * RW_R) * 8 + (size_t)nb * g * RW_R + ment.size() * 16 + 1024; };
-    int G = 0;
-    for (int g = 4; g >= 1 && !G; g >>= 1)
-        if (Q.S % g == 0 && smem_for(g, 4) <= ZM_SMEM_MAX) G = g;
-    const int gopt = (int)opt("spmv_zmarch_g", 0.0);
-    if (gopt == 1 || gopt == 2) { if (G >= gopt && Q.S % gopt == 0) G = gopt; }
+    // ---- how the chains are cut: G tiles per position, and either equal segments handed out round-robin (all chains of a
+    // z-range run together, so the margins a position shares with its neighbours are L2 hits) or, when the operand is about
+    // L2-sized anyway, a balanced partition of the (chain, z) order into one contiguous run per SM.  Costs are in rows per CTA;
+    // the penalties for narrower positions are measured (512^3: G = 4 / 2 / 1 -> 0.440 / 0.445 / 0.61 ms).
+    const int grid = sm_count();
+    const bool fits_l2 = (double)c->n * 8.0 <= 160e6;
+    int G = 0, bestL = 0, balanced = 0;
+    double bestc = 1e300;
+    const int gopt = (int)opt("spmv_zmarch_g", 0.0), lopt = (int)opt("spmv_zmarch_len", 0.0), bopt = (int)opt("spmv_zmarch_balanced", -1.0);
+    for (int g = 4; g >= 1; g >>= 1) {
+        if (Q.S % g || smem_for(g, 4) > ZM_SMEM_MAX) continue;
+        if (gopt > 0 && g != gopt) continue;
+        if (gopt <= 0 && g == 1 && G) continue;                    // single tiles only when nothing wider applies
+        const double pen = g == 4 ? 1.0 : (g == 2 ? 1.015 : 1.35);
+        const long long Spg = Q.S / g, nsg = (Q.ntiles + g - 1) / g, Zcg = (nsg + Spg - 1) / Spg;
+        const double rows = (double)g * RW_R;
+        for (int nseg = 1; nseg <= Zcg && nseg <= 256; ++nseg) {
+            const int Ls = (int)((Zcg + nseg - 1) / nseg);
+            if (nseg > 1 && (Zcg + nseg - 2) / (nseg - 1) == Ls) continue;      // same length as the previous candidate
+            if (lopt > 0 && Ls != lopt && nseg < Zcg) continue;
+            const long long nit = Spg * ((Zcg + Ls - 1) / Ls);
+            if (nit > 16000) break;
+            const long long rounds = (nit + grid - 1) / grid;
+            const double cost = ((double)rounds * (Ls + 2) + 0.25 * (double)nit * (Ls + 2) / grid) * rows * pen / 1.25;
+            if (bopt != 1 && cost < bestc) { bestc = cost; G = g; bestL = Ls; balanced = 0; }
+        }
+        if (bopt != 0) {
+            const double per = (double)(Spg * Zcg) / grid;
+            const double cost = (per + 3.0) * rows * pen * (fits_l2 ? 1.0 : 1.12);
+            if (bopt == 1 ? (cost < bestc || !balanced) : cost < 0.95 * bestc) { bestc = cost; G = g; bestL = 0; balanced = 1; }
+        }
+    }
     if (!G) return AB_OK;
+    if (lopt > 0 && !balanced) bestL = lopt;
     int NB = smem_for(G, 8) <= ZM_SMEM_MAX ? 8 : 4;
     const int nbopt = (int)opt("spmv_zmarch_nb", 0.0);
     if (nbopt == 4) NB = 4;
@@ -1820,42 +1852,62 @@ static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<Mar
         pure[u] = ok;
     }
     const int Zc = (ns + Sp - 1) / Sp;                 // chain length
-    // segment length: rounds x (L + 2 windows per item), plus a quarter of the total window count (traffic)
-    const int grid = sm_count();
-    int bestL = Zc; double bestc = 1e300;
-    for (int nseg = 1; nseg <= Zc && nseg <= 256; ++nseg) {
-        const int Ls = (Zc + nseg - 1) / nseg;
-        if (nseg > 1 && (Zc + nseg - 2) / (nseg - 1) == Ls) continue;      // same length as the previous candidate
-        const long long nit = (long long)Sp * ((Zc + Ls - 1) / Ls);
-        if (nit > 16000) break;
-        const long long rounds = (nit + grid - 1) / grid;
-        const double cost = (double)rounds * (Ls + 2) + 0.25 * (double)nit * (Ls + 2) / grid;
-        if (cost < bestc) { bestc = cost; bestL = Ls; }
-    }
-    const int lopt = (int)opt("spmv_zmarch_len", 0.0);
-    if (lopt > 0) bestL = lopt;
-    std::vector<int32_t> first, count;
-    for (int z0 = 0; z0 < Zc; z0 += bestL)
+    std::vector<int32_t> first, count, cta_first;
+    auto cover = [&](int start, int run) {
+        for (int q = 0; q < run; ++q)
+            for (int i = 0; i < G; ++i) { const long long tt = ((long long)start + (long long)q * Sp) * G + i; if (tt < ntiles) covered[tt] = 1; }
+    };
+    if (!balanced) {
+        for (int z0 = 0; z0 < Zc; z0 += bestL)
+            for (int tI = 0; tI < Sp; ++tI) {
+                int run = 0, start = 0;
+                for (int z = z0; z < Zc && z < z0 + bestL; ++z) {
+                    const long long u = (long long)z * Sp + tI;
+                    const bool ok = u < ns && pure[u];
+                    if (ok) { if (run == 0) start = (int)u; ++run; }
+                    if ((!ok || z + 1 == Zc || z + 1 == z0 + bestL) && run) { first.push_back(start); count.push_back(run); cover(start, run); run = 0; }
+                }
+            }
+    } else {
+        // runs of consecutive pure positions in (chain, z) order, cut into `nc` shares of equal length
+        std::vector<int32_t> rs, rl;
+        long long W = 0;
         for (int tI = 0; tI < Sp; ++tI) {
             int run = 0, start = 0;
-            for (int z = z0; z < Zc && z < z0 + bestL; ++z) {
+            for (int z = 0; z < Zc; ++z) {
                 const long long u = (long long)z * Sp + tI;
                 const bool ok = u < ns && pure[u];
                 if (ok) { if (run == 0) start = (int)u; ++run; }
-                if ((!ok || z + 1 == Zc || z + 1 == z0 + bestL) && run) {
-                    first.push_back(start); count.push_back(run);
-                    for (int q = 0; q < run; ++q)
-                        for (int i = 0; i < G; ++i) { const long long tt = ((long long)start + (long long)q * Sp) * G + i; if (tt < ntiles) covered[tt] = 1; }
-                    run = 0;
-                }
+                if ((!ok || z + 1 == Zc) && run) { rs.push_back(start); rl.push_back(run); W += run; cover(start, run); run = 0; }
             }
         }
+        const long long nc = W < grid ? W : grid;
+        size_t ri = 0; int used = 0;                       // position inside run ri
+        for (long long b = 0; b < nc; ++b) {
+            cta_first.push_back((int32_t)first.size());
+            long long want = (b + 1) * W / nc - b * W / nc;
+            while (want > 0 && ri < rs.size()) {
+                const int take = (int)std::min<long long>(want, rl[ri] - used);
+                first.push_back(rs[ri] + used * Sp); count.push_back(take);
+                used += take; want -= take;
+                if (used == rl[ri]) { ++ri; used = 0; }
+            }
+        }
+        cta_first.push_back((int32_t)first.size());
+    }
     const int nitems = (int)first.size();
     if (nitems == 0 || nitems > 16000) return AB_OK;
     std::vector<int32_t> rest;
     for (int tI = 0; tI < ntiles; ++tI) if (!covered[tI]) rest.push_back(tI);
     dev_free(c->zm_items); c->zm_items = nullptr;
     dev_free(c->zm_rest); c->zm_rest = nullptr;
+    dev_free(c->zm_cta_first); c->zm_cta_first = nullptr;
+    c->zm_ncta = 0;
+    if (!cta_first.empty()) {
+        AB_TRY(dev_alloc((void**)&c->zm_cta_first, cta_first.size() * sizeof(int32_t)));
+        AB_CUDA(cudaMemcpyAsync(c->zm_cta_first, cta_first.data(), cta_first.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+        c->zm_ncta = (int)cta_first.size() - 1;
+    }
     AB_TRY(dev_alloc((void**)&c->zm_items, (size_t)2 * nitems * sizeof(int32_t)));
     AB_CUDA(cudaMemcpyAsync(c->zm_items, first.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
     AB_CUDA(cudaMemcpyAsync(c->zm_items + nitems, count.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
@@ -2022,6 +2074,7 @@ static int launch_zmarch(const Csr* c, const double* x, double* y, const double*
     const unsigned nitems = (unsigned)c->zm_nitems;
     unsigned grid = (unsigned)sm_count();
     if (grid > nitems) grid = nitems;
+    if (c->zm_cta_first) grid = (unsigned)c->zm_ncta;
 #define AB_ZM(GG, KK, CC)                                                                                                     \
     do {                                                                                                                      \
         auto kern = spmv_zmarch_kernel<GG, KK, CC>;                                                                           \
@@ -2033,7 +2086,8 @@ static int launch_zmarch(const Csr* c, const double* x, double* y, const double*
         kern<<<grid, ZM_THREADS, smem, stream()>>>(P, (KK) > 0 ? c->zm_rowmask : c->rowcode, c->rowcode, (const int4*)c->rm_ent,  \
                                                    c->npat_ent, c->pat_info, x,                                               \
                                                    (long long)c->n, y, (unsigned)c->m, c->zm_items, c->zm_items + nitems,    \
-                                                   nitems, dotvec, dot_in_window, partials, ticket, dot_result, done_flag);  \
+                                                   nitems, c->zm_cta_first, dotvec, dot_in_window, partials, ticket,         \
+                                                   dot_result, done_flag);                                                   \
     } while (0)
 #define AB_ZMG(KK, CC) do { if (P.G == 4) AB_ZM(4, KK, CC); else if (P.G == 2) AB_ZM(2, KK, CC); else AB_ZM(1, KK, CC); } while (0)
     if (fast && P.dk == 7 && ck == 3) AB_ZMG(7, 3);
@@ -2246,6 +2300,7 @@ extern "C" int ab_csr_get_info(int64_t h, const char* key, double* value) {
     else if (!strcmp(key, "rowmarch_items")) *value = c->rm_nitems;
     else if (!strcmp(key, "zmarch")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0 && c->rw_ok == 1 && c->rm_ok == 1) ? c->zm_ok : -1;
     else if (!strcmp(key, "zmarch_items")) *value = c->zm_nitems;
+    else if (!strcmp(key, "zmarch_balanced")) *value = c->zm_cta_first ? 1 : 0;
     else if (!strcmp(key, "zmarch_g")) *value = c->zm_plan ? reinterpret_cast<const ab::ZMarchPlan*>(c->zm_plan)->G : 0;
     else if (!strcmp(key, "tile_rows")) *value = ab::spmv_tile_rows(c);
     else if (!strcmp(key, "max_row_nnz")) *value = c->max_row_nnz;
