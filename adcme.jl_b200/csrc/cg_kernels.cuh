@@ -29,7 +29,10 @@ constexpr int EW_THREADS = 256;
 
 static inline unsigned ew_grid(size_t n) {
     size_t nb  = (n + EW_THREADS * 2 - 1) / (EW_THREADS * 2);
-    size_t cap = (size_t)sm_count() * 8;
+    int per_sm = (int)opt("ew_ctas_per_sm", 8.0);
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    size_t cap = (size_t)sm_count() * per_sm;
     if (cap > (size_t)MAX_REDUCE_GRID) cap = MAX_REDUCE_GRID;
     if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
