@@ -29,7 +29,9 @@ constexpr int EW_THREADS = 256;
 
 static inline unsigned ew_grid(size_t n) {
     size_t nb  = (n + EW_THREADS * 2 - 1) / (EW_THREADS * 2);
-    int per_sm = (int)opt("ew_ctas_per_sm", 8.0);
+    // measured (profiles/slab_floor_r02l.log, 512^3): 4 CTAs of 256 threads per SM -> update 0.5015 / direction 0.8384 ms;
+    // 8 -> 0.5128 / 0.8736; 3, 5, 6 are worse again (the grid-stride distance interacts with the DRAM channel interleave)
+    int per_sm = (int)opt("ew_ctas_per_sm", 4.0);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     size_t cap = (size_t)sm_count() * per_sm;

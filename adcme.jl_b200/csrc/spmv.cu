@@ -1770,7 +1770,7 @@ static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<Mar
         if (Q.S % g || smem_for(g, 4) > ZM_SMEM_MAX) continue;
         if (gopt > 0 && g != gopt) continue;
         if (gopt <= 0 && g == 1 && G) continue;                    // single tiles only when nothing wider applies
-        const double pen = g == 4 ? 1.0 : (g == 2 ? 1.015 : 1.35);
+        const double pen = g == 4 ? 1.0 : (g == 2 ? 1.04 : 1.35);
         const long long Spg = Q.S / g, nsg = (Q.ntiles + g - 1) / g, Zcg = (nsg + Spg - 1) / Spg;
         const double rows = (double)g * RW_R;
         for (int nseg = 1; nseg <= Zcg && nseg <= 256; ++nseg) {

@@ -236,6 +236,41 @@ def workload_config(n: int, gpus: int):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+class near_gpu_affinity:
+    """Context manager: run the block with the CPU affinity NVML recommends for the GPU (its NUMA node), then restore
+    the previous affinity (the CPU baseline leg wants all cores back).  Silently a no-op when NVML is unavailable."""
+
+    def __init__(self, index: int):
+        self.index, self.saved = index, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            import torch
+
+            self.saved = os.sched_getaffinity(0)
+            pynvml.nvmlInit()
+            pr = torch.cuda.get_device_properties(self.index)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+            cpus &= self.saved
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception:
+            pass
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:
+                pass
+        return False
+
+
 def spmv_form(lib, h, nloc: int, nnz_loc: int):
     """Which SpMV kernel the CG solver runs for this handle and the bytes that form has to move per launch."""
     info = C.c_double(0)
@@ -324,8 +359,13 @@ def cg_leg(pkg, A, args, rank, world, dev, e2e: bool, sample_clocks: bool, const
     out = {"ms_dev": ms_dev, "launches": int(launches), "clocks": clocks, "relres": relres_dev, "true_relres": err,
            "value": ITERS_PER_STEP * args.steps / (ms_dev * 1e-3)}
     if e2e:
-        b_host = torch.empty(nloc, dtype=torch.float64).pin_memory()
-        u_host = torch.empty(nloc, dtype=torch.float64).pin_memory()
+        # host buffers on the NUMA node next to this rank's GPU: with 8 ranks staging at once, buffers that all sit on
+        # one socket make every copy cross the inter-socket link (measured N=8 e2e before: 15 GB/s per rank)
+        with near_gpu_affinity(dev.index):
+            b_host = torch.empty(nloc, dtype=torch.float64).pin_memory()
+            u_host = torch.empty(nloc, dtype=torch.float64).pin_memory()
+            b_host.fill_(0.0)
+            u_host.fill_(0.0)                       # first touch under the node-local affinity
         b_host.copy_(b)
         torch.cuda.synchronize()
         ms_e2e, _, _ = timed(u_host, b_host, False)
