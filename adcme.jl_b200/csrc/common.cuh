@@ -240,6 +240,8 @@ int radix_sort_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t*
 // dot_result[1] = <y, y> (deterministic two-stage reduction through partials/ticket).
 // done_flag (device int, may be null): the kernel is a no-op when *done_flag != 0.
 constexpr int MAX_REDUCE_GRID = 8192;   // partials buffers hold NV * MAX_REDUCE_GRID doubles
+constexpr int TICKET_GROUP = 32;        // CTAs per first-level ticket word (abd::grid_reduce)
+constexpr int TICKET_WORDS = 1 + MAX_REDUCE_GRID / TICKET_GROUP;   // every ticket buffer holds this many zeroed uint32
 int launch_spmv(const Csr* c, const double* x, double* y, const double* dotvec, double* dot_result,
                 double* partials, uint32_t* ticket, const int* done_flag);
 // restricted to a list of tiles (distributed SpMV: interior first, boundary after the halo);
@@ -337,8 +339,17 @@ __device__ __forceinline__ void grid_reduce(const double (&mine)[NV], double* pa
 #pragma unroll
         for (int k = 0; k < NV; ++k) partials[(size_t)k * gridDim.x + blockIdx.x] = mine[k];
         __threadfence();
-        uint32_t t = atomicAdd(ticket, 1u);
-        s_last     = (t == gridDim.x - 1);
+        // two-level ticket: the CTAs of a kernel finish together, and several hundred atomics on ONE word serialise in the
+        // L2 (tens of cycles each); groups of 32 CTAs count on their own word, the last of each group on word 0
+        const unsigned g = blockIdx.x / ab::TICKET_GROUP, ng = (gridDim.x + ab::TICKET_GROUP - 1) / ab::TICKET_GROUP;
+        const unsigned gsize = min((unsigned)ab::TICKET_GROUP, gridDim.x - g * ab::TICKET_GROUP);
+        bool last = false;
+        if (atomicAdd(ticket + 1 + g, 1u) == gsize - 1) {
+            ticket[1 + g] = 0;                    // re-armed for the next launch (nobody else touches it in this one)
+            __threadfence();
+            last = atomicAdd(ticket, 1u) == ng - 1;
+        }
+        s_last = last;
     }
     __syncthreads();
     if (s_last) {

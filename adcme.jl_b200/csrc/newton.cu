@@ -65,8 +65,8 @@ struct ReduceScratch {
     DevBuf<double> partials, res;
     DevBuf<uint32_t> ticket;
     int init() {
-        AB_TRY(partials.alloc(MAX_REDUCE_GRID)); AB_TRY(res.alloc(1)); AB_TRY(ticket.alloc(1));
-        AB_CUDA(cudaMemsetAsync(ticket.p, 0, sizeof(uint32_t), stream()));
+        AB_TRY(partials.alloc(MAX_REDUCE_GRID)); AB_TRY(res.alloc(1)); AB_TRY(ticket.alloc(TICKET_WORDS));
+        AB_CUDA(cudaMemsetAsync(ticket.p, 0, TICKET_WORDS * sizeof(uint32_t), stream()));
         return AB_OK;
     }
     int fetch(double* out) {

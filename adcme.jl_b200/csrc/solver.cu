@@ -69,8 +69,8 @@ int csr_ensure_work(Csr* c, size_t nvec) {
         AB_TRY(dev_alloc((void**)&c->scal, sizeof(SolveScal)));
         AB_CUDA(cudaMemsetAsync(c->scal, 0, sizeof(SolveScal), stream()));
         AB_TRY(dev_alloc((void**)&c->partials, (size_t)4 * MAX_REDUCE_GRID * sizeof(double)));
-        AB_TRY(dev_alloc((void**)&c->ticket, 4 * sizeof(uint32_t)));
-        AB_CUDA(cudaMemsetAsync(c->ticket, 0, 4 * sizeof(uint32_t), stream()));
+        AB_TRY(dev_alloc((void**)&c->ticket, TICKET_WORDS * sizeof(uint32_t)));
+        AB_CUDA(cudaMemsetAsync(c->ticket, 0, TICKET_WORDS * sizeof(uint32_t), stream()));
     }
     return AB_OK;
 }
