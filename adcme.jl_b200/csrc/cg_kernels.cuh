@@ -221,6 +221,8 @@ cgs_update_kernel(const double* __restrict__ p, const double* __restrict__ Ap, d
                   double* __restrict__ r, size_t n, int parity, SolveScal* s, double* partials, uint32_t* ticket,
                   int raw, int defer_x) {
     __shared__ double sh[32];
+    abd::pdl_launch_dependents();
+    abd::pdl_wait();
     if (s->done) return;
     const double rz = s->rz[parity], pAp = s->dots[0];
     const bool bad = !(pAp > 0.0) || !isfinite(pAp) || !isfinite(rz);
@@ -272,6 +274,8 @@ cgs_update_kernel(const double* __restrict__ p, const double* __restrict__ Ap, d
 static __global__ void __launch_bounds__(EW_THREADS)
 cgs_direction_kernel(const double* __restrict__ r, double* __restrict__ p, double* __restrict__ x, size_t n,
                      int parity, int it, int defer_x, const SolveScal* __restrict__ s) {
+    abd::pdl_launch_dependents();
+    abd::pdl_wait();
     const bool upd_x = defer_x && (s->iters == it + 1);
     const bool upd_p = !s->done;
     if (!upd_x && !upd_p) return;

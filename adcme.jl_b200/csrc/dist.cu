@@ -262,6 +262,8 @@ cgs_direction_halo_kernel(const double* __restrict__ r, double* __restrict__ p, 
                           int defer_x, const SolveScal* __restrict__ s, DistCsr::SendRanges sr, double* const* __restrict__ peer_x,
                           P2PBlock* const* __restrict__ peer_blk, P2PBlock* my_blk, int me, uint32_t halo_seq) {
     __shared__ bool s_last;
+    abd::pdl_launch_dependents();
+    abd::pdl_wait();
     const bool upd_x = defer_x && (s->iters == it + 1);
     const bool upd_p = !s->done;
     if (!upd_x && !upd_p) return;
@@ -333,6 +335,8 @@ __global__ void halo_wait_kernel(P2PBlock* blk, const int* __restrict__ recv_cnt
 __global__ void p2p_allreduce2_kernel(double* vals, P2PBlock* blk, P2PBlock* const* __restrict__ peer_blk, int world,
                                       int me, uint32_t seq, SolveScal* s, int fin_which, int parity, double tol) {
     const int t = threadIdx.x, par = seq & 1u;
+    abd::pdl_launch_dependents();
+    abd::pdl_wait();
     if (t < world) {
         P2PBlock* dst = peer_blk[t];
         dst->red[par][me][0] = vals[0];
@@ -584,7 +588,7 @@ static int allreduce2(DistCsr* d, double* p) {
     if (g_world == 1) return AB_OK;
     if (d->p2p) {
         ++d->red_seq;
-        p2p_allreduce2_kernel<<<1, 32, 0, stream()>>>(p, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq, nullptr, 0, 0, 0.0);
+        launch_pdl(p2p_allreduce2_kernel, dim3(1), dim3(32), 0, p, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq, (SolveScal*)nullptr, 0, 0, 0.0);
         AB_LAUNCH_CHECK();
         return AB_OK;
     }
@@ -596,7 +600,7 @@ static int allreduce2_fin(DistCsr* d, SolveScal* s, int which, int parity, doubl
     if (g_world == 1) return AB_OK;
     if (d->p2p) {
         ++d->red_seq;
-        p2p_allreduce2_kernel<<<1, 32, 0, stream()>>>(s->red, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq, s, which, parity, tol);
+        launch_pdl(p2p_allreduce2_kernel, dim3(1), dim3(32), 0, s->red, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq, s, which, parity, tol);
         AB_LAUNCH_CHECK();
         return AB_OK;
     }
@@ -805,16 +809,16 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
                 continue;
             }
             if (raw) AB_TRY(allreduce2(d, s->dots));
-            if (scaled) cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, raw, defer_x);
+            if (scaled) launch_pdl(cgs_update_kernel, dim3(g), dim3(EW_THREADS), 0, p, Ap, x, r, n, parity, s, c->partials, c->ticket, raw, defer_x);
             else cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, raw);
             AB_LAUNCH_CHECK();
             if (raw) AB_TRY(allreduce2_fin(d, s, 1, parity, tol));
             if (scaled && k3_halo) {
                 ++d->halo_seq;
-                cgs_direction_halo_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, it, defer_x, s, d->sr, d->d_peer_x,
-                                                                          d->d_peer_blk, d->blk, g_rank, d->halo_seq);
+                launch_pdl(cgs_direction_halo_kernel, dim3(g), dim3(EW_THREADS), 0, r, p, x, n, parity, it, defer_x, s, d->sr, d->d_peer_x,
+                           d->d_peer_blk, d->blk, g_rank, d->halo_seq);
                 halo_pushed = true;
-            } else if (scaled) cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, it, defer_x, s);
+            } else if (scaled) launch_pdl(cgs_direction_kernel, dim3(g), dim3(EW_THREADS), 0, r, p, x, n, parity, it, defer_x, s);
             else cg_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, c->dinv, p, n, parity, s);
             AB_LAUNCH_CHECK();
         }

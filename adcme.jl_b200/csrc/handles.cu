@@ -2,6 +2,7 @@
 // Mirrors the reference's "global map keyed by an integer handle" convention
 // (SAMAP, deps/CustomOps/SparseAccumulate/SparseAccumulator.cpp:8).
 #include "common.cuh"
+#include <cstring>
 #include <map>
 #include <string>
 #include <atomic>
@@ -208,12 +209,26 @@ int ab_synchronize(void) {
 }
 int ab_set_option(const char* key, double value) {
     if (!key) return fail(AB_EINVAL, "null option key");
+    if (!strcmp(key, "l2_fetch_granularity")) {
+        // device-wide hint (32 / 64 / 128 bytes): how much the L2 fetches from DRAM around a missing sector.  The random
+        // 8-byte gathers of the assembly / gradient paths pay for every byte of it.
+        AB_TRY(ensure_device());
+        AB_CUDA(cudaDeviceSynchronize());
+        AB_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     g_opts[key] = value;
     return AB_OK;
 }
 int ab_get_option(const char* key, double* value) {
     if (!key || !value) return fail(AB_EINVAL, "null argument");
+    if (!strcmp(key, "l2_fetch_granularity")) {
+        size_t v = 0;
+        AB_TRY(ensure_device());
+        AB_CUDA(cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity));
+        *value = (double)v;
+        return AB_OK;
+    }
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_opts.find(key);
     if (it == g_opts.end()) return fail(AB_EINVAL, "option '%s' is not set", key);

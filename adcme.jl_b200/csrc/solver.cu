@@ -169,7 +169,7 @@ static int run_cg_scaled(Csr* c, const double* b, double* x, double tol, int max
         for (int k = 0; k < chunk; ++k, ++it) {
             const int parity = it & 1;
             AB_TRY(launch_spmv_vals(c, c->svalues, p, Ap, p, s->dots, c->partials, c->ticket, &s->done, nullptr, 0, 0));
-            cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, 0, defer_x);
+            launch_pdl(cgs_update_kernel, dim3(g), dim3(EW_THREADS), 0, p, Ap, x, r, n, parity, s, c->partials, c->ticket, 0, defer_x);
             AB_LAUNCH_CHECK();
             if (replace_due(tol, it + 1)) {
                 double* Ax = work_vec(c, 5);
@@ -177,7 +177,7 @@ static int run_cg_scaled(Csr* c, const double* b, double* x, double tol, int max
                 cg_replace_kernel<<<g, EW_THREADS, 0, stream()>>>(b, c->sinv, Ax, nullptr, r, n, parity, s, c->partials, c->ticket);
                 AB_LAUNCH_CHECK();
             }
-            cgs_direction_kernel<<<g, EW_THREADS, 0, stream()>>>(r, p, x, n, parity, it, defer_x, s);
+            launch_pdl(cgs_direction_kernel, dim3(g), dim3(EW_THREADS), 0, r, p, x, n, parity, it, defer_x, s);
             AB_LAUNCH_CHECK();
         }
         if (tol < 0 && it < maxit) continue;   // fixed-count run: no polling

@@ -887,8 +887,8 @@ spmv_rowwin_kernel(const __grid_constant__ RowWinPlan P, const uint8_t* __restri
     uint8_t*  s_code = reinterpret_cast<uint8_t*>(s_info + 256);                        // [RW_R]
     __shared__ alignas(8) uint64_t bar;
     __shared__ double s_red[32];
-    if (done && *done) return;
     const unsigned t = threadIdx.x;
+    abd::pdl_launch_dependents();
     for (int i = t; i < nent; i += RW_T) s_ent[i] = ent[i];
     for (int i = t; i < 256; i += RW_T) s_info[i] = pinfo[i];
     if (t == 0) {
@@ -896,6 +896,8 @@ spmv_rowwin_kernel(const __grid_constant__ RowWinPlan P, const uint8_t* __restri
         abd::mbar_fence_init();
     }
     __syncthreads();
+    abd::pdl_wait();                 // only static tables and this CTA's shared memory were touched so far
+    if (done && *done) return;
     double dot = 0.0, dot2 = 0.0;
     unsigned phase = 0;
     const double* xt = s_x + t;
@@ -1237,8 +1239,8 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
     __shared__ alignas(8) uint64_t full[ZM_NB_MAX], empty[ZM_NB_MAX];
     __shared__ double s_red[32];
     __shared__ bool s_last;
-    if (done && *done) return;
     const unsigned t = threadIdx.x;
+    abd::pdl_launch_dependents();
     // items of this CTA: every gridDim.x-th one, or (balanced partition) the contiguous run cta_first names
     const unsigned ibeg = cta_first ? (unsigned)cta_first[blockIdx.x] : blockIdx.x;
     const unsigned iend = cta_first ? (unsigned)cta_first[blockIdx.x + 1] : nitems;
@@ -1251,6 +1253,10 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
         abd::mbar_fence_init();
     }
     __syncthreads();
+    // everything above touched only the pattern tables and this CTA's shared memory; from here on the previous kernel's
+    // results (x, the done flag) are read
+    abd::pdl_wait();
+    if (done && *done) return;
 
     if (t >= ZM_NT) {
         // ---------------- producers: feed the ring, L + 2 windows per item (positions -1 .. L)
@@ -2003,9 +2009,9 @@ static int launch_rowwin(const Csr* c, const double* x, double* y, const double*
             AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));                         \
             smem_set = RW_SMEM_MAX;                                                                                           \
         }                                                                                                                     \
-        kern<<<grid, RW_T, smem, stream()>>>(P, c->rowcode, (const int4*)c->rw_ent, c->npat_ent, c->pat_info, c->rw_tmask, x, \
-                                             (long long)c->n, y, (unsigned)c->m, ntiles, tile_list, accumulate, dotvec,       \
-                                             dot_in_window, partials, ticket, dot_result, done_flag, hw);                     \
+        launch_pdl(kern, dim3(grid), dim3(RW_T), smem, P, c->rowcode, (const int4*)c->rw_ent, c->npat_ent, c->pat_info,       \
+                   c->rw_tmask, x, (long long)c->n, y, (unsigned)c->m, ntiles, tile_list, accumulate, dotvec,                 \
+                   dot_in_window, partials, ticket, dot_result, done_flag, hw);                                               \
     } while (0)
 #define AB_RW2(KK, CC) do { if (tile_list) AB_RW(KK, CC, true); else AB_RW(KK, CC, false); } while (0)
     if (fast && P.dk == 7 && ck == 3) AB_RW2(7, 3);
@@ -2083,11 +2089,10 @@ static int launch_zmarch(const Csr* c, const double* x, double* y, const double*
             AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZM_SMEM_MAX));               \
             smem_set = ZM_SMEM_MAX;                                                                                           \
         }                                                                                                                     \
-        kern<<<grid, ZM_THREADS, smem, stream()>>>(P, (KK) > 0 ? c->zm_rowmask : c->rowcode, c->rowcode, (const int4*)c->rm_ent,  \
-                                                   c->npat_ent, c->pat_info, x,                                               \
-                                                   (long long)c->n, y, (unsigned)c->m, c->zm_items, c->zm_items + nitems,    \
-                                                   nitems, c->zm_cta_first, dotvec, dot_in_window, partials, ticket,         \
-                                                   dot_result, done_flag);                                                   \
+        launch_pdl(kern, dim3(grid), dim3(ZM_THREADS), smem, P, (KK) > 0 ? c->zm_rowmask : c->rowcode, c->rowcode,            \
+                   (const int4*)c->rm_ent, c->npat_ent, c->pat_info, x, (long long)c->n, y, (unsigned)c->m, c->zm_items,      \
+                   c->zm_items + nitems, nitems, c->zm_cta_first, dotvec, dot_in_window, partials, ticket, dot_result,        \
+                   done_flag);                                                                                                \
     } while (0)
 #define AB_ZMG(KK, CC) do { if (P.G == 4) AB_ZM(4, KK, CC); else if (P.G == 2) AB_ZM(2, KK, CC); else AB_ZM(1, KK, CC); } while (0)
     if (fast && P.dk == 7 && ck == 3) AB_ZMG(7, 3);
