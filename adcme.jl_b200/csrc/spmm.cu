@@ -162,16 +162,18 @@ spmm_warp_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
 // entries; with a warp per row such a row keeps one 256-byte X gather in flight and the kernel is latency-bound
 // (C5: 0.51 of the gather-model roofline).  Here the group's entries (<= 32 in total) are fetched by one
 // coalesced load, their X-row gathers are issued eight at a time ACROSS row boundaries, and the running sum is
-// flushed to Y whenever the row changes (warp-uniform branch).  Per-row summation order is unchanged (stored
-// order), so Y is bit-identical to the warp-per-row kernel.  Groups holding more than 32 entries (or a long
-// row) fall back to the row-at-a-time walk.
+// flushed to Y whenever the row changes (warp-uniform branch).  Measured alternatives at C5 x 0.4 (25.7 ms with this
+// kernel): 16 gathers in flight per warp (80 registers or spills) 30.6-39.6 ms; groups of 24 rows 25.1 ms; entry-balanced
+// tasks (the rows starting in one 64-entry block of the CSR arrays) 26.3 ms — the row structure is not what limits it.  Per-row summation order is unchanged (stored
+// order), so Y is bit-identical to the warp-per-row kernel.  A group with more than 32 entries is walked in
+// 32-entry windows by the same code; only a group that contains a long row (chunk kernels) goes row by row.
 constexpr int SPMM_GROUP = 8;
 template <int NC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colind,
                   const double* __restrict__ values, const double* __restrict__ X, double* __restrict__ Y,
                   int64_t m, int k, int c0, int long_thresh) {
-    constexpr int UB = NC == 1 ? 8 : 4;
+    constexpr int UB = NC == 1 ? 8 : 4;     // measured: 16 in flight (80 registers, spills) 39.6 ms vs 25.7 ms at C5 x 0.4
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
     const int64_t nwarp = ((int64_t)gridDim.x * 256) >> 5;
@@ -182,8 +184,11 @@ spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
         const int rp = lane <= nr ? rowptr[row0 + lane] : 0;
         const int a = __shfl_sync(0xffffffffu, rp, 0), b = __shfl_sync(0xffffffffu, rp, nr);
         const int cnt = b - a;
-        if (cnt > 32) {
-            // row at a time (long rows are left to the chunk kernels)
+        const int rp_next = __shfl_down_sync(0xffffffffu, rp, 1);
+        const int mylen = lane < nr ? rp_next - rp : 0;
+        const bool has_long = __any_sync(0xffffffffu, lane < nr && mylen > long_thresh);
+        if (has_long) {
+            // a long row sits in this group: row at a time (the long row itself is left to the chunk kernels)
             for (int rr = 0; rr < nr; ++rr) {
                 const int ra = __shfl_sync(0xffffffffu, rp, rr), rb = __shfl_sync(0xffffffffu, rp, rr + 1);
                 if (rb - ra > long_thresh) continue;
@@ -200,10 +205,6 @@ spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
             }
             continue;
         }
-        int cj = 0, rid = 0;
-        double vj = 0.0;
-        if (lane < cnt) { cj = colind[a + lane]; vj = values[a + lane]; }
-        for (int rr = 1; rr <= nr; ++rr) rid += (__shfl_sync(0xffffffffu, rp, rr) <= a + lane) ? 1 : 0;   // row (within the group) of entry `lane`
         double acc[NC];
 #pragma unroll
         for (int q = 0; q < NC; ++q) acc[q] = 0.0;
@@ -220,28 +221,37 @@ spmm_group_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                 ++cur;
             }
         };
-        for (int q0 = 0; q0 < cnt; q0 += UB) {
-            double xv[UB][NC], vq[UB];
-            int rq[UB];
+        // the group's entries in windows of 32 (one coalesced index/value load each); the X-row gathers run UB at a time
+        // straight across row boundaries AND window boundaries of the group
+        for (int w0 = 0; w0 < cnt; w0 += 32) {
+            const int wn = min(32, cnt - w0);
+            int cj = 0, rid = 0;
+            double vj = 0.0;
+            if (lane < wn) { cj = colind[a + w0 + lane]; vj = values[a + w0 + lane]; }
+            for (int rr = 1; rr <= nr; ++rr) rid += (__shfl_sync(0xffffffffu, rp, rr) <= a + w0 + lane) ? 1 : 0;   // row (within the group) of entry `lane`
+            for (int q0 = 0; q0 < wn; q0 += UB) {
+                double xv[UB][NC], vq[UB];
+                int rq[UB];
 #pragma unroll
-            for (int b8 = 0; b8 < UB; ++b8) {
-                const int q = q0 + b8;
-                const int cq = __shfl_sync(0xffffffffu, cj, q & 31);
-                vq[b8] = __shfl_sync(0xffffffffu, vj, q & 31);
-                rq[b8] = __shfl_sync(0xffffffffu, rid, q & 31);
-                const double* xr = X + (size_t)cq * k + c0;
+                for (int b8 = 0; b8 < UB; ++b8) {
+                    const int q = q0 + b8;
+                    const int cq = __shfl_sync(0xffffffffu, cj, q & 31);
+                    vq[b8] = __shfl_sync(0xffffffffu, vj, q & 31);
+                    rq[b8] = __shfl_sync(0xffffffffu, rid, q & 31);
+                    const double* xr = X + (size_t)cq * k + c0;
 #pragma unroll
-                for (int u = 0; u < NC; ++u) {
-                    const int cc = lane + 32 * u;
-                    xv[b8][u] = (q < cnt && c0 + cc < k) ? __ldg(xr + cc) : 0.0;
+                    for (int u = 0; u < NC; ++u) {
+                        const int cc = lane + 32 * u;
+                        xv[b8][u] = (q < wn && c0 + cc < k) ? __ldg(xr + cc) : 0.0;
+                    }
                 }
-            }
 #pragma unroll
-            for (int b8 = 0; b8 < UB; ++b8) {
-                if (q0 + b8 < cnt) {
-                    flush_to(rq[b8]);
+                for (int b8 = 0; b8 < UB; ++b8) {
+                    if (q0 + b8 < wn) {
+                        flush_to(rq[b8]);
 #pragma unroll
-                    for (int u = 0; u < NC; ++u) acc[u] = fma(vq[b8], xv[b8][u], acc[u]);
+                        for (int u = 0; u < NC; ++u) acc[u] = fma(vq[b8], xv[b8][u], acc[u]);
+                    }
                 }
             }
         }
@@ -449,6 +459,54 @@ sddmm_warp_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     }
 }
 
+// 32 <= k <= 128, entry-parallel form: a warp takes 16 consecutive stored ENTRIES whatever rows they belong to — on a
+// power-law matrix most rows hold 1-3 entries, and a warp per row keeps one or two 256-byte X gathers in flight.  Here
+// every warp has 16 X-row gathers and 16 dY-row loads in flight (consecutive entries share their dY row: L1 hits);
+// long rows need no chunking.  Same per-entry arithmetic and the same butterfly as sddmm_range: identical bits.
+template <int NC>
+__global__ void __launch_bounds__(256)
+sddmm_entry_kernel(const int32_t* __restrict__ entry_row, const int32_t* __restrict__ colind,
+                   const double* __restrict__ dY, const double* __restrict__ X, size_t nnz, int k,
+                   double* __restrict__ dv) {
+    constexpr int EB = 16;
+    const int lane = threadIdx.x & 31;
+    const size_t warp0 = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const size_t nwarp = ((size_t)gridDim.x * 256) >> 5;
+    for (size_t base = warp0 * EB; base < nnz; base += nwarp * EB) {
+        const int cnt = (int)min((size_t)EB, nnz - base);
+        const int cj = lane < cnt ? colind[base + lane] : 0;
+        const int rj = lane < cnt ? entry_row[base + lane] : 0;
+        double prod[EB];
+#pragma unroll
+        for (int q = 0; q < EB; ++q) {
+            const int cq = __shfl_sync(0xffffffffu, cj, q), rq = __shfl_sync(0xffffffffu, rj, q);
+            const double* xr = X + (size_t)cq * k;
+            const double* yr = dY + (size_t)rq * k;
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < NC; ++u) {
+                const int cc = lane + 32 * u;
+                const double xv = __ldg(xr + (cc < k ? cc : 0));
+                const double yv = __ldg(yr + (cc < k ? cc : 0));
+                s = cc < k ? fma(yv, xv, s) : s;
+            }
+            prod[q] = s;
+        }
+#pragma unroll
+        for (int s = EB / 2; s >= 1; s >>= 1) {
+            const bool up = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < s; ++i) {
+                const double send = up ? prod[i] : prod[i + s];
+                const double keep = up ? prod[i + s] : prod[i];
+                prod[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            }
+        }
+        const double tot = prod[0] + __shfl_xor_sync(0xffffffffu, prod[0], 16);
+        if (lane < cnt) dv[base + lane] = tot;
+    }
+}
+
 __global__ void gather_slot_kernel(const int32_t* __restrict__ slot, const double* __restrict__ dv, size_t T,
                                    double* __restrict__ out) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -457,6 +515,20 @@ __global__ void gather_slot_kernel(const int32_t* __restrict__ slot, const doubl
 
 static int launch_sddmm(Csr* c, const double* dY, const double* X, int k, double* dv) {
     if (c->nnz == 0) return AB_OK;
+    if (k >= 32 && k <= 128 && opt("sddmm_entry", 1.0) != 0.0) {
+        AB_TRY(csr_ensure_entry_row(c));
+        const size_t nwork = ((size_t)c->nnz + 15) / 16;
+        size_t nblk = (nwork + 7) / 8, cap = (size_t)sm_count() * 8 * 8;
+        const unsigned grid = (unsigned)(nblk < cap ? nblk : cap);
+#define AB_SDE(NCC) sddmm_entry_kernel<NCC><<<grid, 256, 0, stream()>>>(c->entry_row, c->colind, dY, X, (size_t)c->nnz, k, dv)
+        if (k <= 32) AB_SDE(1);
+        else if (k <= 64) AB_SDE(2);
+        else if (k <= 96) AB_SDE(3);
+        else AB_SDE(4);
+#undef AB_SDE
+        AB_LAUNCH_CHECK();
+        return AB_OK;
+    }
     if (k >= 32 && k <= 128) {
         AB_TRY(csr_ensure_long(c));
         const int thresh = c->long_nrows > 0 ? LONG_ROW : INT32_MAX;
