@@ -55,7 +55,16 @@ const char* ab_last_error(void);
 const char* ab_version(void);
 int         ab_set_stream(void* cuda_stream); /* launches go to this cudaStream_t (default: 0)   */
 int         ab_synchronize(void);
-/* tunables: "tol" (default solve tolerance), "maxit", "spmv_variant", "check_every", "verbose" */
+/* tunables: "tol" (default solve tolerance), "maxit", "check_every", "verbose", "refine", and A/B switches of the
+ * kernel forms (every one defaults to the measured-best setting; none changes a result beyond fp64 rounding of the
+ * fused inner products, and the SpMV output itself is bit-identical under all of them):
+ *   SpMV form of the solver   "spmv_rowpat", "spmv_code", "spmv_off8", "spmv_rowwin", "spmv_rowmarch", "spmv_zmarch",
+ *                             "spmv_zmarch_g" (tiles per chain position), "spmv_zmarch_len", "spmv_zmarch_balanced",
+ *                             "spmv_zmarch_tma" (1: cp.async.bulk, 0: 16-byte cp.async), "spmv_variant"
+ *   vector kernels            "ew_ctas_per_sm" (default 4), "cg_defer_x", "cg_scaled", "pdl" (programmatic dependent launch)
+ *   distributed iteration     "dist_p2p", "dist_fused_wait", "dist_fused_reduce", "dist_fused_push", "dist_k3_halo"
+ *   SpMM / SDDMM              "spmm_group", "sddmm_entry"
+ *   device                    "l2_fetch_granularity" (cudaLimitMaxL2FetchGranularity; applied at once) */
 int         ab_set_option(const char* key, double value);
 int         ab_get_option(const char* key, double* value);
 
