@@ -234,7 +234,23 @@ cgs_update_kernel(const double* __restrict__ p, const double* __restrict__ Ap, d
     double2* x2 = reinterpret_cast<double2*>(x);
     double2* r2 = reinterpret_cast<double2*>(r);
     if (defer_x) {
-        for (size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x; i < n2; i += (size_t)gridDim.x * EW_THREADS) {
+        // two grid-stride steps per trip: four 16-byte loads in flight per thread (at 4 CTAs per SM the single-step loop
+        // keeps 32 KB per SM in flight, short of what HBM latency needs); the sum order per thread is unchanged
+        // — measured (profiles/slab_floor_r02s.log): 73.8 -> 70.0 us on a 16.7 M-row slab, but 501.5 -> 511.7 us at 134 M rows
+        // (the doubled stride meets the DRAM channel interleave badly), so only vectors up to 48 M rows take it
+        const size_t step = (size_t)gridDim.x * EW_THREADS;
+        size_t i = (size_t)blockIdx.x * EW_THREADS + threadIdx.x;
+        const size_t n2u = n <= ((size_t)48 << 20) ? n2 : 0;
+        for (; i + step < n2u; i += 2 * step) {
+            double2 av = Ap2[i], rv = r2[i], av1 = Ap2[i + step], rv1 = r2[i + step];
+            rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
+            rv1.x = fma(-alpha, av1.x, rv1.x); rv1.y = fma(-alpha, av1.y, rv1.y);
+            r2[i] = rv;
+            r2[i + step] = rv1;
+            a0 = fma(rv.x, rv.x, a0); a0 = fma(rv.y, rv.y, a0);
+            a0 = fma(rv1.x, rv1.x, a0); a0 = fma(rv1.y, rv1.y, a0);
+        }
+        for (; i < n2; i += step) {
             double2 av = Ap2[i], rv = r2[i];
             rv.x = fma(-alpha, av.x, rv.x); rv.y = fma(-alpha, av.y, rv.y);
             r2[i] = rv;
