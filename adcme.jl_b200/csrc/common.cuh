@@ -281,6 +281,10 @@ struct P2PBlock {
     // the other CTAs of a kernel wait on a device-scope flag instead of all hammering the NVLink-written lines
     double   sum[2][2];               // [parity][2 values]
     uint32_t sum_flag[2];             // sequence number whose sums sit in sum[parity]
+    // flag-in-payload slots of p2p_allreduce2_kernel: four 8-byte words per (parity, source rank), each = (sequence
+    // number << 32) | one 32-bit half of the two doubles — an aligned 8-byte store arrives whole, so a word whose upper
+    // half shows the awaited sequence number carries its data and no fence / separate flag round trip is needed
+    unsigned long long ll[2][P2P_MAXW][4];
 };
 struct HaloWait {
     const uint32_t* flags;     // [world] sequence numbers published by the peers (this rank's memory)

@@ -333,23 +333,55 @@ __global__ void halo_wait_kernel(P2PBlock* blk, const int* __restrict__ recv_cnt
 // s != nullptr: the CG scalar logic that follows the reduction (cg_fin_kernel) runs right here —
 // fin_which 0 = after the init kernel, 1 = after the update kernel — one launch fewer per iteration.
 __global__ void p2p_allreduce2_kernel(double* vals, P2PBlock* blk, P2PBlock* const* __restrict__ peer_blk, int world,
-                                      int me, uint32_t seq, SolveScal* s, int fin_which, int parity, double tol) {
+                                      int me, uint32_t seq, SolveScal* s, int fin_which, int parity, double tol, int ll) {
     const int t = threadIdx.x, par = seq & 1u;
     abd::pdl_launch_dependents();
     abd::pdl_wait();
-    if (t < world) {
+    double v0 = 0.0, v1 = 0.0;                 // lane t: rank t's two partial sums
+    if (ll) {
+        // flag-in-payload exchange (P2PBlock::ll): no fence, no separate flag store — one NVLink latency instead of two
+        if (t < world) {
+            const unsigned long long b0 = (unsigned long long)__double_as_longlong(vals[0]);
+            const unsigned long long b1 = (unsigned long long)__double_as_longlong(vals[1]);
+            const unsigned long long tag = (unsigned long long)seq << 32;
+            unsigned long long* dst = &peer_blk[t]->ll[par][me][0];
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 0), "l"(tag | (b0 & 0xffffffffull)) : "memory");
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(tag | (b0 >> 32)) : "memory");
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 2), "l"(tag | (b1 & 0xffffffffull)) : "memory");
+            asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 3), "l"(tag | (b1 >> 32)) : "memory");
+            const unsigned long long* src = &blk->ll[par][t][0];
+            unsigned long long w[4];
+            const long long t0 = clock64();
+            for (;;) {
+                bool ok = true;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[i]) : "l"(src + i) : "memory");
+                    ok = ok && (uint32_t)(w[i] >> 32) == seq;
+                }
+                if (ok) break;
+                if (clock64() - t0 > (1ll << abd::AB_WAIT_CLOCKS_LOG2)) { atomicExch(&blk->err, 1u); break; }
+            }
+            v0 = __longlong_as_double((long long)((w[1] << 32) | (w[0] & 0xffffffffull)));
+            v1 = __longlong_as_double((long long)((w[3] << 32) | (w[2] & 0xffffffffull)));
+        }
+    } else if (t < world) {
         P2PBlock* dst = peer_blk[t];
         dst->red[par][me][0] = vals[0];
         dst->red[par][me][1] = vals[1];
         __threadfence_system();
         st_release_sys(&dst->red_flag[par][me], seq);
         wait_seq(&blk->red_flag[par][t], seq, &blk->err);
+        v0 = ((const volatile double*)&blk->red[par][t][0])[0];
+        v1 = ((const volatile double*)&blk->red[par][t][0])[1];
     }
     __syncwarp();
+    double s0 = 0.0, s1 = 0.0;
+    for (int p = 0; p < world; ++p) {          // rank order: same bits everywhere
+        s0 += __shfl_sync(0xffffffffu, v0, p);
+        s1 += __shfl_sync(0xffffffffu, v1, p);
+    }
     if (t == 0) {
-        double s0 = 0.0, s1 = 0.0;
-        const volatile double* r = &blk->red[par][0][0];
-        for (int p = 0; p < world; ++p) { s0 += r[2 * p]; s1 += r[2 * p + 1]; }   // rank order: same bits everywhere
         vals[0] = s0;
         vals[1] = s1;
         if (s) {
@@ -588,7 +620,8 @@ static int allreduce2(DistCsr* d, double* p) {
     if (g_world == 1) return AB_OK;
     if (d->p2p) {
         ++d->red_seq;
-        launch_pdl(p2p_allreduce2_kernel, dim3(1), dim3(32), 0, p, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq, (SolveScal*)nullptr, 0, 0, 0.0);
+        launch_pdl(p2p_allreduce2_kernel, dim3(1), dim3(32), 0, p, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq, (SolveScal*)nullptr, 0, 0, 0.0,
+                   opt("dist_ll", 1.0) != 0.0 ? 1 : 0);
         AB_LAUNCH_CHECK();
         return AB_OK;
     }
@@ -600,7 +633,8 @@ static int allreduce2_fin(DistCsr* d, SolveScal* s, int which, int parity, doubl
     if (g_world == 1) return AB_OK;
     if (d->p2p) {
         ++d->red_seq;
-        launch_pdl(p2p_allreduce2_kernel, dim3(1), dim3(32), 0, s->red, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq, s, which, parity, tol);
+        launch_pdl(p2p_allreduce2_kernel, dim3(1), dim3(32), 0, s->red, d->blk, d->d_peer_blk, g_world, g_rank, d->red_seq, s, which, parity, tol,
+                   opt("dist_ll", 1.0) != 0.0 ? 1 : 0);
         AB_LAUNCH_CHECK();
         return AB_OK;
     }

@@ -71,26 +71,26 @@ def dist_parity(pkg, rank: int, world: int, dev, n: int = 96, variants: bool = T
         # every combination of data path the solver can take: NCCL vs peer memory, separate halo-wait launch vs the
         # in-kernel wait (row-pattern kernel and x-window kernel), all-reduces as launches vs folded into K2'/K3'
         # ... and K3 pushing the next halos while it sweeps (k3h) vs the separate halo_push_kernel launch
-        combos = [dict(dist_p2p=0, dist_fused_wait=0, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=1),
-                  dict(dist_p2p=1, dist_fused_wait=0, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=0),
-                  dict(dist_p2p=1, dist_fused_wait=0, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=1),
-                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=0, dist_k3_halo=1),
-                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=1, dist_fused_push=0, spmv_rowwin=0, dist_k3_halo=1),
-                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=1, dist_fused_push=1, spmv_rowwin=0, dist_k3_halo=1),
-                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=0),
-                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=1),
-                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=1, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=1),
-                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=1, dist_fused_push=1, spmv_rowwin=1, dist_k3_halo=1)]
+        combos = [dict(dist_p2p=0, dist_fused_wait=0, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=1, dist_ll=1),
+                  dict(dist_p2p=1, dist_fused_wait=0, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=0, dist_ll=0),
+                  dict(dist_p2p=1, dist_fused_wait=0, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=1, dist_ll=1),
+                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=0, dist_k3_halo=1, dist_ll=1),
+                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=1, dist_fused_push=0, spmv_rowwin=0, dist_k3_halo=1, dist_ll=1),
+                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=1, dist_fused_push=1, spmv_rowwin=0, dist_k3_halo=1, dist_ll=1),
+                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=0, dist_ll=1),
+                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=1, dist_ll=1),
+                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=1, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=1, dist_ll=1),
+                  dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=1, dist_fused_push=1, spmv_rowwin=1, dist_k3_halo=1, dist_ll=1)]
         saved = {}
         for k in combos[0]:
             v = C.c_double(0)
             saved[k] = v.value if lib.ab_get_option(k.encode(), C.byref(v)) == 0 else None
-        defaults = dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=1)
+        defaults = dict(dist_p2p=1, dist_fused_wait=1, dist_fused_reduce=0, dist_fused_push=0, spmv_rowwin=1, dist_k3_halo=1, dist_ll=1)
         defaults.update({k: v for k, v in saved.items() if v is not None})       # A/B switches of the caller survive
         for cmb in combos:
             _set(lib, check, **cmb)
-            tag = "p2p%d_wait%d_red%d_push%d_win%d_k3h%d:" % (cmb["dist_p2p"], cmb["dist_fused_wait"], cmb["dist_fused_reduce"],
-                                                             cmb["dist_fused_push"], cmb["spmv_rowwin"], cmb["dist_k3_halo"])
+            tag = "p2p%d_wait%d_red%d_push%d_win%d_k3h%d_ll%d:" % (cmb["dist_p2p"], cmb["dist_fused_wait"], cmb["dist_fused_reduce"],
+                                                                  cmb["dist_fused_push"], cmb["spmv_rowwin"], cmb["dist_k3_halo"], cmb["dist_ll"])
             try:
                 stencil_case(tag, False)
             finally:
