@@ -191,6 +191,7 @@ struct Csr {
     int       zm_ok = 0;
     uint8_t*  zm_rowmask = nullptr; // [m + pad] zm_mask[rowcode[r]]: the byte stream the kernel stages when the dominant pattern is in its parameters
     uint8_t*  zm_mask = nullptr;   // [256] per pattern: which entries of the dominant pattern it keeps (0x80: walk the table)
+    uint8_t*  rw_mask = nullptr;     // [256] per pattern: which entries of the window kernel's dominant pattern it keeps (0x80: walk)
     uint8_t*  rw_exclude = nullptr;  // [ceil(m/1024)] optional (dist.cu): tiles that must not join a chain (they read halo columns)
     // triplet bookkeeping (null when the handle was created from CSR: identity map)
     uint32_t* perm     = nullptr; // [T]  sorted position -> input triplet

@@ -875,7 +875,7 @@ __device__ __forceinline__ bool rowwin_range(const RowWinPlan& P, int i, unsigne
 template <int K, int CK, bool LIST>
 __global__ void __launch_bounds__(RW_T)
 spmv_rowwin_kernel(const __grid_constant__ RowWinPlan P, const uint8_t* __restrict__ rowcode, const int4* __restrict__ ent,
-                   int nent, const uint32_t* __restrict__ pinfo, const uint8_t* __restrict__ tmask,
+                   int nent, const uint32_t* __restrict__ pinfo, const uint8_t* __restrict__ pmask, const uint8_t* __restrict__ tmask,
                    const double* __restrict__ x, long long xlen, double* __restrict__ y, unsigned m, unsigned ntiles,
                    const int32_t* __restrict__ tile_list, int accumulate, const double* __restrict__ dotvec,
                    int dot_in_window, double* partials, uint32_t* ticket, double* dot_result,
@@ -887,10 +887,11 @@ spmv_rowwin_kernel(const __grid_constant__ RowWinPlan P, const uint8_t* __restri
     uint8_t*  s_code = reinterpret_cast<uint8_t*>(s_info + 256);                        // [RW_R]
     __shared__ alignas(8) uint64_t bar;
     __shared__ double s_red[32];
+    __shared__ uint8_t s_mask[256];
     const unsigned t = threadIdx.x;
     abd::pdl_launch_dependents();
     for (int i = t; i < nent; i += RW_T) s_ent[i] = ent[i];
-    for (int i = t; i < 256; i += RW_T) s_info[i] = pinfo[i];
+    for (int i = t; i < 256; i += RW_T) { s_info[i] = pinfo[i]; s_mask[i] = pmask[i]; }
     if (t == 0) {
         abd::mbar_init(&bar, 1);
         abd::mbar_fence_init();
@@ -922,23 +923,75 @@ spmv_rowwin_kernel(const __grid_constant__ RowWinPlan P, const uint8_t* __restri
         }
         abd::mbar_wait(&bar, phase);
         phase ^= 1u;
+        if (K > 0) {
+            // same scheme as spmv_zmarch_kernel: every row first as the dominant pattern with the FMAs of missing entries
+            // predicated off by the pattern's mask (Dirichlet faces / edges / corners are sub-patterns of the interior
+            // stencil), straight-line over the thread's four rows; bit 7 = some other pattern, walked from its table
+            constexpr unsigned FULL = (1u << K) - 1u;
+            unsigned mk[RW_J];
+            double acc[RW_J];
+            bool allfull = true;
+#pragma unroll
+            for (int j = 0; j < RW_J; ++j) {
+                const unsigned tl = t + (unsigned)j * RW_T;
+                mk[j] = tl < nr ? (unsigned)s_code[tl] : (unsigned)P.dom;
+                mk[j] = s_mask[mk[j]] | (mk[j] << 8);
+                allfull = allfull && (mk[j] & 0xffu) == FULL;
+            }
+            if (__all_sync(0xffffffffu, allfull)) {
+#pragma unroll
+                for (int j = 0; j < RW_J; ++j) acc[j] = 0.0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+#pragma unroll
+                    for (int j = 0; j < RW_J; ++j) acc[j] = fma(P.dval[k], xt[j * RW_T + P.dsoff[k]], acc[j]);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < RW_J; ++j) acc[j] = 0.0;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+#pragma unroll
+                    for (int j = 0; j < RW_J; ++j)
+                        if ((mk[j] >> k) & 1u) acc[j] = fma(P.dval[k], xt[j * RW_T + P.dsoff[k]], acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < RW_J; ++j) {
+                    if (mk[j] & 0x80u) {
+                        const double* xb = xt + j * RW_T;
+                        const uint32_t info = s_info[mk[j] >> 8];
+                        const int4* e = s_ent + (info & 0xffffu);
+                        const int len = (int)(info >> 16);
+                        double a = 0.0;
+                        for (int k = 0; k < len; ++k) {
+                            const int4 q0 = e[k];
+                            a = fma(__hiloint2double(q0.y, q0.x), xb[q0.z], a);
+                        }
+                        acc[j] = a;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < RW_J; ++j) {
+                const unsigned tl = t + (unsigned)j * RW_T;
+                if (tl < nr) {
+                    y[r0 + tl] = acc[j];
+                    if (dotvec) {
+                        const double w = dot_in_window ? xt[j * RW_T + P.center] : dotvec[r0 + tl];
+                        dot  = fma(acc[j], w, dot);
+                        dot2 = fma(acc[j], acc[j], dot2);
+                    }
+                }
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < RW_J; ++j) {
             const unsigned tl = t + (unsigned)j * RW_T;
             if (tl < nr) {
                 const unsigned code = s_code[tl];
                 const double* xb = xt + j * RW_T;
-                double acc = 0.0, xc = 0.0;
-                bool have_xc = false;
-                if (K > 0 && code == (unsigned)P.dom) {
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const double xk = xb[P.dsoff[k]];
-                        if (k == CK) xc = xk;
-                        acc = fma(P.dval[k], xk, acc);
-                    }
-                    have_xc = CK >= 0;
-                } else {
+                double acc = 0.0;
+                {
                     const uint32_t info = s_info[code];
                     const int4* e = s_ent + (info & 0xffffu);
                     const int len = (int)(info >> 16);
@@ -956,11 +1009,12 @@ spmv_rowwin_kernel(const __grid_constant__ RowWinPlan P, const uint8_t* __restri
                 }
                 y[r0 + tl] = acc;
                 if (dotvec) {
-                    const double w = have_xc ? xc : (dot_in_window ? xb[P.center] : dotvec[r0 + tl]);
+                    const double w = dot_in_window ? xb[P.center] : dotvec[r0 + tl];
                     dot  = fma(acc, w, dot);
                     dot2 = fma(acc, acc, dot2);
                 }
             }
+        }
         }
         __syncthreads();   // the stage is rewritten by the next tile
     };
@@ -1611,6 +1665,22 @@ static int csr_build_rowwin(Csr* c, const std::vector<CodeEnt>& pent, const std:
         P.dom = dom; P.dk = dlen;
         for (int k = 0; k < dlen; ++k) { P.dsoff[k] = went[dst + k].off; P.dval[k] = went[dst + k].v; }
     }
+    // ---- per-pattern masks: which entries of the dominant pattern a pattern keeps (same stage offset, same value bits,
+    // same order); 0x80: not a sub-pattern — walked from the table
+    std::vector<uint8_t> rwmask(256, 0x80);
+    if (P.dom >= 0) {
+        const int dst0 = (int)(pinfo[P.dom] & 0xffffu);
+        for (int p = 0; p < npat; ++p) {
+            const int st = (int)(pinfo[p] & 0xffffu), len = (int)(pinfo[p] >> 16);
+            unsigned mask = 0;
+            int k = 0;
+            for (int e = 0; e < P.dk && k < len; ++e)
+                if (went[dst0 + e].off == went[st + k].off && memcmp(&went[dst0 + e].v, &went[st + k].v, sizeof(double)) == 0) { mask |= 1u << e; ++k; }
+            if (k == len && P.dk <= 7) rwmask[p] = (uint8_t)mask;
+        }
+    }
+    if (!c->rw_mask) AB_TRY(dev_alloc((void**)&c->rw_mask, 256));
+    AB_CUDA(cudaMemcpyAsync(c->rw_mask, rwmask.data(), 256, cudaMemcpyHostToDevice, stream()));
     // ---- device tables
     const int64_t ntile = (c->m + RW_R - 1) / RW_R;
     DevBuf<uint32_t> dpm;
@@ -2010,7 +2080,7 @@ static int launch_rowwin(const Csr* c, const double* x, double* y, const double*
             smem_set = RW_SMEM_MAX;                                                                                           \
         }                                                                                                                     \
         launch_pdl(kern, dim3(grid), dim3(RW_T), smem, P, c->rowcode, (const int4*)c->rw_ent, c->npat_ent, c->pat_info,       \
-                   c->rw_tmask, x, (long long)c->n, y, (unsigned)c->m, ntiles, tile_list, accumulate, dotvec,                 \
+                   c->rw_mask, c->rw_tmask, x, (long long)c->n, y, (unsigned)c->m, ntiles, tile_list, accumulate, dotvec,                 \
                    dot_in_window, partials, ticket, dot_result, done_flag, hw);                                               \
     } while (0)
 #define AB_RW2(KK, CC) do { if (tile_list) AB_RW(KK, CC, true); else AB_RW(KK, CC, false); } while (0)
