@@ -182,7 +182,8 @@ struct Csr {
     int32_t*  rm_rest = nullptr;   // [rm_nrest] those tiles, ascending
     int       rm_ok = 0;
     void*     zm_plan  = nullptr;  // host copy of the z-register marching plan (spmv.cu ZMarchPlan)
-    int32_t*  zm_items = nullptr;  // [2 * zm_nitems]: first chain position (group of G tiles) of each work item, then its length
+    void*     zm_ent   = nullptr;  // [npat_ent] x {double value; int32 offset inside the window; int32 plane}
+    int32_t*  zm_items = nullptr;  // [3 * zm_nitems]: first row of each work item's first chain position, its length, rows per position
     int       zm_nitems = 0;
     int32_t*  zm_cta_first = nullptr; // [zm_ncta + 1] balanced partition: CTA b runs items [zm_cta_first[b], zm_cta_first[b+1]) (null: round-robin)
     int       zm_ncta = 0;

@@ -124,7 +124,7 @@ Csr::~Csr() {
     dev_free(svalues); dev_free(sinv); dev_free(off8); dev_free(offtab); dev_free(code8); dev_free(codetab); dev_free(rowcode); dev_free(pat_ent); dev_free(pat_info);
     dev_free(rw_ent); dev_free(rw_tmask); dev_free(rw_mask); free(rw_plan);
     dev_free(rm_ent); dev_free(rm_items); free(rm_plan); dev_free(rm_rest); dev_free(rw_exclude);
-    dev_free(zm_items); dev_free(zm_rest); free(zm_plan); dev_free(zm_mask); dev_free(zm_rowmask); dev_free(zm_cta_first);
+    dev_free(zm_items); dev_free(zm_ent); dev_free(zm_rest); free(zm_plan); dev_free(zm_mask); dev_free(zm_rowmask); dev_free(zm_cta_first);
     dev_free(long_rows); dev_free(long_row_chunk0); dev_free(long_chunk_row); dev_free(long_chunk_start);
 }
 

@@ -739,8 +739,7 @@ struct RowWinPlan;
 static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat);
 struct RowMarchPlan;
 struct MarchEnt { double v; int32_t soff; int32_t plane; };     // pattern entry of the marching kernels (16 bytes, read as int4)
-static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<MarchEnt>& ment, const std::vector<uint32_t>& pinfo, int npat,
-                            const std::vector<char>& pat_ok, const std::vector<uint8_t>& hmask, unsigned marchmask);
+static int csr_build_zmarch(Csr* c, const RowWinPlan& W, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat);
 
 // npat > 0 afterwards: rowcode/pat_ent/pat_info encode the matrix the pattern codes encode
 static int csr_ensure_rowpat(Csr* c) {
@@ -1244,11 +1243,11 @@ constexpr int ZM_THREADS = ZM_NT + 32 * ZM_NPW;
 constexpr int ZM_NB_MAX = 8;                // ring slots: 4 or 8 (as many as fit)
 constexpr size_t ZM_SMEM_MAX = 225 * 1024;
 struct ZMarchPlan {
-    int G, S;               // 1024-row tiles per chain position; march stride in positions
+    int G;                  // 1024-row tiles per chain position
+    long long M;            // rows between consecutive chain positions (the plane stride; need not be a multiple of the tile)
     int lo, len;            // window: x[r0 + lo, r0 + lo + len), r0 = first row of the position; len in doubles (even)
     int center;             // offset of x[row] inside the window relative to the local row (= -lo)
     int dom, dk;            // dominant pattern and its length (dom < 0: every row walks its pattern)
-    int nsuper;             // chain positions (groups of G tiles) in the matrix
     int nb;                 // ring slots (power of two <= ZM_NB_MAX)
     int chunk;              // TMA mode: bytes per bulk copy (a window is streamed as several copies on the same mbarrier)
     int tma;                // 1: windows by cp.async.bulk (one thread); 0: by 16-byte cp.async of the producer warps (LDGSTS)
@@ -1276,8 +1275,9 @@ template <int G, int K, int CK>
 __global__ void __launch_bounds__(ZM_THREADS, 1)
 spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restrict__ rowcode, const uint8_t* __restrict__ rowpat,
                    const int4* __restrict__ ent, int nent, const uint32_t* __restrict__ pinfo, const double* __restrict__ x, long long xlen,
-                   double* __restrict__ y, unsigned m, const int32_t* __restrict__ item_first,
-                   const int32_t* __restrict__ item_count, unsigned nitems, const int32_t* __restrict__ cta_first,
+                   double* __restrict__ y, unsigned m, const uint32_t* __restrict__ item_first,
+                   const int32_t* __restrict__ item_count, const int32_t* __restrict__ item_rows, unsigned nitems,
+                   const int32_t* __restrict__ cta_first,
                    const double* __restrict__ dotvec, int dot_in_window, double* partials, uint32_t* ticket,
                    double* dot_result, const int* __restrict__ done) {
     constexpr int TR = G * RW_R;
@@ -1323,16 +1323,17 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
         if (!tma || pt == 0) {
             unsigned cnt = 0;
             for (unsigned item = ibeg; item < iend; item += istep) {
-                const int first = item_first[item], L = item_count[item];
+                const long long first = item_first[item];
+                const int L = item_count[item], irows = item_rows[item];
                 for (int q = 0; q < L + 2; ++q, ++cnt) {
                     const unsigned slot = cnt & NBM, use = cnt >> nbsh;
                     if (use > 0) abd::mbar_wait(&empty[slot], (use - 1) & 1u);
-                    const long long u = (long long)first + (long long)(q - 1) * P.S;
+                    const long long rr = first + (long long)(q - 1) * P.M;        // first row of chain position q - 1
                     unsigned bytes = 0, cbytes = 0, r0 = 0;
                     long long a = 0, b = 0, tail = -1, base = 0;
-                    if (u >= 0 && u < P.nsuper) {
-                        r0 = (unsigned)u * (unsigned)TR;
-                        const unsigned nr = min((unsigned)TR, m - r0);
+                    if (rr >= 0 && rr < (long long)m) {
+                        r0 = (unsigned)rr;
+                        const unsigned nr = min((unsigned)irows, m - r0);
                         cbytes = (nr + 15u) & ~15u;
                         base = (long long)r0 + P.lo;
                         a = base; b = base + len;
@@ -1370,7 +1371,8 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
             if (lane == 0) mbar_arrive(&empty[c & NBM]);
         };
         for (unsigned item = ibeg; item < iend; item += istep) {
-            const int first = item_first[item], L = item_count[item];
+            const long long first = item_first[item];
+            const int L = item_count[item], irows = item_rows[item];
             double dot = 0.0, dot2 = 0.0;
             double prv[RPT], cur[RPT];
             wait_full(cnt);
@@ -1389,8 +1391,8 @@ spmv_zmarch_kernel(const __grid_constant__ ZMarchPlan P, const uint8_t* __restri
             }
             for (int k = 0; k < L; ++k) {
                 wait_full(cnt + 1);
-                const unsigned r0 = (unsigned)(first + k * P.S) * (unsigned)TR;
-                const unsigned nr = min((unsigned)TR, m - r0);
+                const unsigned r0 = (unsigned)(first + (long long)k * P.M);
+                const unsigned nr = min((unsigned)irows, m - r0);
                 const double* wc = s_ring + (size_t)(cnt & NBM) * len + t;                       // + window offset + j * ZM_NT
                 const double* wn = s_ring + (size_t)((cnt + 1) & NBM) * len + P.center + t;
                 const uint8_t* codes = s_code + (cnt & NBM) * TR + t;
@@ -1697,7 +1699,8 @@ static int csr_build_rowwin(Csr* c, const std::vector<CodeEnt>& pent, const std:
     if (!c->rw_plan) return fail(AB_ECUDA, "out of host memory");
     memcpy(c->rw_plan, &P, sizeof(P));
     c->rw_ok = 1;
-    return csr_build_rowmarch(c, P, pent, pinfo, npat);
+    AB_TRY(csr_build_rowmarch(c, P, pent, pinfo, npat));
+    return csr_build_zmarch(c, P, pent, pinfo, npat);
 }
 
 // rm_ok = 1 afterwards when chains of tiles can share their windows (see spmv_rowmarch_kernel)
@@ -1750,6 +1753,15 @@ static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<Cod
             else pat_ok[p] = 0;
             ment[st + k] = e;
         }
+    }
+    // The stride must be the matrix' own: some entry sits exactly M rows from its row.  (A stride merely NEAR the plane
+    // distance — the shifted centre window still covers the neighbour interval — gave wrong products on 150^3 and 300^3,
+    // where the rounded stride exceeds the plane distance (profiles/scripts/forms_check.py); those grids take the
+    // z-register kernel with the exact stride, or the x-window kernel.)
+    {
+        bool exact = false;
+        for (const CodeEnt& e : pent) exact = exact || e.off == M || e.off == -M;
+        if (!exact) return AB_OK;
     }
     if (W.dom >= 0 && pat_ok[W.dom]) {
         const int st = (int)(pinfo[W.dom] & 0xffffu);
@@ -1817,50 +1829,105 @@ static int csr_build_rowmarch(Csr* c, const RowWinPlan& W, const std::vector<Cod
     c->rm_nitems = nitems;
     c->rm_nrest = (long long)ntiles - npure;
     c->rm_ok = 1;
-    return csr_build_zmarch(c, Q, ment, pinfo, npat, pat_ok, hmask, marchmask);
+    return AB_OK;
 }
 
-// zm_ok = 1 afterwards when the z-register marching kernel applies: every entry of the planes -M / +M sits exactly M rows
-// from its row (so those operands are what the owning thread read one / two chain positions earlier).
-static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<MarchEnt>& ment, const std::vector<uint32_t>& pinfo, int npat,
-                            const std::vector<char>& pat_ok, const std::vector<uint8_t>& hmask, unsigned marchmask) {
+// zm_ok = 1 afterwards when the z-register marching kernel applies: every pattern offset lies in the centre interval or
+// exactly M rows below / above its row (so those operands are what the owning thread read one / two chain positions
+// earlier).  Derived from the raw pattern offsets alone: M is the plane stride itself and need NOT be a multiple of the
+// tile — a chain is a strip of <= G * 1024 consecutive rows of the first plane and its images M, 2M, ... rows further
+// (the last strip of a plane is narrower); only M % 16 == 0 is asked (16-byte aligned copies of the mask stream).  Tiles
+// the distributed path excludes (they read halo columns) need strips that coincide with tiles: M % (G * 1024) == 0 then.
+static int csr_build_zmarch(Csr* c, const RowWinPlan& W, const std::vector<CodeEnt>& pent, const std::vector<uint32_t>& pinfo, int npat) {
     c->zm_ok = 0;
-    for (int p = 0; p < npat; ++p) {
-        if (!pat_ok[p]) continue;
-        const int st = (int)(pinfo[p] & 0xffffu), len = (int)(pinfo[p] >> 16);
-        for (int k = 0; k < len; ++k)
-            if (ment[st + k].plane != 0 && ment[st + k].soff != Q.center) return AB_OK;
+    int ic = -1;
+    for (int i = 0; i < W.ni; ++i) if (0 >= W.lo[i] && RW_R <= W.lo[i] + W.len[i]) ic = i;
+    if (ic < 0 || pent.empty() || c->m < 1) return AB_OK;
+    const long long loc = W.lo[ic], lenc = W.len[ic];
+    // ---- the plane stride M: the one off-centre distance of the dominant pattern
+    if (W.dom < 0) return AB_OK;
+    long long M = 0;
+    {
+        const int st = (int)(pinfo[W.dom] & 0xffffu), len = (int)(pinfo[W.dom] >> 16);
+        for (int k = 0; k < len; ++k) {
+            const long long o = pent[st + k].off;
+            if (o >= loc && o + RW_R <= loc + lenc) continue;
+            const long long a = o < 0 ? -o : o;
+            if (M == 0) M = a;
+            if (a != M) return AB_OK;
+        }
     }
-    const int margins = Q.len - RW_R;
+    if (M <= 0 || (M & 15) || M < RW_R) return AB_OK;
+    // ---- entries: plane 0 (inside the centre interval) or plane -1 / +1 (exactly M away); a pattern with any other
+    // offset (halo columns of a distributed block, ...) is left to the x-window kernel together with its whole tile
+    std::vector<MarchEnt> ment(pent.size());
+    std::vector<uint32_t> pbad(256, 0);
+    bool any_bad = false;
+    for (int p = 0; p < npat; ++p) {
+        const int st = (int)(pinfo[p] & 0xffffu), len = (int)(pinfo[p] >> 16);
+        for (int k = 0; k < len; ++k) {
+            const long long o = pent[st + k].off;
+            MarchEnt e; e.v = pent[st + k].v; e.soff = 0; e.plane = 0;
+            if (o >= loc && o + RW_R <= loc + lenc) e.soff = (int)(o - loc);
+            else if (o == M || o == -M) { e.plane = o < 0 ? -1 : 1; e.soff = (int)(0 - loc); }
+            else { pbad[p] = 1; any_bad = true; }
+            ment[st + k] = e;
+        }
+    }
+    const int margins = (int)(lenc - RW_R);
+    const int ntiles = (int)((c->m + RW_R - 1) / RW_R);
+    // ---- excluded tiles: those the distributed path names (they read halo columns) and those holding a row of a bad pattern
+    std::vector<uint8_t> hex((size_t)ntiles, 0);
+    bool any_excl = false;
+    if (c->rw_exclude) {
+        AB_CUDA(cudaMemcpyAsync(hex.data(), c->rw_exclude, (size_t)ntiles, cudaMemcpyDeviceToHost, stream()));
+        AB_CUDA(cudaStreamSynchronize(stream()));
+    }
+    if (any_bad) {
+        DevBuf<uint32_t> dpb; DevBuf<uint8_t> dbt;
+        AB_TRY(dpb.alloc(256)); AB_TRY(dbt.alloc((size_t)ntiles));
+        for (int p = npat; p < 256; ++p) pbad[p] = pbad[npat - 1];
+        AB_CUDA(cudaMemcpyAsync(dpb.p, pbad.data(), 256 * sizeof(uint32_t), cudaMemcpyHostToDevice, stream()));
+        rowwin_tmask_kernel<<<(unsigned)ntiles, 256, 0, stream()>>>(c->rowcode, c->m, dpb.p, dbt.p);
+        AB_LAUNCH_CHECK();
+        std::vector<uint8_t> hbt((size_t)ntiles);
+        AB_CUDA(cudaMemcpyAsync(hbt.data(), dbt.p, (size_t)ntiles, cudaMemcpyDeviceToHost, stream()));
+        AB_CUDA(cudaStreamSynchronize(stream()));
+        for (int tI = 0; tI < ntiles; ++tI) hex[tI] |= hbt[tI];
+    }
+    for (int tI = 0; tI < ntiles; ++tI) any_excl = any_excl || hex[tI];
     auto smem_for = [&](int g, int nb) { return (size_t)nb * (margins + g * RW_R) * 8 + (size_t)nb * g * RW_R + ment.size() * 16 + 1024; };
-    // ---- how the chains are cut: G tiles per position, and either equal segments handed out round-robin (all chains of a
+    // ---- how the chains are cut: G tiles per position, and either equal z-segments handed out round-robin (all chains of a
     // z-range run together, so the margins a position shares with its neighbours are L2 hits) or, when the operand is about
     // L2-sized anyway, a balanced partition of the (chain, z) order into one contiguous run per SM.  Costs are in rows per CTA;
     // the penalties for narrower positions are measured (512^3: G = 4 / 2 / 1 -> 0.440 / 0.445 / 0.61 ms).
     const int grid = sm_count();
     const bool fits_l2 = (double)c->n * 8.0 <= 160e6;
+    const long long Zc = (c->m + M - 1) / M;                       // chain length (planes)
     int G = 0, bestL = 0, balanced = 0;
     double bestc = 1e300;
     const int gopt = (int)opt("spmv_zmarch_g", 0.0), lopt = (int)opt("spmv_zmarch_len", 0.0), bopt = (int)opt("spmv_zmarch_balanced", -1.0);
     for (int g = 4; g >= 1; g >>= 1) {
-        if (Q.S % g || smem_for(g, 4) > ZM_SMEM_MAX) continue;
+        const long long TRg = (long long)g * RW_R;
+        if (smem_for(g, 4) > ZM_SMEM_MAX) continue;
+        if (any_excl && M % TRg) continue;
         if (gopt > 0 && g != gopt) continue;
         if (gopt <= 0 && g == 1 && G) continue;                    // single tiles only when nothing wider applies
         const double pen = g == 4 ? 1.0 : (g == 2 ? 1.04 : 1.35);
-        const long long Spg = Q.S / g, nsg = (Q.ntiles + g - 1) / g, Zcg = (nsg + Spg - 1) / Spg;
-        const double rows = (double)g * RW_R;
-        for (int nseg = 1; nseg <= Zcg && nseg <= 256; ++nseg) {
-            const int Ls = (int)((Zcg + nseg - 1) / nseg);
-            if (nseg > 1 && (Zcg + nseg - 2) / (nseg - 1) == Ls) continue;      // same length as the previous candidate
-            if (lopt > 0 && Ls != lopt && nseg < Zcg) continue;
-            const long long nit = Spg * ((Zcg + Ls - 1) / Ls);
+        const long long Spg = (M + TRg - 1) / TRg;                 // chains per plane
+        const double rows = (double)M / (double)Spg;               // average rows per position
+        for (int nseg = 1; nseg <= Zc && nseg <= 256; ++nseg) {
+            const int Ls = (int)((Zc + nseg - 1) / nseg);
+            if (nseg > 1 && (Zc + nseg - 2) / (nseg - 1) == Ls) continue;      // same length as the previous candidate
+            if (lopt > 0 && Ls != lopt && nseg < Zc) continue;
+            const long long nit = Spg * ((Zc + Ls - 1) / Ls);
             if (nit > 16000) break;
             const long long rounds = (nit + grid - 1) / grid;
             const double cost = ((double)rounds * (Ls + 2) + 0.25 * (double)nit * (Ls + 2) / grid) * rows * pen / 1.25;
             if (bopt != 1 && cost < bestc) { bestc = cost; G = g; bestL = Ls; balanced = 0; }
         }
         if (bopt != 0) {
-            const double per = (double)(Spg * Zcg) / grid;
+            const double per = (double)(Spg * Zc) / grid;
             const double cost = (per + 3.0) * rows * pen * (fits_l2 ? 1.0 : 1.12);
             if (bopt == 1 ? (cost < bestc || !balanced) : cost < 0.95 * bestc) { bestc = cost; G = g; bestL = 0; balanced = 1; }
         }
@@ -1870,22 +1937,23 @@ static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<Mar
     int NB = smem_for(G, 8) <= ZM_SMEM_MAX ? 8 : 4;
     const int nbopt = (int)opt("spmv_zmarch_nb", 0.0);
     if (nbopt == 4) NB = 4;
+    const long long TR = (long long)G * RW_R;
+    const long long Sp = (M + TR - 1) / TR;
     ZMarchPlan Z;
     memset(&Z, 0, sizeof(Z));
-    Z.G = G; Z.S = Q.S / G; Z.lo = Q.lo; Z.len = margins + G * RW_R; Z.center = Q.center; Z.dom = -1;
+    Z.G = G; Z.M = M; Z.lo = (int)loc; Z.len = margins + G * RW_R; Z.center = (int)(0 - loc); Z.dom = -1;
     Z.nb = NB;
     Z.chunk = (int)opt("spmv_zmarch_chunk", 4096.0) & ~15;
     if (Z.chunk < 512) Z.chunk = 512;
     Z.tma = opt("spmv_zmarch_tma", 1.0) != 0.0 ? 1 : 0;
-    const int ntiles = Q.ntiles;
-    Z.nsuper = (ntiles + G - 1) / G;
-    // dominant pattern in the kernel parameters only in the shape {plane -1 @centre, plane 0 ..., plane +1 @centre}
-    if (Q.dom >= 0 && Q.dk >= 3 && Q.dplane[0] == -1 && Q.dsoff[0] == Q.center && Q.dplane[Q.dk - 1] == 1 && Q.dsoff[Q.dk - 1] == Q.center) {
-        bool mid0 = true;
-        for (int k = 1; k + 1 < Q.dk; ++k) mid0 = mid0 && Q.dplane[k] == 0;
-        if (mid0) {
-            Z.dom = Q.dom; Z.dk = Q.dk;
-            for (int k = 0; k < Q.dk; ++k) { Z.dsoff[k] = Q.dsoff[k]; Z.dval[k] = Q.dval[k]; }
+    // dominant pattern in the kernel parameters only in the shape {plane -1, plane 0 ..., plane +1}
+    if (W.dom >= 0 && W.dk >= 3 && W.dk <= 7) {
+        const int dst = (int)(pinfo[W.dom] & 0xffffu);
+        bool shape = ment[dst].plane == -1 && ment[dst + W.dk - 1].plane == 1;
+        for (int k = 1; k + 1 < W.dk; ++k) shape = shape && ment[dst + k].plane == 0;
+        if (shape) {
+            Z.dom = W.dom; Z.dk = W.dk;
+            for (int k = 0; k < W.dk; ++k) { Z.dsoff[k] = ment[dst + k].soff; Z.dval[k] = ment[dst + k].v; }
         }
     }
     // ---- per-pattern masks: which entries of the dominant pattern a row pattern keeps (same plane, offset and value bits,
@@ -1894,7 +1962,6 @@ static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<Mar
     if (Z.dom >= 0) {
         const int dst = (int)(pinfo[Z.dom] & 0xffffu);
         for (int p = 0; p < npat; ++p) {
-            if (!pat_ok[p]) continue;
             const int st = (int)(pinfo[p] & 0xffffu), len = (int)(pinfo[p] >> 16);
             unsigned mask = 0;
             int k = 0;
@@ -1902,7 +1969,7 @@ static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<Mar
                 const MarchEnt &a = ment[dst + e], &b = ment[st + k];
                 if (a.plane == b.plane && a.soff == b.soff && memcmp(&a.v, &b.v, sizeof(double)) == 0) { mask |= 1u << e; ++k; }
             }
-            if (k == len && Z.dk <= 7) pmask[p] = (uint8_t)mask;
+            if (k == len && !pbad[p]) pmask[p] = (uint8_t)mask;
         }
     }
     if (!c->zm_mask) AB_TRY(dev_alloc((void**)&c->zm_mask, 256));
@@ -1917,56 +1984,73 @@ static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<Mar
         rowmask_kernel<<<(unsigned)(nblk < cap ? nblk : cap), 256, 0, stream()>>>(c->rowcode, c->m, c->zm_mask, c->zm_rowmask);
         AB_LAUNCH_CHECK();
     }
+    dev_free(c->zm_ent); c->zm_ent = nullptr;
+    AB_TRY(dev_alloc(&c->zm_ent, ment.size() * sizeof(MarchEnt)));
+    AB_CUDA(cudaMemcpyAsync(c->zm_ent, ment.data(), ment.size() * sizeof(MarchEnt), cudaMemcpyHostToDevice, stream()));
     AB_CUDA(cudaStreamSynchronize(stream()));
-    // ---- chain positions that only touch the three marching intervals
-    const int ns = Z.nsuper, Sp = Z.S;
-    std::vector<uint8_t> pure((size_t)ns);
+    // ---- chain positions: (strip s of the plane, plane z) -> rows [s * TR + z * M, + min(TR, M - s * TR)) clipped at m
+    auto pos_row = [&](long long sI, long long z) { return sI * TR + z * M; };
+    auto pos_rows = [&](long long sI, long long z) {
+        const long long r0 = pos_row(sI, z);
+        long long w = std::min<long long>(TR, M - sI * TR);
+        if (r0 + w > c->m) w = c->m - r0;
+        return w;                                                   // <= 0: the position does not exist
+    };
+    auto pos_ok = [&](long long sI, long long z) {
+        const long long r0 = pos_row(sI, z), w = pos_rows(sI, z);
+        if (w <= 0) return false;
+        if (any_excl)                                               // strips coincide with tiles here (M % TR == 0)
+            for (long long tt = r0 / RW_R; tt <= (r0 + w - 1) / RW_R; ++tt) if (hex[(size_t)tt]) return false;
+        return true;
+    };
+    std::vector<uint32_t> first;
+    std::vector<int32_t> count, rowsv, cta_first;
     std::vector<uint8_t> covered((size_t)ntiles, 0);
-    for (int u = 0; u < ns; ++u) {
-        bool ok = true;
-        for (int i = 0; i < G && u * G + i < ntiles; ++i) ok = ok && (hmask[(size_t)u * G + i] & ~marchmask) == 0;
-        pure[u] = ok;
-    }
-    const int Zc = (ns + Sp - 1) / Sp;                 // chain length
-    std::vector<int32_t> first, count, cta_first;
-    auto cover = [&](int start, int run) {
-        for (int q = 0; q < run; ++q)
-            for (int i = 0; i < G; ++i) { const long long tt = ((long long)start + (long long)q * Sp) * G + i; if (tt < ntiles) covered[tt] = 1; }
+    auto cover = [&](long long sI, long long z0, int run) {
+        if (!any_excl) return;
+        for (int q = 0; q < run; ++q) {
+            const long long r0 = pos_row(sI, z0 + q), w = pos_rows(sI, z0 + q);
+            for (long long tt = r0 / RW_R; tt <= (r0 + w - 1) / RW_R; ++tt) covered[(size_t)tt] = 1;
+        }
+    };
+    auto emit = [&](long long sI, long long z0, int run) {
+        first.push_back((uint32_t)pos_row(sI, z0)); count.push_back(run);
+        rowsv.push_back((int32_t)std::min<long long>(TR, M - sI * TR));
+        cover(sI, z0, run);
     };
     if (!balanced) {
-        for (int z0 = 0; z0 < Zc; z0 += bestL)
-            for (int tI = 0; tI < Sp; ++tI) {
-                int run = 0, start = 0;
-                for (int z = z0; z < Zc && z < z0 + bestL; ++z) {
-                    const long long u = (long long)z * Sp + tI;
-                    const bool ok = u < ns && pure[u];
-                    if (ok) { if (run == 0) start = (int)u; ++run; }
-                    if ((!ok || z + 1 == Zc || z + 1 == z0 + bestL) && run) { first.push_back(start); count.push_back(run); cover(start, run); run = 0; }
+        for (long long z0 = 0; z0 < Zc; z0 += bestL)
+            for (long long sI = 0; sI < Sp; ++sI) {
+                int run = 0; long long start = 0;
+                for (long long z = z0; z < Zc && z < z0 + bestL; ++z) {
+                    const bool ok = pos_ok(sI, z);
+                    if (ok) { if (run == 0) start = z; ++run; }
+                    if ((!ok || z + 1 == Zc || z + 1 == z0 + bestL) && run) { emit(sI, start, run); run = 0; }
                 }
             }
     } else {
-        // runs of consecutive pure positions in (chain, z) order, cut into `nc` shares of equal length
-        std::vector<int32_t> rs, rl;
-        long long W = 0;
-        for (int tI = 0; tI < Sp; ++tI) {
-            int run = 0, start = 0;
-            for (int z = 0; z < Zc; ++z) {
-                const long long u = (long long)z * Sp + tI;
-                const bool ok = u < ns && pure[u];
-                if (ok) { if (run == 0) start = (int)u; ++run; }
-                if ((!ok || z + 1 == Zc) && run) { rs.push_back(start); rl.push_back(run); W += run; cover(start, run); run = 0; }
+        // runs of consecutive positions in (strip, z) order, cut into `nc` shares of equal length
+        struct Run { long long sI, z0; int len; };
+        std::vector<Run> runs;
+        long long Wtot = 0;
+        for (long long sI = 0; sI < Sp; ++sI) {
+            int run = 0; long long start = 0;
+            for (long long z = 0; z < Zc; ++z) {
+                const bool ok = pos_ok(sI, z);
+                if (ok) { if (run == 0) start = z; ++run; }
+                if ((!ok || z + 1 == Zc) && run) { runs.push_back({sI, start, run}); Wtot += run; run = 0; }
             }
         }
-        const long long nc = W < grid ? W : grid;
-        size_t ri = 0; int used = 0;                       // position inside run ri
+        const long long nc = Wtot < grid ? Wtot : grid;
+        size_t ri = 0; int used = 0;
         for (long long b = 0; b < nc; ++b) {
             cta_first.push_back((int32_t)first.size());
-            long long want = (b + 1) * W / nc - b * W / nc;
-            while (want > 0 && ri < rs.size()) {
-                const int take = (int)std::min<long long>(want, rl[ri] - used);
-                first.push_back(rs[ri] + used * Sp); count.push_back(take);
+            long long want = (b + 1) * Wtot / nc - b * Wtot / nc;
+            while (want > 0 && ri < runs.size()) {
+                const int take = (int)std::min<long long>(want, runs[ri].len - used);
+                emit(runs[ri].sI, runs[ri].z0 + used, take);
                 used += take; want -= take;
-                if (used == rl[ri]) { ++ri; used = 0; }
+                if (used == runs[ri].len) { ++ri; used = 0; }
             }
         }
         cta_first.push_back((int32_t)first.size());
@@ -1974,7 +2058,7 @@ static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<Mar
     const int nitems = (int)first.size();
     if (nitems == 0 || nitems > 16000) return AB_OK;
     std::vector<int32_t> rest;
-    for (int tI = 0; tI < ntiles; ++tI) if (!covered[tI]) rest.push_back(tI);
+    if (any_excl) for (int tI = 0; tI < ntiles; ++tI) if (!covered[tI]) rest.push_back(tI);
     dev_free(c->zm_items); c->zm_items = nullptr;
     dev_free(c->zm_rest); c->zm_rest = nullptr;
     dev_free(c->zm_cta_first); c->zm_cta_first = nullptr;
@@ -1984,9 +2068,10 @@ static int csr_build_zmarch(Csr* c, const RowMarchPlan& Q, const std::vector<Mar
         AB_CUDA(cudaMemcpyAsync(c->zm_cta_first, cta_first.data(), cta_first.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
         c->zm_ncta = (int)cta_first.size() - 1;
     }
-    AB_TRY(dev_alloc((void**)&c->zm_items, (size_t)2 * nitems * sizeof(int32_t)));
+    AB_TRY(dev_alloc((void**)&c->zm_items, (size_t)3 * nitems * sizeof(int32_t)));
     AB_CUDA(cudaMemcpyAsync(c->zm_items, first.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
     AB_CUDA(cudaMemcpyAsync(c->zm_items + nitems, count.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
+    AB_CUDA(cudaMemcpyAsync(c->zm_items + 2 * (size_t)nitems, rowsv.data(), (size_t)nitems * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
     if (!rest.empty()) {
         AB_TRY(dev_alloc((void**)&c->zm_rest, rest.size() * sizeof(int32_t)));
         AB_CUDA(cudaMemcpyAsync(c->zm_rest, rest.data(), rest.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream()));
@@ -2160,9 +2245,9 @@ static int launch_zmarch(const Csr* c, const double* x, double* y, const double*
             smem_set = ZM_SMEM_MAX;                                                                                           \
         }                                                                                                                     \
         launch_pdl(kern, dim3(grid), dim3(ZM_THREADS), smem, P, (KK) > 0 ? c->zm_rowmask : c->rowcode, c->rowcode,            \
-                   (const int4*)c->rm_ent, c->npat_ent, c->pat_info, x, (long long)c->n, y, (unsigned)c->m, c->zm_items,      \
-                   c->zm_items + nitems, nitems, c->zm_cta_first, dotvec, dot_in_window, partials, ticket, dot_result,        \
-                   done_flag);                                                                                                \
+                   (const int4*)c->zm_ent, c->npat_ent, c->pat_info, x, (long long)c->n, y, (unsigned)c->m,                   \
+                   (const uint32_t*)c->zm_items, c->zm_items + nitems, c->zm_items + 2 * (size_t)nitems, nitems,              \
+                   c->zm_cta_first, dotvec, dot_in_window, partials, ticket, dot_result, done_flag);                          \
     } while (0)
 #define AB_ZMG(KK, CC) do { if (P.G == 4) AB_ZM(4, KK, CC); else if (P.G == 2) AB_ZM(2, KK, CC); else AB_ZM(1, KK, CC); } while (0)
     if (fast && P.dk == 7 && ck == 3) AB_ZMG(7, 3);
@@ -2315,10 +2400,9 @@ static int launch_spmv_impl(const Csr* c, const double* vals, const double* x, d
             AB_TRY(csr_ensure_code(const_cast<Csr*>(c), vals));
             if (c->ncode > 0 && c->npat < 0) AB_TRY(csr_ensure_rowpat(const_cast<Csr*>(c)));
         }
-        if (rowwin_ready(c, vals, x) && !tile_list && !accumulate && c->rm_ok == 1 && c->rm_plan && (!dotvec || partials) &&
-            opt("spmv_rowmarch", 1.0) != 0.0) {
+        if (rowwin_ready(c, vals, x) && !tile_list && !accumulate && (!dotvec || partials) && opt("spmv_rowmarch", 1.0) != 0.0) {
             if (zmarch_ready(c) && c->zm_nrest == 0) return launch_zmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag);
-            if (c->rm_nrest == 0) return launch_rowmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag);
+            if (c->rm_ok == 1 && c->rm_plan && c->rm_nrest == 0) return launch_rowmarch(c, x, y, dotvec, dot_result, partials, ticket, done_flag);
         }
         if (rowwin_ready(c, vals, x) && (!tile_list || list_rows == RW_R))
             return launch_rowwin(c, x, y, dotvec, dot_result, partials, ticket, done_flag, tile_list, nlist, accumulate, hwp);
@@ -2373,7 +2457,7 @@ extern "C" int ab_csr_get_info(int64_t h, const char* key, double* value) {
     else if (!strcmp(key, "rowwin")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0) ? c->rw_ok : -1;
     else if (!strcmp(key, "rowmarch")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0 && c->rw_ok == 1) ? c->rm_ok : -1;
     else if (!strcmp(key, "rowmarch_items")) *value = c->rm_nitems;
-    else if (!strcmp(key, "zmarch")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0 && c->rw_ok == 1 && c->rm_ok == 1) ? c->zm_ok : -1;
+    else if (!strcmp(key, "zmarch")) *value = (c->code_version == c->values_version && c->ncode > 0 && c->npat > 0 && c->rw_ok == 1) ? c->zm_ok : -1;
     else if (!strcmp(key, "zmarch_items")) *value = c->zm_nitems;
     else if (!strcmp(key, "zmarch_balanced")) *value = c->zm_cta_first ? 1 : 0;
     else if (!strcmp(key, "zmarch_g")) *value = c->zm_plan ? reinterpret_cast<const ab::ZMarchPlan*>(c->zm_plan)->G : 0;

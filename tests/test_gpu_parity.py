@@ -685,9 +685,10 @@ def test_pattern_code_spmv_is_lossless(pkg):
             for k in keys:
                 pkg.check(pkg.lib.ab_set_option(k, 1.0))
 
-    # 67: tiles straddle planes, odd sizes; 64, 96, 128: n^2 is a multiple of the 1024-row tile -> marching kernels
-    # (z-register form with 4 / 1 / 4 tiles per chain position and 1 / 9 / 4 chains)
-    for n in (48, 67, 64, 96, 128):
+    # 67: tiles straddle planes, odd sizes (x-window kernel); 64, 96, 128: n^2 is a multiple of the 1024-row tile ->
+    # both marching kernels; 48, 100: n^2 is only a multiple of 16 -> the z-register kernel with the exact plane stride
+    # (strips of the plane that do not coincide with tiles; the last strip is narrower)
+    for n in (48, 67, 64, 96, 128, 100):
         N = n ** 3
         h = C.c_int64(0)
         pkg.check(pkg.lib.ab_poisson3d_csr(n, n, n, 0, N, C.byref(h)))
@@ -708,7 +709,7 @@ def test_pattern_code_spmv_is_lossless(pkg):
             return u
 
         ys = {name: with_form(a, b, c, d, e, g, spmv) for name, a, b, c, d, e, g in forms}
-        if n in (64, 96, 128):
+        if n in (48, 64, 96, 100, 128):
             zi = C.c_double(0)
             pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"zmarch", C.byref(zi)))
             assert zi.value == 1.0, "the z-register marching kernel should apply to this grid"
