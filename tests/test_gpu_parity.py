@@ -661,6 +661,45 @@ def test_c3_cg_solve_converges_128cubed(pkg):
     assert torch.equal(u, u2)
 
 
+@pytest.mark.parametrize("n", [150, 120])
+def test_solver_spmv_forms_on_unaligned_grids(pkg, n):
+    """Grids whose plane stride n^2 is no multiple of the 1024-row tile (150^2 = 22500: not even of 16; 120^2 = 14400 =
+    16 * 900): every SpMV form the solver can take — whichever kernel the form falls back to on this grid — reproduces the
+    plain int32 kernel bit for bit.  (A marching ring with a stride rounded to the tile size once gave wrong products
+    exactly here.)"""
+    import torch
+
+    keys = (b"spmv_rowpat", b"spmv_code", b"spmv_off8", b"spmv_rowwin", b"spmv_rowmarch", b"spmv_zmarch")
+    forms = (("zmarch", 1, 1, 1, 1, 1, 1), ("rowmarch", 1, 1, 1, 1, 1, 0), ("rowwin", 1, 1, 1, 1, 0, 0), ("rowpat", 1, 1, 1, 0, 0, 0),
+             ("code", 0, 1, 1, 0, 0, 0), ("off8", 0, 0, 1, 0, 0, 0), ("plain", 0, 0, 0, 0, 0, 0))
+    N = n ** 3
+    h = C.c_int64(0)
+    pkg.check(pkg.lib.ab_poisson3d_csr(n, n, n, 0, N, C.byref(h)))
+    A = pkg.SparseTensor.from_handle(h.value)
+    gen = torch.Generator(device="cuda").manual_seed(233)
+    x = torch.randn(N, dtype=torch.float64, device="cuda", generator=gen)
+    ys = {}
+    try:
+        for name, *vals in forms:
+            for k, v in zip(keys, vals):
+                pkg.check(pkg.lib.ab_set_option(k, float(v)))
+            y = torch.empty_like(x)
+            pkg.check(pkg.lib.ab_spmv_solver_form(A.handle(), x.data_ptr(), y.data_ptr()))
+            ys[name] = y
+    finally:
+        for k in keys:
+            pkg.check(pkg.lib.ab_set_option(k, 1.0))
+    for name, y in ys.items():
+        assert torch.equal(y, ys["plain"]), (n, name)
+    S = A.to_scipy()
+    dinv = 1.0 / np.sqrt(S.diagonal())
+    y0 = dinv * (S @ (dinv * x.cpu().numpy()))
+    assert np.max(np.abs(ys["plain"].cpu().numpy() - y0)) <= 1e-13 * np.max(np.abs(y0))
+    zi = C.c_double(0)
+    pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"zmarch", C.byref(zi)))
+    assert zi.value == (1.0 if n == 120 else 0.0)
+
+
 def test_pattern_code_spmv_is_lossless(pkg):
     """The solver's compressed SpMV forms — row patterns (1 byte per row), pattern codes (1 byte per
     entry naming an {offset, value} pair), offset dictionary — must reproduce the plain int32 kernel
