@@ -391,6 +391,86 @@ dense_lu_kernel(double* __restrict__ A, double* __restrict__ x, int d, int* __re
     }
 }
 
+// ---- the same elimination over the whole GPU for DENSE_LU_MAX < n <= "dense_lu_max" (default 8192) -------------
+// Two launches per column: one CTA finds the pivot of column k, swaps rows k / pivot (and the right-hand side) and
+// publishes 1 / pivot; then one warp per remaining row subtracts its multiple of row k (row-major: coalesced).  O(n^3)
+// flops and n^3 / 3 * 16 bytes of traffic — about a second at n = 8192: a LAST RESORT for the legacy direct-solver
+// strings when both Krylov methods have failed (the reference's SparseLU never fails on a regular matrix), not a
+// substitute for a sparse factorisation.
+__global__ void __launch_bounds__(1024)
+dense_lu_pivot_kernel(double* __restrict__ A, double* __restrict__ x, int d, int k, double* __restrict__ pinv, int* __restrict__ info) {
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_piv;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (*info) return;
+    double best = -1.0; int bi = k;
+    for (int r = k + t; r < d; r += 1024) { double v = fabs(A[(size_t)r * d + k]); if (v > best) { best = v; bi = r; } }
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { s_val[w] = best; s_idx[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+        best = s_val[lane]; bi = s_idx[lane];
+        for (int o = 16; o > 0; o >>= 1) {
+            double ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) s_piv = (best > 0.0 && isfinite(best)) ? bi : -1;
+    }
+    __syncthreads();
+    const int piv = s_piv;
+    if (piv < 0) { if (t == 0) *info = k + 1; return; }
+    if (piv != k) {
+        for (int cc = k + t; cc < d; cc += 1024) { double a = A[(size_t)k * d + cc]; A[(size_t)k * d + cc] = A[(size_t)piv * d + cc]; A[(size_t)piv * d + cc] = a; }
+        if (t == 0) { double a = x[k]; x[k] = x[piv]; x[piv] = a; }
+    }
+    __syncthreads();
+    if (t == 0) *pinv = 1.0 / A[(size_t)k * d + k];
+}
+__global__ void __launch_bounds__(256)
+dense_lu_update_kernel(double* __restrict__ A, double* __restrict__ x, int d, int k, const double* __restrict__ pinv, const int* __restrict__ info) {
+    if (*info) return;
+    const int lane = threadIdx.x & 31;
+    const int r = k + 1 + (int)(((size_t)blockIdx.x * 256 + threadIdx.x) >> 5);
+    if (r >= d) return;
+    const double f = A[(size_t)r * d + k] * *pinv;
+    if (f != 0.0) {
+        const double* __restrict__ rk = A + (size_t)k * d;
+        double* __restrict__ rr = A + (size_t)r * d;
+        for (int cc = k + 1 + lane; cc < d; cc += 32) rr[cc] = fma(-f, rk[cc], rr[cc]);
+        if (lane == 0) x[r] = fma(-f, x[k], x[r]);
+    }
+}
+// x = U^-1 x, one CTA (U = the upper triangle left in A)
+__global__ void __launch_bounds__(1024)
+dense_backsub_kernel(const double* __restrict__ A, double* __restrict__ x, int d) {
+    __shared__ double s_val[32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    for (int k = d - 1; k >= 0; --k) {
+        double acc = 0.0;
+        for (int cc = k + 1 + t; cc < d; cc += 1024) acc += A[(size_t)k * d + cc] * x[cc];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_val[w] = acc;
+        __syncthreads();
+        if (t == 0) {
+            double sum = 0.0;
+            for (int i = 0; i < 32; ++i) sum += s_val[i];
+            x[k] = (x[k] - sum) / A[(size_t)k * d + k];
+        }
+        __syncthreads();
+    }
+}
+
+static int dense_lu_limit() {
+    int lim = (int)opt("dense_lu_max", 8192.0);
+    if (lim < DENSE_LU_MAX) lim = DENSE_LU_MAX;
+    if (lim > 32768) lim = 32768;
+    return lim;
+}
+
 static int dense_lu_solve(Csr* c, const double* b, double* x) {
     const int d = (int)c->m;
     DevBuf<double> A; DevBuf<int> info;
@@ -400,8 +480,24 @@ static int dense_lu_solve(Csr* c, const double* b, double* x) {
     csr_to_dense_kernel<<<(d + 255) / 256, 256, 0, stream()>>>(c->rowptr, c->colind, c->values, d, A.p);
     AB_LAUNCH_CHECK();
     if (x != b) AB_CUDA(cudaMemcpyAsync(x, b, (size_t)d * sizeof(double), cudaMemcpyDeviceToDevice, stream()));
-    dense_lu_kernel<<<1, 1024, 0, stream()>>>(A.p, x, d, info.p);
-    AB_LAUNCH_CHECK();
+    if (d <= DENSE_LU_MAX) {
+        dense_lu_kernel<<<1, 1024, 0, stream()>>>(A.p, x, d, info.p);
+        AB_LAUNCH_CHECK();
+    } else {
+        DevBuf<double> pinv;
+        AB_TRY(pinv.alloc(1));
+        for (int k = 0; k < d; ++k) {
+            dense_lu_pivot_kernel<<<1, 1024, 0, stream()>>>(A.p, x, d, k, pinv.p, info.p);
+            AB_LAUNCH_CHECK();
+            const int rows = d - k - 1;
+            if (rows > 0) {
+                dense_lu_update_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream()>>>(A.p, x, d, k, pinv.p, info.p);
+                AB_LAUNCH_CHECK();
+            }
+        }
+        dense_backsub_kernel<<<1, 1024, 0, stream()>>>(A.p, x, d);
+        AB_LAUNCH_CHECK();
+    }
     int h = 0;
     AB_CUDA(cudaMemcpyAsync(&h, info.p, sizeof(int), cudaMemcpyDeviceToHost, stream()));
     AB_CUDA(cudaStreamSynchronize(stream()));
@@ -539,7 +635,7 @@ static int solve_dev_impl(Csr* c, Method meth, const double* b, double* x, doubl
         if (relres) *relres = tr;
         if (isfinite(tr) && tr <= tol * 10) return AB_OK;
     }
-    if (meth == M_GENERAL && c->m <= DENSE_LU_MAX) {
+    if (meth == M_GENERAL && c->m <= dense_lu_limit()) {
         double tr2 = 0;
         AB_TRY(dense_lu_solve(c, b, x));
         AB_TRY(true_relres(c, b, x, &tr2));

@@ -8,7 +8,7 @@ from dataclasses import dataclass, field
 @dataclass
 class OptionsSparse:
     auto_reorder: bool = True   # options.jl:12 — find() returns row-major sorted triplets
-    solver: str = "SparseLU"    # options.jl:11 — mapped: LLT/LDLT -> CG; SparseLU/SparseQR/auto -> CG first when the matrix is bitwise symmetric with a positive diagonal, else BiCGSTAB (+ dense LU for n <= 2048)
+    solver: str = "SparseLU"    # options.jl:11 — mapped: LLT/LDLT -> CG; SparseLU/SparseQR/auto -> CG first when the matrix is bitwise symmetric with a positive diagonal, else BiCGSTAB (+ dense partial-pivot LU on the device as the last resort for n <= 8192)
     tol: float = 1e-12          # new: relative residual target of the iterative solvers
     maxiter: int = 0            # new: 0 = library default (10 n + 100, capped)
 

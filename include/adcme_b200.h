@@ -148,8 +148,10 @@ int ab_spmm_grad_dense(int64_t h, const double* dY, int64_t k, double* dX);
  *       positive diagonal (one cached check per set of values — the FEM / stencil systems
  *       this path exists for; the adjoint then needs no transpose), BiCGSTAB otherwise or
  *       when CG breaks down / stalls, and a one-CTA dense partial-pivot LU when BiCGSTAB
- *       fails too and n <= 2048 (a direct solver never fails on a regular matrix).
- * Both Krylov solvers are Jacobi-preconditioned: the supported matrix class above 2048
+ *       fails too and n <= 2048, the same elimination spread over the whole GPU for n <= "dense_lu_max"
+ *       (option, default 8192, at most 32768; O(n^3): about a second at 8192 — a last resort, a direct
+ *       solver never fails on a regular matrix).
+ * Both Krylov solvers are Jacobi-preconditioned: the supported matrix class above "dense_lu_max"
  * unknowns is "Jacobi-Krylov converges" (SPD, diagonally dominant, mildly unsymmetric);
  * strongly indefinite / saddle-point systems of that size return AB_ENOCONV / AB_EBREAKDOWN
  * where the reference's SparseLU would succeed.  tol <= 0 / maxit <= 0 pick the options

@@ -10,6 +10,7 @@ import ctypes as C
 import numpy as np
 import pytest
 import scipy.sparse as sp
+import scipy.sparse.linalg as spla
 
 pytestmark = pytest.mark.gpu
 
@@ -427,6 +428,38 @@ def test_solve_random_nonsymmetric_like_reference_test(pkg, orc):
     b = rng.uniform(size=10)
     u = pkg.backslash(pkg.SparseTensor(ii, jj, vv, 10, 10), b, "SparseLU")
     assert np.linalg.norm(u - np.linalg.solve(S.toarray(), b)) / np.linalg.norm(u) <= 1e-9
+
+
+def test_solve_indefinite_saddle_point_beyond_2048_uses_the_wide_dense_fallback(pkg):
+    """A saddle-point system [[K, B'], [B, 0]] with 3000 unknowns: zero diagonal block, indefinite, unsymmetric after the
+    perturbation — with the iteration budget cut to 5 no Jacobi-Krylov method gets anywhere, the reference's SparseLU
+    would not care.  The legacy strings must cope too: above the one-CTA dense LU (n <= 2048) the same partial-pivot
+    elimination runs over the whole GPU (n <= "dense_lu_max", default 8192).  Explicit "BiCGSTAB" still reports the
+    failure instead of a wrong answer."""
+    rng = np.random.default_rng(233)
+    n1, n2 = 2000, 1000
+    K = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n1, n1)) + 0.01 * sp.random(n1, n1, 0.001, random_state=1)
+    B = sp.random(n2, n1, 0.004, random_state=2) + sp.eye(n2, n1)
+    S = sp.bmat([[K, B.T], [B, None]]).tocoo()
+    d = n1 + n2
+    ii, jj, vv = S.row + 1, S.col + 1, S.data
+    b = rng.uniform(size=d)
+    A = pkg.SparseTensor(ii, jj, vv, d, d)
+    u0 = spla.spsolve(S.tocsc(), b)
+    pkg.check(pkg.lib.ab_set_option(b"maxit", 5.0))
+    try:
+        u = pkg.backslash(A, b, "SparseLU")
+        assert np.linalg.norm(S @ u - b) / np.linalg.norm(b) <= TOL_SOLVE
+        assert np.linalg.norm(u - u0) / np.linalg.norm(u0) <= 1e-8
+        with pytest.raises(pkg.ADCMEError):
+            pkg.backslash(A, b, "BiCGSTAB")
+        # and the cliff itself moved, it did not vanish: above "dense_lu_max" the failure is reported
+        pkg.check(pkg.lib.ab_set_option(b"dense_lu_max", 2048.0))
+        with pytest.raises(pkg.ADCMEError):
+            pkg.backslash(A, b, "SparseLU")
+    finally:
+        pkg.check(pkg.lib.ab_set_option(b"dense_lu_max", 8192.0))
+        pkg.check(pkg.lib.ab_set_option(b"maxit", 0.0))
 
 
 def test_solve_gradients_parity_and_fd(pkg, orc):
