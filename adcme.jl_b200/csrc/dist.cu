@@ -1695,7 +1695,8 @@ int ab_dist_solve(int64_t dh, const char* method, const double* f, double* u, do
     int meth = DM_AUTO;
     AB_TRY(parse_dist_method(method, &meth));
     if (tol <= 0) tol = opt("tol", 1e-10);   // Hypre tolerance in the reference: 1e-10 (MPITensor.h:66,91)
-    if (maxit <= 0) maxit = (int)opt("maxit", 100000);
+    if (maxit <= 0) maxit = (int)opt("maxit", 0.0);       // an option set back to 0 means "default" here too
+    if (maxit <= 0) maxit = 100000;
     return dist_solve_common(dh, meth, f, u, tol, maxit, iters, relres);
 }
 
@@ -1762,7 +1763,8 @@ int ab_dist_solve_grad(int64_t dh, const double* grad_u_, const double* u_, doub
     if (!d) return AB_EHANDLE;
     if (d->nloc && (!grad_u_ || (grad_vals_ && !u_))) return fail(AB_EINVAL, "null vector");
     if (tol <= 0) tol = opt("tol", 1e-10);
-    if (maxit <= 0) maxit = (int)opt("maxit", 100000);
+    if (maxit <= 0) maxit = (int)opt("maxit", 0.0);       // an option set back to 0 means "default" here too
+    if (maxit <= 0) maxit = 100000;
     DevBuf<double> xbuf;
     bool sym = false;
     {
