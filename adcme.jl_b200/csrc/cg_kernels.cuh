@@ -219,7 +219,7 @@ cgs_init_kernel(const double* __restrict__ b, const double* __restrict__ sinv, d
 static __global__ void __launch_bounds__(EW_THREADS)
 cgs_update_kernel(const double* __restrict__ p, const double* __restrict__ Ap, double* __restrict__ x,
                   double* __restrict__ r, size_t n, int parity, SolveScal* s, double* partials, uint32_t* ticket,
-                  int raw, int defer_x) {
+                  int raw, int defer_x, ArExch ex) {
     __shared__ double sh[32];
     abd::pdl_launch_dependents();
     abd::pdl_wait();
@@ -278,7 +278,12 @@ cgs_update_kernel(const double* __restrict__ p, const double* __restrict__ Ap, d
     mine[1] = mine[0];
     abd::grid_reduce<EW_THREADS, 2>(mine, partials, ticket, sh, [=](const double(&t)[2]) {
         s->alpha = alpha;
-        if (raw) { s->red[0] = t[0]; s->red[1] = t[1]; s->bad = bad ? 1 : 0; }
+        if (raw && ex.blk) {
+            // the box-wide <r,r> right here (one thread of the last CTA): no all-reduce launch between K2 and K3
+            double g0 = t[0], g1 = t[1];
+            abd::ll_allreduce2(ex.blk, ex.peer_blk, ex.world, ex.me, ex.seq, g0, g1);
+            cg_update_fin(s, parity, g0, g1, bad);
+        } else if (raw) { s->red[0] = t[0]; s->red[1] = t[1]; s->bad = bad ? 1 : 0; }
         else cg_update_fin(s, parity, t[0], t[1], bad);
     });
 }

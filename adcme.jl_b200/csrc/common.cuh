@@ -300,6 +300,17 @@ struct HaloWait {
     P2PBlock* const* peer_blk; // [world] (nullptr: no push)
     int              me;
     uint32_t         red_seq;
+    // exchange != 0: the last CTA does the WHOLE all-reduce (tagged words to every peer, poll, rank-order sum) and leaves
+    // the box-wide sums in dot_result — no all-reduce launch follows the SpMV
+    P2PBlock*        my_blk;
+    int              exchange;
+};
+// the same for a vector kernel with a fused inner product (cgs_update_kernel): blk == nullptr: no exchange
+struct ArExch {
+    P2PBlock*        blk = nullptr;
+    P2PBlock* const* peer_blk = nullptr;
+    int              world = 1, me = 0;
+    uint32_t         seq = 0;
 };
 bool spmv_supports_halo_wait(const Csr* c, const double* vals);
 int  launch_spmv_halo(const Csr* c, const double* vals, const double* x, double* y, const double* dotvec,
@@ -467,6 +478,42 @@ __device__ __forceinline__ void p2p_push2(ab::P2PBlock* const* peer_blk, int wor
     }
     __threadfence_system();
     for (int p = 0; p < world; ++p) st_release_sys(&peer_blk[p]->red_flag[par][me], seq);
+}
+// ONE thread: box-wide sums of (v0, v1) by the flag-in-payload exchange (P2PBlock::ll) — four tagged 8-byte words to every
+// rank's slot for `me` (own included), then the eight slots of this rank polled and added in rank order: same bits on
+// every rank.  Called from the last CTA of the kernel that produced the partial sums, so no all-reduce launch follows.
+__device__ __forceinline__ void ll_allreduce2(ab::P2PBlock* blk, ab::P2PBlock* const* peer_blk, int world, int me, uint32_t seq,
+                                              double& v0, double& v1) {
+    const int par = seq & 1u;
+    const unsigned long long b0 = (unsigned long long)__double_as_longlong(v0), b1 = (unsigned long long)__double_as_longlong(v1);
+    const unsigned long long tag = (unsigned long long)seq << 32;
+    for (int p = 0; p < world; ++p) {
+        unsigned long long* dst = &peer_blk[p]->ll[par][me][0];
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 0), "l"(tag | (b0 & 0xffffffffull)) : "memory");
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(tag | (b0 >> 32)) : "memory");
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 2), "l"(tag | (b1 & 0xffffffffull)) : "memory");
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + 3), "l"(tag | (b1 >> 32)) : "memory");
+    }
+    double s0 = 0.0, s1 = 0.0;
+    const long long t0 = clock64();
+    for (int p = 0; p < world; ++p) {
+        const unsigned long long* src = &blk->ll[par][p][0];
+        unsigned long long w[4];
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(w[i]) : "l"(src + i) : "memory");
+                ok = ok && (uint32_t)(w[i] >> 32) == seq;
+            }
+            if (ok) break;
+            if (clock64() - t0 > (1ll << AB_WAIT_CLOCKS_LOG2)) { atomicExch(&blk->err, 1u); break; }
+        }
+        s0 += __longlong_as_double((long long)((w[1] << 32) | (w[0] & 0xffffffffull)));
+        s1 += __longlong_as_double((long long)((w[3] << 32) | (w[2] & 0xffffffffull)));
+    }
+    v0 = s0;
+    v1 = s1;
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

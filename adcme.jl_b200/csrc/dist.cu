@@ -648,9 +648,11 @@ static int allreduce2_fin(DistCsr* d, SolveScal* s, int which, int parity, doubl
 // push_seq != 0: the SpMV's last CTA pushes the fused dots into the peers' all-reduce slots under that
 // sequence number (only honoured on the one-launch path; *pushed tells the caller whether it happened)
 static int dist_spmv_dev(DistCsr* d, const double* vals, double* y, const double* dotvec, double* dots, const int* done,
-                         uint32_t push_seq = 0, bool* pushed = nullptr, bool halo_pushed_already = false) {
+                         uint32_t push_seq = 0, bool* pushed = nullptr, bool halo_pushed_already = false,
+                         uint32_t exch_seq = 0, bool* exchanged = nullptr) {
     Csr* c = d->loc;
     if (pushed) *pushed = false;
+    if (exchanged) *exchanged = false;
     AB_TRY(halo_begin(d, halo_pushed_already));
     const bool split = g_world > 1 && d->p2p && d->tiles_int && d->n_bnd > 0;
     if (!split) {
@@ -665,6 +667,10 @@ static int dist_spmv_dev(DistCsr* d, const double* vals, double* y, const double
             if (push_seq && dotvec) {
                 hm.peer_blk = d->d_peer_blk; hm.me = g_rank; hm.red_seq = push_seq;
                 if (pushed) *pushed = true;
+            } else if (exch_seq && dotvec) {
+                // the boundary-tile kernel's last CTA performs the whole <p,Ap> all-reduce
+                hm.peer_blk = d->d_peer_blk; hm.me = g_rank; hm.red_seq = exch_seq; hm.my_blk = d->blk; hm.exchange = 1;
+                if (exchanged) *exchanged = true;
             }
             return launch_spmv_march_halo(c, vals, d->xext, y, dotvec, dots, c->partials, c->ticket, done, hm);
         }
@@ -809,6 +815,8 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
     const bool push_opt = opt("dist_fused_push", 0.0) != 0.0;
     bool halo_pushed = false;     // the previous iteration's K3'' already pushed the halos of the coming SpMV
     // K3 that pushes the halos of the next SpMV while it sweeps (default path; needs contiguous send runs)
+    // all-reduces performed by the last CTA of the kernel that produced the partial sums (boundary-tile SpMV, K2)
+    const bool epi = raw && scaled && d->p2p && defer_x && opt("dist_epilogue_reduce", 1.0) != 0.0 && opt("dist_ll", 1.0) != 0.0;
     bool k3_halo = raw && scaled && d->p2p && d->next > 0 && opt("dist_k3_halo", 1.0) != 0.0;
     if (k3_halo) { AB_TRY(dist_check_send_ranges(d)); k3_halo = d->sr_ok == 1; }
     while (it < maxit) {
@@ -821,8 +829,10 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
             // 2994 — with eight ranks the 1184 CTAs of K2'/K3' all polling the same eight flag words slow the
             // arrival of the remote stores more than the two saved launches return.  Default: on for <= 2 ranks.
             const bool fuse = raw && scaled && defer_x && d->p2p && fuse_opt;
-            bool pushed = false;
-            AB_TRY(dist_spmv_dev(d, vals, Ap, p, s->dots, &s->done, fuse ? d->red_seq + 1 : 0, &pushed, halo_pushed));
+            bool pushed = false, exchanged = false;
+            AB_TRY(dist_spmv_dev(d, vals, Ap, p, s->dots, &s->done, fuse ? d->red_seq + 1 : 0, &pushed, halo_pushed,
+                                 (!fuse && epi) ? d->red_seq + 1 : 0, &exchanged));
+            if (exchanged) ++d->red_seq;
             halo_pushed = false;
             if (pushed) {
                 const uint32_t seq1 = ++d->red_seq, seq2 = ++d->red_seq;
@@ -842,11 +852,13 @@ static int dist_run_cg(DistCsr* d, const double* b, double* x, double tol, int m
                 AB_LAUNCH_CHECK();
                 continue;
             }
-            if (raw) AB_TRY(allreduce2(d, s->dots));
-            if (scaled) launch_pdl(cgs_update_kernel, dim3(g), dim3(EW_THREADS), 0, p, Ap, x, r, n, parity, s, c->partials, c->ticket, raw, defer_x);
+            if (raw && !exchanged) AB_TRY(allreduce2(d, s->dots));
+            ArExch ex;
+            if (epi) { ex.blk = d->blk; ex.peer_blk = d->d_peer_blk; ex.world = g_world; ex.me = g_rank; ex.seq = ++d->red_seq; }
+            if (scaled) launch_pdl(cgs_update_kernel, dim3(g), dim3(EW_THREADS), 0, p, Ap, x, r, n, parity, s, c->partials, c->ticket, raw, defer_x, ex);
             else cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, raw);
             AB_LAUNCH_CHECK();
-            if (raw) AB_TRY(allreduce2_fin(d, s, 1, parity, tol));
+            if (raw && !epi) AB_TRY(allreduce2_fin(d, s, 1, parity, tol));
             if (scaled && k3_halo) {
                 ++d->halo_seq;
                 launch_pdl(cgs_direction_halo_kernel, dim3(g), dim3(EW_THREADS), 0, r, p, x, n, parity, it, defer_x, s, d->sr, d->d_peer_x,

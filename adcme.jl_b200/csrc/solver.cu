@@ -169,7 +169,7 @@ static int run_cg_scaled(Csr* c, const double* b, double* x, double tol, int max
         for (int k = 0; k < chunk; ++k, ++it) {
             const int parity = it & 1;
             AB_TRY(launch_spmv_vals(c, c->svalues, p, Ap, p, s->dots, c->partials, c->ticket, &s->done, nullptr, 0, 0));
-            launch_pdl(cgs_update_kernel, dim3(g), dim3(EW_THREADS), 0, p, Ap, x, r, n, parity, s, c->partials, c->ticket, 0, defer_x);
+            launch_pdl(cgs_update_kernel, dim3(g), dim3(EW_THREADS), 0, p, Ap, x, r, n, parity, s, c->partials, c->ticket, 0, defer_x, ArExch{});
             AB_LAUNCH_CHECK();
             if (replace_due(tol, it + 1)) {
                 double* Ax = work_vec(c, 5);
@@ -886,7 +886,7 @@ extern "C" int ab_bench_cg_kernels(int64_t h, int reps, double* ms_spmv_dot, dou
         AB_CUDA(cudaEventRecord(ev[4 * it + 0], stream()));
         AB_TRY(launch_spmv_vals(c, scaled ? c->svalues : c->values, p, Ap, p, s->dots, c->partials, c->ticket, &s->done, nullptr, 0, 0));
         AB_CUDA(cudaEventRecord(ev[4 * it + 1], stream()));
-        if (scaled) cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, 0, defer_x);
+        if (scaled) cgs_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, x, r, n, parity, s, c->partials, c->ticket, 0, defer_x, ArExch{});
         else cg_update_kernel<<<g, EW_THREADS, 0, stream()>>>(p, Ap, c->dinv, x, r, n, parity, s, c->partials, c->ticket, 0);
         AB_LAUNCH_CHECK();
         AB_CUDA(cudaEventRecord(ev[4 * it + 2], stream()));

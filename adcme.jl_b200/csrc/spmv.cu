@@ -1033,14 +1033,21 @@ spmv_rowwin_kernel(const __grid_constant__ RowWinPlan P, const uint8_t* __restri
             mine[0] = abd::block_sum<RW_T>(dot, s_red);
             mine[1] = abd::block_sum<RW_T>(dot2, s_red);
             P2PBlock* const* pb = hw.peer_blk;
-            const int world = hw.world, me = hw.me;
+            P2PBlock* myb = hw.my_blk;
+            const int world = hw.world, me = hw.me, exchange = hw.exchange;
             const uint32_t rseq = hw.red_seq;
             abd::grid_reduce<RW_T, 2>(mine, partials, ticket, s_red, [=](const double(&tot)[2]) {
-                const double t0 = accumulate ? dot_result[0] + tot[0] : tot[0];
-                const double t1 = accumulate ? dot_result[1] + tot[1] : tot[1];
-                dot_result[0] = t0;
-                dot_result[1] = t1;
-                abd::p2p_push2(pb, world, me, rseq, t0, t1);
+                double t0 = accumulate ? dot_result[0] + tot[0] : tot[0];
+                double t1 = accumulate ? dot_result[1] + tot[1] : tot[1];
+                if (exchange) {
+                    abd::ll_allreduce2(myb, pb, world, me, rseq, t0, t1);      // box-wide sums: no all-reduce launch follows
+                    dot_result[0] = t0;
+                    dot_result[1] = t1;
+                } else {
+                    dot_result[0] = t0;
+                    dot_result[1] = t1;
+                    abd::p2p_push2(pb, world, me, rseq, t0, t1);
+                }
             });
         }
         return;
