@@ -14,17 +14,21 @@
 // Data path (default, "dist_p2p" = 1): peer memory over NVLink, no NCCL call inside the iteration.
 //   * the direction vector (owned part + halo tail) and a small flag block live in cudaMalloc
 //     memory that every peer maps with CUDA IPC;
-//   * halo_push_kernel gathers the boundary values and STORES them straight into the consumers'
-//     halo tails (st.global on peer-mapped pointers), then the last CTA releases a sequence flag
-//     in each consumer's flag block;
-//   * interior tiles are multiplied while those stores fly; halo_wait_kernel acquires the flags;
-//     boundary tiles follow and add their share of the fused dot products;
-//   * the two inner products per iteration are all-reduced by p2p_allreduce2_kernel: every rank
-//     stores its two partial sums into all peers' slots, spins on the eight sequence flags, and
-//     adds the slots in rank order — bit-identical on every rank, ~one NVLink round trip.
-//   Ordering: a rank cannot push halo k+1 before it has passed the <p,Ap> reduction of iteration
-//   k, which needs every peer's contribution, which a peer issues only after its SpMV k finished
-//   reading its halo — so one halo buffer suffices; reduction slots are double-buffered by parity.
+//   * the CG iteration on a stencil block is FOUR launches: (1) the marching SpMV over the chains of tiles that read
+//     no halo column; (2) the x-window SpMV over the remaining tiles (first / last plane of the slab): it acquires the
+//     peers' halo flags in-kernel, adds its share of the fused dots, and its LAST CTA performs the whole <p,Ap>
+//     all-reduce — four TAGGED 8-byte words (sequence number << 32 | one half of a double) stored into every peer's
+//     slot, the eight own slots polled and added in rank order (same bits on every rank; an aligned 8-byte store
+//     arrives whole, so no fence and no separate flag); (3) K2, whose last CTA does the same for <r,r> and applies
+//     the CG scalar logic; (4) K3, which also STORES the new p of the rows a peer needs straight into that peer's
+//     halo tail while its grid-stride sweep passes over them (send lists that are contiguous runs of rows) and whose
+//     last CTA publishes the halo sequence number;
+//   * other matrices / options: halo_push_kernel (gather + store + flag) as its own launch, interior tiles while the
+//     stores fly, halo_wait_kernel or the in-kernel acquire, boundary tiles; p2p_allreduce2_kernel (one 32-thread CTA)
+//     for the all-reduces (BiCGSTAB, true-residual vetting, set-up).
+//   Ordering: a rank's K3 of iteration k starts after its <r,r> all-reduce, which needs every peer's K2(k), which a
+//   peer issues only after its SpMV k finished reading its halo — so one halo buffer suffices; reduction slots are
+//   double-buffered by the parity of the sequence number.
 // Fallback ("dist_p2p" = 0 or IPC unavailable): pack -> grouped ncclSend/ncclRecv, ncclAllReduce.
 //
 // NCCL is dlopen()ed (libnccl.so.2 — the copy PyTorch already loaded when the host is Python);
