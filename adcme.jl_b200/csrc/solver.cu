@@ -17,7 +17,8 @@
 // CG iteration = 3 launches:   K1  Ap = A p, pAp            (spmv.cu)
 //                              K2  x += a p, r -= a Ap, rz' = <r, D^-1 r>, rr = <r,r>
 //                              K3  p = D^-1 r + b p
-// Algorithmic bytes / iteration: 12*nnz + 4*(N+1) + 13*8*N.
+// Algorithmic bytes / iteration: 12*nnz + 4*(N+1) + 13*8*N; the scaled form CG normally runs
+// (cg_kernels.cuh: S A S, x update deferred into K3) streams 10 vector passes plus the SpMV form's matrix bytes.
 #include "common.cuh"
 #include <string>
 #include <map>
@@ -149,7 +150,7 @@ int csr_ensure_scaled(Csr* c) {
     return AB_OK;
 }
 
-// scaled form (cg_kernels.cuh): 11 instead of 13 vector passes per iteration
+// scaled form (cg_kernels.cuh): 10 instead of 13 vector passes per iteration (x update riding in K3)
 static int run_cg_scaled(Csr* c, const double* b, double* x, double tol, int maxit, SolveScal* fin) {
     const size_t n = (size_t)c->m;
     AB_TRY(csr_ensure_work(c, 10));

@@ -44,6 +44,14 @@
 //    its pattern byte by byte, so the form is lossless or not used; summation order inside a row is
 //    the stored order, hence results are bit-identical to the other kernels.
 //
+//  * spmv_rowwin_kernel / spmv_rowmarch_kernel / spmv_zmarch_kernel — the row-pattern form with the x operands
+//    staged instead of gathered (see the comments at each kernel): x intervals per 1024-row tile streamed into
+//    shared memory by the TMA unit (rowwin); a ring of such windows marched along the chains of tiles one plane
+//    apart (rowmarch); and the form CG runs on a 3-D stencil — planes -M / +M carried in REGISTERS along the
+//    chain, one window of G tiles + margins per position through a ring of mbarrier-guarded slots fed by a
+//    producer warp, boundary rows as masked sub-patterns of the interior stencil (zmarch: 0.37 ms at 512^3 =
+//    0.94 of the measured HBM peak on the 17 bytes per row the form streams; rowpat: 0.75 ms).
+//
 //  * spmv_vector_kernel<L> — general fallback (long / irregular rows): L lanes per row straight
 //    from global memory, shuffle reduction.
 //
