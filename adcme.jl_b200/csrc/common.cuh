@@ -249,9 +249,10 @@ std::mutex& big_lock();
 // ---------------------------------------------------------------- primitives (assemble.cu)
 // exclusive prefix sum of uint32 (in -> out, may alias); total written to *d_total (device) if non-null
 int scan_exclusive_u32(const uint32_t* in, uint32_t* out, size_t n, uint32_t* d_total);
-// stable LSD radix sort of 64-bit keys (bits [0,nbits)) carrying a 32-bit payload
+// stable LSD radix sort of 64-bit keys by their bits [bit0, bit0 + nbits), carrying a 32-bit payload that the first pass
+// synthesises from the position (the payload on return is the input position of each element)
 int radix_sort_u64(uint64_t* keys, uint32_t* vals, uint64_t* keys_tmp, uint32_t* vals_tmp,
-                   size_t n, int nbits, uint64_t** keys_out, uint32_t** vals_out);
+                   size_t n, int nbits, uint64_t** keys_out, uint32_t** vals_out, int bit0 = 0);
 
 // ---------------------------------------------------------------- spmv.cu
 // y = A x.  When dotvec != nullptr the launch also produces dot_result[0] = <y, dotvec> and
