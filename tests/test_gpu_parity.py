@@ -733,6 +733,60 @@ def test_solver_spmv_forms_on_unaligned_grids(pkg, n):
     assert zi.value == (1.0 if n == 120 else 0.0)
 
 
+@pytest.mark.parametrize("n", [1040, 2048])
+def test_solver_spmv_forms_on_2d_grids_with_long_lines(pkg, n):
+    """2-D 5-point stencil with lines of >= 1024 points: the line length is the marching stride (1040 = 16 * 65: strips
+    that do not coincide with tiles; 2048: two tiles per line), the dominant pattern has five entries — the
+    spmv_zmarch_kernel<G, 5, 2> instantiation.  Every form against the plain int32 kernel, bit for bit."""
+    import torch
+
+    keys = (b"spmv_rowpat", b"spmv_code", b"spmv_off8", b"spmv_rowwin", b"spmv_rowmarch", b"spmv_zmarch")
+    forms = (("zmarch", 1, 1, 1, 1, 1, 1), ("rowmarch", 1, 1, 1, 1, 1, 0), ("rowwin", 1, 1, 1, 1, 0, 0), ("rowpat", 1, 1, 1, 0, 0, 0),
+             ("plain", 0, 0, 0, 0, 0, 0))
+    N = n * n
+    h = C.c_int64(0)
+    kappa = np.ones((n + 2, n + 2))
+    pkg.check(pkg.lib.ab_poisson2d_csr(n, kappa.ctypes.data, -1, C.byref(h)))
+    A = pkg.SparseTensor.from_handle(h.value)
+    gen = torch.Generator(device="cuda").manual_seed(233)
+    x = torch.randn(N, dtype=torch.float64, device="cuda", generator=gen)
+    ys = {}
+    try:
+        for name, *vals in forms:
+            for k, v in zip(keys, vals):
+                pkg.check(pkg.lib.ab_set_option(k, float(v)))
+            y = torch.empty_like(x)
+            pkg.check(pkg.lib.ab_spmv_solver_form(A.handle(), x.data_ptr(), y.data_ptr()))
+            ys[name] = y
+    finally:
+        for k in keys:
+            pkg.check(pkg.lib.ab_set_option(k, 1.0))
+    for name, y in ys.items():
+        assert torch.equal(y, ys["plain"]), (n, name)
+    S = A.to_scipy()
+    dinv = 1.0 / np.sqrt(S.diagonal())
+    y0 = dinv * (S @ (dinv * x.cpu().numpy()))
+    assert np.max(np.abs(ys["plain"].cpu().numpy() - y0)) <= 1e-13 * np.max(np.abs(y0))
+    zi = C.c_double(0)
+    pkg.check(pkg.lib.ab_csr_get_info(A.handle(), b"zmarch", C.byref(zi)))
+    assert zi.value == 1.0
+    # and 30 CG iterations through it agree with the plain kernel's iterates to rounding (fused dots differ in order)
+    f = torch.rand(N, dtype=torch.float64, device="cuda", generator=gen)
+    rr = C.c_double(0)
+    us = {}
+    try:
+        for name, *vals in (forms[0], forms[-1]):
+            for k, v in zip(keys, vals):
+                pkg.check(pkg.lib.ab_set_option(k, float(v)))
+            u = torch.empty_like(f)
+            pkg.check(pkg.lib.ab_cg_fixed(A.handle(), f.data_ptr(), u.data_ptr(), 30, C.byref(rr)))
+            us[name] = u
+    finally:
+        for k in keys:
+            pkg.check(pkg.lib.ab_set_option(k, 1.0))
+    assert float((us["zmarch"] - us["plain"]).abs().max() / us["plain"].abs().max()) <= 1e-11
+
+
 def test_pattern_code_spmv_is_lossless(pkg):
     """The solver's compressed SpMV forms — row patterns (1 byte per row), pattern codes (1 byte per
     entry naming an {offset, value} pair), offset dictionary — must reproduce the plain int32 kernel
