@@ -62,7 +62,11 @@ int         ab_synchronize(void);
  *                             "spmv_zmarch_g" (tiles per chain position), "spmv_zmarch_len", "spmv_zmarch_balanced",
  *                             "spmv_zmarch_tma" (1: cp.async.bulk, 0: 16-byte cp.async), "spmv_variant"
  *   vector kernels            "ew_ctas_per_sm" (default 4), "cg_defer_x", "cg_scaled", "pdl" (programmatic dependent launch)
- *   distributed iteration     "dist_p2p", "dist_fused_wait", "dist_fused_reduce", "dist_fused_push", "dist_k3_halo"
+ *   distributed iteration     "dist_p2p", "dist_fused_wait", "dist_k3_halo" (K3 stores the next halos), "dist_ll" (all-reduce with
+ *                             the flag inside the payload), "dist_epilogue_reduce" (all-reduces in the last CTA of the
+ *                             producing kernel), "dist_fused_reduce", "dist_fused_push" (measured slower: off)
+ *   assembly                  "asm_rowsort" (row bits first, columns inside each row)
+ *   solver fallback           "dense_lu_max" (largest n the dense partial-pivot LU may take, default 8192)
  *   SpMM / SDDMM              "spmm_group", "sddmm_entry"
  *   device                    "l2_fetch_granularity" (cudaLimitMaxL2FetchGranularity; applied at once) */
 int         ab_set_option(const char* key, double value);
