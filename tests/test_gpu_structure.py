@@ -135,6 +135,25 @@ def test_sparse_indexing_matches_oracle(pkg, orc, m, n, T, ni, nj):
     assert np.array_equal(r[2], orc.sparse_indexing_grad(g, I, J, ii1, jj1, ii, jj))
 
 
+def test_sparse_indexing_grad_with_repeated_indices_is_ordered(pkg, orc):
+    """Repeated entries in ii / jj make several output positions point at the same input triplet: their gradient
+    contributions are summed in ascending output order (the reference's sequential loop, SparseIndexing.h:66-83) by a
+    sort + fixed-order segment reduction — no floating-point atomics — so the result equals the oracle bit for bit and is
+    the same on every run."""
+    rng = np.random.default_rng(7)
+    m, n, T = 300, 400, 20000
+    ii1, jj1, vv1 = rand_coo(rng, m, n, T, dup_frac=0.2)
+    ii = rng.choice(np.arange(1, m + 1), 150, replace=True).astype(np.int64)      # repeats
+    jj = rng.choice(np.arange(1, n + 1), 120, replace=True).astype(np.int64)
+    I0, J0, V0 = orc.sparse_indexing(ii1, jj1, vv1, m, n, ii, jj)
+    g = rng.standard_normal(len(V0)) * 10.0 ** rng.integers(-8, 8, len(V0))       # wide range: the order of the sum matters
+    op = pkg.load_system_op("sparse_indexing")
+    r1 = op.grad(g, I0, J0, V0, ii1, jj1, vv1, m, n, ii, jj)[2]
+    r2 = op.grad(g, I0, J0, V0, ii1, jj1, vv1, m, n, ii, jj)[2]
+    assert np.array_equal(r1, r2)
+    assert np.array_equal(r1, orc.sparse_indexing_grad(g, I0, J0, ii1, jj1, ii, jj))
+
+
 def test_getindex_reference_tests(pkg, golden):
     B1 = sp.random(10, 10, 0.3, random_state=13, format="csr")         # test/sparse.jl:63-69
     B = pkg.SparseTensor(B1)
