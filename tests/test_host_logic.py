@@ -117,3 +117,18 @@ def test_newton_options_and_jacobian_reuse_decision(pkg):
     assert not op._same_indices(i, np.array([1, 2, 3])) and not op._same_indices(i, None)
     with pytest.raises(ValueError):
         pkg.newton_raphson(lambda th, u: (u, None), np.ones((2, 2)))  # "Initial guess must be a vector"
+
+
+def test_bench_affinity_helper_is_a_noop_without_a_gpu():
+    """bench.py pins its e2e host buffers next to the rank's GPU; without NVML / a GPU the context manager must do nothing
+    and must always restore the affinity it found."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    before = os.sched_getaffinity(0)
+    with bench.near_gpu_affinity(0):
+        inside = os.sched_getaffinity(0)
+        assert inside <= before and len(inside) > 0
+    assert os.sched_getaffinity(0) == before
