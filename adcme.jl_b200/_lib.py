@@ -109,6 +109,8 @@ SIGNATURES = {
     "ab_launch_count": (_i64, []),
     "ab_spmv_solver_form": (C.c_int, [_i64, _ptr, _ptr]),
     "ab_csr_get_info": (C.c_int, [_i64, _str, _ptr]),
+    "ab_test_zmarch_plan": (C.c_int, [_i64, _i64, C.c_int, _ptr, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ptr, _i64,
+                                      _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr]),
 }
 
 

@@ -65,6 +65,7 @@
 //
 // Algorithmic bytes per launch: 12*nnz + 4*(m+1) + 8*n + 8*m.
 #include "common.cuh"
+#include "zmarch_plan.h"
 #include <algorithm>
 #include <vector>
 
@@ -1912,48 +1913,18 @@ static int csr_build_zmarch(Csr* c, const RowWinPlan& W, const std::vector<CodeE
     }
     for (int tI = 0; tI < ntiles; ++tI) any_excl = any_excl || hex[tI];
     auto smem_for = [&](int g, int nb) { return (size_t)nb * (margins + g * RW_R) * 8 + (size_t)nb * g * RW_R + ment.size() * 16 + 1024; };
-    // ---- how the chains are cut: G tiles per position, and either equal z-segments handed out round-robin (all chains of a
-    // z-range run together, so the margins a position shares with its neighbours are L2 hits) or, when the operand is about
-    // L2-sized anyway, a balanced partition of the (chain, z) order into one contiguous run per SM.  Costs are in rows per CTA;
-    // the penalties for narrower positions are measured (512^3: G = 4 / 2 / 1 -> 0.440 / 0.445 / 0.61 ms).
+    // ---- how the chains are cut (zmarch_plan.h): G tiles per position, and either equal z-segments handed out round-robin
+    // (all chains of a z-range run together, so the margins a position shares with its neighbours are L2 hits) or, when the
+    // operand is about L2-sized anyway, a balanced partition of the (strip, z) order into one contiguous run per SM
     const int grid = sm_count();
-    const bool fits_l2 = (double)c->n * 8.0 <= 160e6;
-    const long long Zc = (c->m + M - 1) / M;                       // chain length (planes)
-    int G = 0, bestL = 0, balanced = 0;
-    double bestc = 1e300;
-    const int gopt = (int)opt("spmv_zmarch_g", 0.0), lopt = (int)opt("spmv_zmarch_len", 0.0), bopt = (int)opt("spmv_zmarch_balanced", -1.0);
-    for (int g = 4; g >= 1; g >>= 1) {
-        const long long TRg = (long long)g * RW_R;
-        if (smem_for(g, 4) > ZM_SMEM_MAX) continue;
-        if (any_excl && M % TRg) continue;
-        if (gopt > 0 && g != gopt) continue;
-        if (gopt <= 0 && g == 1 && G) continue;                    // single tiles only when nothing wider applies
-        const double pen = g == 4 ? 1.0 : (g == 2 ? 1.04 : 1.35);
-        const long long Spg = (M + TRg - 1) / TRg;                 // chains per plane
-        const double rows = (double)M / (double)Spg;               // average rows per position
-        for (int nseg = 1; nseg <= Zc && nseg <= 256; ++nseg) {
-            const int Ls = (int)((Zc + nseg - 1) / nseg);
-            if (nseg > 1 && (Zc + nseg - 2) / (nseg - 1) == Ls) continue;      // same length as the previous candidate
-            if (lopt > 0 && Ls != lopt && nseg < Zc) continue;
-            const long long nit = Spg * ((Zc + Ls - 1) / Ls);
-            if (nit > 16000) break;
-            const long long rounds = (nit + grid - 1) / grid;
-            const double cost = ((double)rounds * (Ls + 2) + 0.25 * (double)nit * (Ls + 2) / grid) * rows * pen / 1.25;
-            if (bopt != 1 && cost < bestc) { bestc = cost; G = g; bestL = Ls; balanced = 0; }
-        }
-        if (bopt != 0) {
-            const double per = (double)(Spg * Zc) / grid;
-            const double cost = (per + 3.0) * rows * pen * (fits_l2 ? 1.0 : 1.12);
-            if (bopt == 1 ? (cost < bestc || !balanced) : cost < 0.95 * bestc) { bestc = cost; G = g; bestL = 0; balanced = 1; }
-        }
-    }
+    const ZmCut cut = zm_choose_cut(M, (long long)c->m, grid, any_excl, (double)c->n * 8.0 <= 160e6,
+                                    [&](int g) { return smem_for(g, 4) <= ZM_SMEM_MAX; }, (int)opt("spmv_zmarch_g", 0.0),
+                                    (int)opt("spmv_zmarch_len", 0.0), (int)opt("spmv_zmarch_balanced", -1.0));
+    const int G = cut.G;
     if (!G) return AB_OK;
-    if (lopt > 0 && !balanced) bestL = lopt;
     int NB = smem_for(G, 8) <= ZM_SMEM_MAX ? 8 : 4;
     const int nbopt = (int)opt("spmv_zmarch_nb", 0.0);
     if (nbopt == 4) NB = 4;
-    const long long TR = (long long)G * RW_R;
-    const long long Sp = (M + TR - 1) / TR;
     ZMarchPlan Z;
     memset(&Z, 0, sizeof(Z));
     Z.G = G; Z.M = M; Z.lo = (int)loc; Z.len = margins + G * RW_R; Z.center = (int)(0 - loc); Z.dom = -1;
@@ -2003,77 +1974,13 @@ static int csr_build_zmarch(Csr* c, const RowWinPlan& W, const std::vector<CodeE
     AB_TRY(dev_alloc(&c->zm_ent, ment.size() * sizeof(MarchEnt)));
     AB_CUDA(cudaMemcpyAsync(c->zm_ent, ment.data(), ment.size() * sizeof(MarchEnt), cudaMemcpyHostToDevice, stream()));
     AB_CUDA(cudaStreamSynchronize(stream()));
-    // ---- chain positions: (strip s of the plane, plane z) -> rows [s * TR + z * M, + min(TR, M - s * TR)) clipped at m
-    auto pos_row = [&](long long sI, long long z) { return sI * TR + z * M; };
-    auto pos_rows = [&](long long sI, long long z) {
-        const long long r0 = pos_row(sI, z);
-        long long w = std::min<long long>(TR, M - sI * TR);
-        if (r0 + w > c->m) w = c->m - r0;
-        return w;                                                   // <= 0: the position does not exist
-    };
-    auto pos_ok = [&](long long sI, long long z) {
-        const long long r0 = pos_row(sI, z), w = pos_rows(sI, z);
-        if (w <= 0) return false;
-        if (any_excl)                                               // strips coincide with tiles here (M % TR == 0)
-            for (long long tt = r0 / RW_R; tt <= (r0 + w - 1) / RW_R; ++tt) if (hex[(size_t)tt]) return false;
-        return true;
-    };
-    std::vector<uint32_t> first;
-    std::vector<int32_t> count, rowsv, cta_first;
-    std::vector<uint8_t> covered((size_t)ntiles, 0);
-    auto cover = [&](long long sI, long long z0, int run) {
-        if (!any_excl) return;
-        for (int q = 0; q < run; ++q) {
-            const long long r0 = pos_row(sI, z0 + q), w = pos_rows(sI, z0 + q);
-            for (long long tt = r0 / RW_R; tt <= (r0 + w - 1) / RW_R; ++tt) covered[(size_t)tt] = 1;
-        }
-    };
-    auto emit = [&](long long sI, long long z0, int run) {
-        first.push_back((uint32_t)pos_row(sI, z0)); count.push_back(run);
-        rowsv.push_back((int32_t)std::min<long long>(TR, M - sI * TR));
-        cover(sI, z0, run);
-    };
-    if (!balanced) {
-        for (long long z0 = 0; z0 < Zc; z0 += bestL)
-            for (long long sI = 0; sI < Sp; ++sI) {
-                int run = 0; long long start = 0;
-                for (long long z = z0; z < Zc && z < z0 + bestL; ++z) {
-                    const bool ok = pos_ok(sI, z);
-                    if (ok) { if (run == 0) start = z; ++run; }
-                    if ((!ok || z + 1 == Zc || z + 1 == z0 + bestL) && run) { emit(sI, start, run); run = 0; }
-                }
-            }
-    } else {
-        // runs of consecutive positions in (strip, z) order, cut into `nc` shares of equal length
-        struct Run { long long sI, z0; int len; };
-        std::vector<Run> runs;
-        long long Wtot = 0;
-        for (long long sI = 0; sI < Sp; ++sI) {
-            int run = 0; long long start = 0;
-            for (long long z = 0; z < Zc; ++z) {
-                const bool ok = pos_ok(sI, z);
-                if (ok) { if (run == 0) start = z; ++run; }
-                if ((!ok || z + 1 == Zc) && run) { runs.push_back({sI, start, run}); Wtot += run; run = 0; }
-            }
-        }
-        const long long nc = Wtot < grid ? Wtot : grid;
-        size_t ri = 0; int used = 0;
-        for (long long b = 0; b < nc; ++b) {
-            cta_first.push_back((int32_t)first.size());
-            long long want = (b + 1) * Wtot / nc - b * Wtot / nc;
-            while (want > 0 && ri < runs.size()) {
-                const int take = (int)std::min<long long>(want, runs[ri].len - used);
-                emit(runs[ri].sI, runs[ri].z0 + used, take);
-                used += take; want -= take;
-                if (used == runs[ri].len) { ++ri; used = 0; }
-            }
-        }
-        cta_first.push_back((int32_t)first.size());
-    }
+    // ---- work items (zmarch_plan.h)
+    ZmItems items;
+    zm_make_items(M, (long long)c->m, cut, grid, any_excl ? hex : std::vector<uint8_t>(), &items);
+    const std::vector<uint32_t>& first = items.first;
+    const std::vector<int32_t>&count = items.count, &rowsv = items.rows, &cta_first = items.cta_first, &rest = items.rest;
     const int nitems = (int)first.size();
     if (nitems == 0 || nitems > 16000) return AB_OK;
-    std::vector<int32_t> rest;
-    if (any_excl) for (int tI = 0; tI < ntiles; ++tI) if (!covered[tI]) rest.push_back(tI);
     dev_free(c->zm_items); c->zm_items = nullptr;
     dev_free(c->zm_rest); c->zm_rest = nullptr;
     dev_free(c->zm_cta_first); c->zm_cta_first = nullptr;
@@ -2461,6 +2368,33 @@ int launch_spmv(const Csr* c, const double* x, double* y, const double* dotvec, 
 }
 
 }  // namespace ab
+
+extern "C" int ab_test_zmarch_plan(int64_t M, int64_t m, int grid, const uint8_t* excl, int64_t n_excl, int fits_g_max, int fits_l2,
+                                   int g_opt, int len_opt, int bal_opt, int* out3, int64_t cap, uint32_t* first, int32_t* count,
+                                   int32_t* rows, int32_t* cta_first, int32_t* rest, int64_t* n_items, int64_t* n_cta, int64_t* n_rest) {
+    if (M < 1 || m < 1 || grid < 1 || !out3 || !n_items || !n_cta || !n_rest) return ab::fail(AB_EINVAL, "bad argument");
+    std::vector<uint8_t> ex;
+    if (excl && n_excl > 0) ex.assign(excl, excl + n_excl);
+    if (!ex.empty() && (int64_t)ex.size() != (m + ab::ZM_TILE_ROWS - 1) / ab::ZM_TILE_ROWS) return ab::fail(AB_EINVAL, "excl needs one flag per 1024-row tile");
+    bool any = false;
+    for (uint8_t e : ex) any = any || e;
+    const ab::ZmCut cut = ab::zm_choose_cut(M, m, grid, any, fits_l2 != 0, [&](int g) { return g <= fits_g_max; }, g_opt, len_opt, bal_opt);
+    out3[0] = cut.G; out3[1] = cut.balanced; out3[2] = cut.seg_len;
+    *n_items = *n_cta = *n_rest = 0;
+    if (!cut.G) return AB_OK;
+    ab::ZmItems it;
+    ab::zm_make_items(M, m, cut, grid, ex, &it);
+    *n_items = (int64_t)it.first.size();
+    *n_cta = it.cta_first.empty() ? 0 : (int64_t)it.cta_first.size() - 1;
+    *n_rest = (int64_t)it.rest.size();
+    if (*n_items > cap || *n_rest > cap || (int64_t)it.cta_first.size() > cap) return ab::fail(AB_EINVAL, "cap too small");
+    if (first) std::copy(it.first.begin(), it.first.end(), first);
+    if (count) std::copy(it.count.begin(), it.count.end(), count);
+    if (rows) std::copy(it.rows.begin(), it.rows.end(), rows);
+    if (cta_first) std::copy(it.cta_first.begin(), it.cta_first.end(), cta_first);
+    if (rest) std::copy(it.rest.begin(), it.rest.end(), rest);
+    return AB_OK;
+}
 
 extern "C" int ab_csr_get_info(int64_t h, const char* key, double* value) {
     ab::Csr* c = ab::csr_get(h);

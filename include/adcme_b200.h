@@ -369,6 +369,16 @@ int ab_spmv_solver_form(int64_t h, const double* x, double* y);
  * "ncode" (pattern-code dictionary size of the solver values, 0 = none), "tile_rows",
  * "max_row_nnz", "scaled" (1 when CG runs on the symmetrically scaled copy) */
 int ab_csr_get_info(int64_t h, const char* key, double* value);
+/* test hook, HOST ONLY (no device needed): the work-item plan of the marching SpMV kernel for a matrix of m rows whose
+ * stencil planes are M rows apart, on a device with `grid` SMs — csrc/zmarch_plan.h.  excl: one flag per 1024-row tile
+ * that must stay out of every item (NULL: none).  fits_g_max: the widest position (tiles) the kernel can stage; fits_l2:
+ * the operand is about L2-sized.  g_opt / len_opt / bal_opt: overrides (0 / 0 / -1 = automatic).  Outputs: out3 = {G,
+ * balanced, segment length}, and up to `cap` items (first row, chain length, rows per position), the CTA offsets of the
+ * balanced mode (grid + 1 entries at most) and the uncovered tiles; counts in n_items / n_cta / n_rest.  AB_EINVAL when
+ * `cap` is too small. */
+int ab_test_zmarch_plan(int64_t M, int64_t m, int grid, const uint8_t* excl, int64_t n_excl, int fits_g_max, int fits_l2,
+                        int g_opt, int len_opt, int bal_opt, int* out3, int64_t cap, uint32_t* first, int32_t* count,
+                        int32_t* rows, int32_t* cta_first, int32_t* rest, int64_t* n_items, int64_t* n_cta, int64_t* n_rest);
 
 #ifdef __cplusplus
 }

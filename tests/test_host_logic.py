@@ -132,3 +132,90 @@ def test_bench_affinity_helper_is_a_noop_without_a_gpu():
         inside = os.sched_getaffinity(0)
         assert inside <= before and len(inside) > 0
     assert os.sched_getaffinity(0) == before
+
+
+def _zmarch_plan(pkg, M, m, grid, excl=None, fits_g_max=4, fits_l2=0, g_opt=0, len_opt=0, bal_opt=-1):
+    import ctypes as C
+
+    cap = 40000
+    out3 = (C.c_int * 3)()
+    first = np.zeros(cap, np.uint32); count = np.zeros(cap, np.int32); rows = np.zeros(cap, np.int32)
+    cta = np.zeros(cap, np.int32); rest = np.zeros(cap, np.int32)
+    ni, nc, nr = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    ex = None if excl is None else np.ascontiguousarray(excl, np.uint8)
+    pkg.check(pkg.lib.ab_test_zmarch_plan(M, m, grid, None if ex is None else ex.ctypes.data, 0 if ex is None else len(ex), fits_g_max,
+                                          fits_l2, g_opt, len_opt, bal_opt, out3, cap, first.ctypes.data, count.ctypes.data,
+                                          rows.ctypes.data, cta.ctypes.data, rest.ctypes.data, C.byref(ni), C.byref(nc), C.byref(nr)))
+    n = ni.value
+    return dict(G=out3[0], balanced=out3[1], seg=out3[2], first=first[:n].astype(np.int64), count=count[:n].astype(np.int64),
+                rows=rows[:n].astype(np.int64), cta=cta[:nc.value + 1] if nc.value else None, rest=rest[:nr.value])
+
+
+@pytest.mark.parametrize("M,planes,grid,kw", [
+    (512 * 512, 512, 148, {}),                          # the headline grid: G = 4, round-robin z-segments
+    (512 * 512, 64, 148, dict(fits_l2=1)),              # one rank's slab at N = 8: balanced partition
+    (400 * 400, 400, 148, {}),                          # plane stride not a multiple of the tile: narrower last strip
+    (100 * 100, 100, 148, {}),
+    (1040, 1040, 148, {}),                              # 2-D grid with long lines: one strip per line
+    (64 * 64, 64, 148, {}),
+    (512 * 512, 512, 148, dict(g_opt=2)),
+    (512 * 512, 64, 132, dict(bal_opt=1)),
+])
+def test_zmarch_plan_covers_every_row_exactly_once(pkg, M, planes, grid, kw):
+    """Host-side planning of the marching SpMV (csrc/zmarch_plan.h through the host-only hook): the work items are chains of
+    positions `M` rows apart; together they must cover every row of the matrix exactly once, no position wider than G tiles,
+    and a balanced partition hands every CTA the same number of positions (+-1)."""
+    m = M * planes
+    p = _zmarch_plan(pkg, M, m, grid, **kw)
+    assert p["G"] in (1, 2, 4) and len(p["first"]) > 0
+    TR = 1024 * p["G"]
+    seen = np.zeros(m + 1, np.int64)                    # difference array over rows
+    for f, c, r in zip(p["first"], p["count"], p["rows"]):
+        assert 1 <= r <= TR and c >= 1
+        assert (f % M) % TR == 0 and r == min(TR, M - f % M)            # a strip of the plane, full or the narrow last one
+        for q in range(c):
+            a = f + q * M
+            b = min(a + r, m)
+            assert a < m
+            seen[a] += 1; seen[b] -= 1
+    cover = np.cumsum(seen[:-1])
+    assert cover.min() == 1 and cover.max() == 1
+    assert len(p["rest"]) == 0
+    if p["balanced"]:
+        cta = p["cta"]
+        assert cta is not None and cta[0] == 0 and cta[-1] == len(p["first"]) and len(cta) - 1 <= grid
+        per = [int(p["count"][cta[b]:cta[b + 1]].sum()) for b in range(len(cta) - 1)]
+        assert max(per) - min(per) <= 1 and sum(per) == int(p["count"].sum())
+    else:
+        assert p["cta"] is None and p["seg"] >= 1 and p["count"].max() <= p["seg"]
+
+
+def test_zmarch_plan_with_excluded_tiles_leaves_them_to_the_rest_list(pkg):
+    """A distributed block: the tiles of the first and last plane read halo columns and are excluded; every other row is
+    covered exactly once, the excluded tiles (and nothing else) form the rest list, chains are cut around them."""
+    M, planes, grid = 512 * 512, 64, 148
+    m = M * planes
+    ntiles = m // 1024
+    excl = np.zeros(ntiles, np.uint8)
+    excl[: M // 1024] = 1
+    excl[-(M // 1024):] = 1
+    for kw in (dict(fits_l2=1), dict(bal_opt=0)):
+        p = _zmarch_plan(pkg, M, m, grid, excl=excl, **kw)
+        TR = 1024 * p["G"]
+        assert M % TR == 0                               # strips coincide with tiles when tiles are excluded
+        tiles = np.zeros(ntiles, np.int64)
+        for f, c, r in zip(p["first"], p["count"], p["rows"]):
+            for q in range(c):
+                a = f + q * M
+                tiles[a // 1024:(a + r) // 1024] += 1
+        assert np.array_equal(tiles, 1 - excl.astype(np.int64))
+        assert np.array_equal(np.sort(p["rest"]), np.nonzero(excl)[0])
+
+
+def test_zmarch_plan_needs_tile_aligned_strips_when_tiles_are_excluded(pkg):
+    M, planes = 400 * 400, 8                            # 160000 rows per plane: no multiple of 1024
+    m = M * planes
+    excl = np.zeros((m + 1023) // 1024, np.uint8)
+    excl[0] = 1
+    p = _zmarch_plan(pkg, M, m, 148, excl=excl)
+    assert p["G"] == 0 and len(p["first"]) == 0          # the kernel steps aside (x-window kernel takes the matrix)
