@@ -219,3 +219,28 @@ def test_zmarch_plan_needs_tile_aligned_strips_when_tiles_are_excluded(pkg):
     excl[0] = 1
     p = _zmarch_plan(pkg, M, m, 148, excl=excl)
     assert p["G"] == 0 and len(p["first"]) == 0          # the kernel steps aside (x-window kernel takes the matrix)
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """The driver launches `bench.py --impl reference` exactly like the GPU arm (torchrun for N > 1).  Rank 0 alone runs the CPU
+    port and prints ONE JSON line; the other rank exits 0 without output; the thread count is set explicitly (torchrun exports
+    OMP_NUM_THREADS=1 — the round-1 scaling run measured one core at N >= 2 because of it)."""
+    import json
+    import subprocess
+
+    port = 31000 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+           "--warmup", "0", "--grid", "48"]
+    out = subprocess.run(cmd, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["gpu_launches"] == 0
+    assert d["unit"] == "CG iterations/s" and d["higher_is_better"] is True and d["value"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["single_thread_value"] > 0
+    ncpu = len(os.sched_getaffinity(0))
+    assert cb["cores"] == ncpu or ncpu == 1, (cb, ncpu)              # every host thread, whatever torchrun put into the environment
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
